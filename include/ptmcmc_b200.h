@@ -1,0 +1,187 @@
+/* ptmcmc_b200.h -- C ABI of the B200-native chain-stepping engine ("ptg").
+ *
+ * This is the drop-in boundary for the hot path of JohnGBaker/ptmcmc:
+ *     parallel_tempering_chains::step      chain.cc:1393-1761
+ *       -> swap scheduling + swap tests    chain.cc:1410-1538   (+ pry_temps chain.cc:1809-1846)
+ *       -> MH_chain::step(prop)            chain.cc:966-1022
+ *            -> proposal_distribution_set::draw / gaussian_prop::draw / differential_evolution::draw
+ *                                           proposal_distribution.cc:99-129,489-591,744-801 ; .hh:119-129,194-218
+ *            -> state::enforce             states.cc:11-58,86-102,161-166
+ *            -> prior evaluate_log         probability_function.hh:59 ; .cc:49-81,156-166,281-304
+ *            -> likelihood evaluate_log    (device functor; bayesian.hh:553-581 is the host hook it replaces)
+ *            -> MH_chain::add_state        chain.cc:916-949
+ * batched over n_ladders independent temperature ladders resident on ONE GPU.
+ *
+ * The reference has no C ABI: its seams are C++ virtuals (chain.hh:34-142, proposal_distribution.hh:38-88,
+ * probability_function.hh:31-83).  Every entry point below cites the reference interface it stands in for;
+ * INTEGRATION.md shows the C++ facade (`gpu_parallel_tempering_chains : chain`) a maintainer adds on the
+ * reference side to bind these.
+ *
+ * Conventions: plain pointers and sizes only; all arrays are HOST memory unless a name ends in `_dev`;
+ * every call returns 0 on success or a negative PTG_E* code, with a message in ptg_last_error();
+ * no C++ exception crosses the boundary; one handle = one GPU = one host thread at a time.
+ * Chains are indexed  chain = ladder * n_rungs + rung  (rung 0 = coldest, beta = 1).
+ * There is NO CPU fallback: ptg_create fails if no CUDA device is usable.
+ */
+#ifndef PTMCMC_B200_H
+#define PTMCMC_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTG_ABI_VERSION 1
+#define PTG_MAX_DIM 128        /* thread-per-chain kernels cover dim<=16, the warp-per-chain kernel dim<=128 */
+#define PTG_MAX_PROPOSALS 16
+#define PTG_MAX_RUNGS 64
+
+/* error codes */
+#define PTG_OK 0
+#define PTG_EINVAL (-1)   /* bad argument / call order            */
+#define PTG_ECUDA (-2)    /* CUDA runtime error                   */
+#define PTG_ETAPE (-3)    /* injected tape exhausted              */
+#define PTG_ESTUCK (-4)   /* init could not draw a valid state (chain.cc:854-866) */
+#define PTG_ENOMEM (-5)
+
+/* boundary types: states.hh:35-38 */
+enum { PTG_BOUND_OPEN = 0, PTG_BOUND_LIMIT = 1, PTG_BOUND_REFLECT = 2, PTG_BOUND_WRAP = 3 };
+/* 1-D prior factor types: mixed_dist_product, probability_function.hh:151-155 */
+enum { PTG_PRIOR_UNIFORM = 1, PTG_PRIOR_GAUSSIAN = 2, PTG_PRIOR_POLAR = 3, PTG_PRIOR_COPOLAR = 4, PTG_PRIOR_LOG = 5 };
+/* device likelihood functors */
+enum {
+  PTG_LIKE_FLAT = 0,          /* log L = 0                                  (example.cc:22-72 "constant") */
+  PTG_LIKE_GAUSS_ISO = 1,     /* lnnormfac - r^2/twosigmasq                  (example.cc:116-143)          */
+  PTG_LIKE_SINES = 2,         /* sin^4 multimodal surface                    (sines.hh:22-54)              */
+  PTG_LIKE_POLY_CHI2 = 3,     /* chi^2 of polynomial model over data         (bayesian.hh:595-622, poly_example.cc:85-106) */
+  PTG_LIKE_SINUSOID_CHI2 = 4, /* chi^2 of sum of sinusoids over data         (same chi^2) */
+  PTG_LIKE_GAUSS_FULLCOV = 5  /* like0 - x^T Cinv x / 2                      (cython/exampleGaussian.py:103-109) */
+};
+/* proposal kinds (members of a proposal_distribution_set, proposal_distribution.cc:99-129) */
+enum { PTG_PROP_DE = 1, PTG_PROP_GAUSS = 2, PTG_PROP_PRIOR_DRAW = 3 };
+enum { PTG_SWAP_REFERENCE = 0, PTG_SWAP_EVEN_ODD = 1 };
+enum { PTG_RNG_PHILOX = 0, PTG_RNG_TAPE = 1 };
+/* history record level: 0 = x, lpost, llike per stored sample; 1 = + acceptance_ratio, invtemp, type
+ * (the full record of MH_chain::add_state, chain.cc:936-943) */
+enum { PTG_RECORD_BASIC = 0, PTG_RECORD_FULL = 1 };
+
+typedef struct ptg_handle ptg_handle;
+
+/* Stands in for the constructor arguments of parallel_tempering_chains (chain.cc:1163) and
+ * MH_chain (chain.cc:647), plus evolve_temps (chain.hh:302) and the RNG seeding of chain::chain() (chain.hh:58). */
+typedef struct ptg_config {
+  int32_t abi_version;      /* must be PTG_ABI_VERSION */
+  int32_t device;           /* CUDA device ordinal */
+  int32_t n_ladders;        /* independent ladders on this GPU */
+  int32_t n_rungs;          /* Ntemps; 1 = plain MH_chain */
+  int32_t dim;
+  int32_t save_every;       /* add_every_N */
+  int32_t hist_capacity;    /* history slots per chain (ring once exceeded) */
+  int32_t n_init;           /* Ninit: prior draws that seed each chain's history (ptmcmc.cc:86) */
+  int32_t swap_mode;        /* PTG_SWAP_* */
+  int32_t rng_mode;         /* PTG_RNG_* */
+  int32_t record_level;     /* PTG_RECORD_* */
+  int32_t trace_steps;      /* >0: keep a decision trace for this many PT steps (parity runs) */
+  double swap_rate;         /* pt_swap_rate */
+  double Tmax;              /* pt_Tmax: geometric ladder 1..Tmax (chain.cc:1181-1183) */
+  double dprior_min;        /* chain_dprior_min (minPrior, chain.cc:980) */
+  double evolve_rate;       /* pt_evolve_rate; 0 = fixed temperatures */
+  double evolve_lpost_cut;  /* pt_evolve_lpost_cut; <0 = off */
+  uint64_t seed;            /* Philox key */
+  int64_t ladder_offset;    /* global id of local ladder 0: makes results invariant to the GPU count */
+} ptg_config;
+
+/* one member of the proposal set; fields of differential_evolution (proposal_distribution.hh:361-414)
+ * and gaussian_prop (proposal_distribution.hh:145-227) */
+typedef struct ptg_proposal {
+  int32_t kind;             /* PTG_PROP_* */
+  int32_t reserved;
+  double share;             /* static share (normalised by the engine like reset_bins, proposal_distribution.cc:37-59) */
+  double hot_share;         /* share at beta -> 0 when Tpow > 0 */
+  /* PTG_PROP_DE */
+  double snooker, gamma_one_frac, b_small, ignore_frac, unlikely_alpha, reduce_gamma;
+  /* PTG_PROP_GAUSS */
+  double one_d_frac;
+  const double *sigmas;     /* [dim] */
+  const double *transform;  /* [dim*dim] row-major eigenvector matrix M (offset = M (z o sigma)), or NULL = identity */
+} ptg_proposal;
+
+const char *ptg_last_error(void);
+int ptg_abi_version(void);
+
+/* lifecycle ------------------------------------------------------------------------------------ */
+int ptg_create(const ptg_config *cfg, ptg_handle **out);
+int ptg_destroy(ptg_handle *h);
+
+/* model set-up (all before ptg_init_*) --------------------------------------------------------- */
+/* stateSpace::set_bound (states.hh) per dimension */
+int ptg_set_space(ptg_handle *h, const int32_t *lower_type, const int32_t *upper_type,
+                  const double *xmin, const double *xmax);
+/* uniform/gaussian/mixed_dist_product: per dimension (type, a, b): uniform/polar/copolar/log (xmin,xmax); gaussian (x0,sigma) */
+int ptg_set_prior(ptg_handle *h, const int32_t *type, const double *a, const double *b);
+/* device likelihood functor; replaces bayes_likelihood::register_evaluate_log (bayesian.hh:544-552).
+ *   GAUSS_ISO      params = [lnnormfac, twosigmasq, x0[dim]]
+ *   SINES          params = [height, step_scale, k[dim], min[dim], max[dim]]
+ *   POLY_CHI2      params = [like0]; data = [x[N], y[N], var[N]]  (n_data = N)
+ *   SINUSOID_CHI2  params = [like0]; data = [t[N], y[N], var[N]]; state = (A,f,phi) triples
+ *   GAUSS_FULLCOV  params = [like0]; data = Cinv[dim*dim] row-major (n_data = dim*dim) */
+int ptg_set_likelihood(ptg_handle *h, int32_t kind, const double *params, int32_t n_params,
+                       const double *data, int64_t n_data);
+/* proposal_distribution_set constructor (proposal_distribution.cc:61-93).  wrap_in_set=0 (n must be 1) uses the
+ * single proposal bare, as ptmcmc drivers do when they pass e.g. a differential_evolution directly to
+ * set_proposal (testMH.cpp:91-160): no selection draw, type() not multiplied by 10. */
+int ptg_set_proposals(ptg_handle *h, int32_t n, const ptg_proposal *props, double Tpow, int32_t wrap_in_set);
+/* explicit inverse temperatures instead of the geometric ladder; [n_ladders*n_rungs] or NULL */
+int ptg_set_betas(ptg_handle *h, const double *betas);
+
+/* random numbers --------------------------------------------------------------------------------- */
+int ptg_seed(ptg_handle *h, uint64_t seed);
+/* PTG_RNG_TAPE: injected draws.  Streams 0..n_chains-1 are the chains' own generators (chain.hh:45),
+ * streams n_chains..n_chains+n_ladders-1 the ladders' (parallel_tempering_chains is itself a chain).
+ * u_off/z_off have n_streams+1 entries; the tapes are copied to the device. */
+int ptg_inject_tapes(ptg_handle *h, const double *u, const int64_t *u_off, const double *z, const int64_t *z_off);
+
+/* initialisation: MH_chain::initialize (chain.cc:846-876) ------------------------------------------- */
+int ptg_init_from_prior(ptg_handle *h);
+/* seed each chain's history from caller-provided states x[n_chains][n_init][dim] (chain_init_file path) */
+int ptg_init_states(ptg_handle *h, const double *x);
+
+/* the hot path: n_steps iterations of parallel_tempering_chains::step for every ladder ------------------ */
+int ptg_step(ptg_handle *h, int64_t n_steps);
+int ptg_synchronize(ptg_handle *h);
+/* same, end-to-end with host buffers: steps, then copies the cold chains' newest `n_out` stored samples
+ * of every ladder to host memory x_out[n_ladders][n_out][dim], lpost_out/llike_out[n_ladders][n_out] */
+int ptg_step_host(ptg_handle *h, int64_t n_steps, int32_t n_out, double *x_out, double *lpost_out, double *llike_out);
+
+/* read-back: chain::getState/getLogPost/getLogLike/invTemp (chain.hh:86-124) ---------------------------- */
+int ptg_get_current(ptg_handle *h, double *x, double *lpost, double *llike, double *beta);
+int ptg_get_counters(ptg_handle *h, int64_t *nhist, int64_t *nsize, int64_t *ntries, int64_t *naccept,
+                     int32_t *last_type, double *map_lpost);
+/* raw-indexed history of one chain, elements [first, first+count); entries older than the ring are an error.
+ * acc/beta/type may be NULL (and must be unless record_level = FULL) */
+int ptg_get_history(ptg_handle *h, int32_t ladder, int32_t rung, int64_t first, int64_t count,
+                    double *x, double *lpost, double *llike, double *acc, double *beta, int32_t *type);
+/* swap_count / swap_accept_count (chain.hh:244-245) [n_ladders][n_rungs-1]; directions/ups/downs/instances
+ * (chain.hh:238-242) [n_ladders][n_rungs]; any pointer may be NULL */
+int ptg_get_swap_stats(ptg_handle *h, int64_t *swap_count, int64_t *swap_accept, int32_t *directions,
+                       int32_t *ups, int32_t *downs, int32_t *instances);
+/* decision trace (parity harness): for PT step s in [first, first+count) and every chain,
+ * lhr[s][chain] = log Hastings ratio tested, code[s][chain] = see PTG_TRACE_* */
+int ptg_get_trace(ptg_handle *h, int64_t first, int64_t count, double *lhr, int32_t *code);
+#define PTG_TRACE_TYPE_MASK 0xff     /* proposal type() as recorded by the set (i + 10*member type) */
+#define PTG_TRACE_ACCEPT 0x100
+#define PTG_TRACE_INVALID 0x200      /* proposed state failed boundary enforcement */
+#define PTG_TRACE_SWAPPED 0x400      /* rung took part in a swap trial this step (no MH update) */
+#define PTG_TRACE_NOLIKE 0x800       /* prior gate skipped the likelihood (chain.cc:980-987) */
+/* total history appends (= tempered chain-steps, the BASELINE metric) since init */
+int ptg_get_total_steps(ptg_handle *h, int64_t *total);
+/* device pointer + stream for zero-copy consumers (torch / NCCL gather of cold samples) */
+int ptg_get_device_views(ptg_handle *h, void **hist_x_dev, void **hist_meta_dev, void **cur_x_dev, void **stream);
+
+/* checkpoint / restore of the complete engine state (restart.hh semantics; format in DESIGN.md) */
+int ptg_checkpoint(ptg_handle *h, const char *path);
+int ptg_restore(ptg_handle *h, const char *path);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTMCMC_B200_H */

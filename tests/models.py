@@ -1,0 +1,222 @@
+"""Model / proposal specifications shared by the parity tests.
+
+One `Spec` describes a hot-path configuration and can (a) configure any engine behind the C ABI
+(the CUDA engine or the CPU oracle) and (b) produce the command line of oracle/_ref/ref_trace, the driver that runs
+the unmodified reference on the same configuration.
+"""
+import os
+import numpy as np
+from ptmcmc_b200 import _capi as K
+
+
+def default_mix(scales, gauss_draw_frac=0.2, g1d=0.5, unlikely_alpha=0.0):
+    """the 7-member default set of ptmcmc_sampler::select_proposal (ptmcmc.cc:67-139)"""
+    Ng = 6
+    props = [dict(kind=K.PROP_DE, share=1 - gauss_draw_frac, snooker=0.1, gamma_one_frac=0.3, b_small=1e-4,
+                  ignore_frac=0.0, unlikely_alpha=unlikely_alpha, reduce_gamma=4.0)]
+    total = 2.0 ** (Ng + 1) - 2
+    stepfac = 2.0
+    fac = (2.0 / stepfac) ** 4.0
+    sharefac = 1.0
+    for _ in range(Ng):
+        fac *= stepfac
+        sharefac *= 2
+        props.append(dict(kind=K.PROP_GAUSS, share=sharefac / total * gauss_draw_frac, sigmas=scales / 100.0 / fac,
+                          one_d_frac=g1d))
+    return props
+
+
+class Spec:
+    def __init__(self, model, dim, rungs, *, prop="default", prior="uniform", centers=None, halfwidths=None,
+                 bound="open", Tmax=1e9, swap_rate=0.1, evolve_rate=0.0, evolve_lpost_cut=-1.0, save_every=1,
+                 de_ni=50, seed=0.224, extra=None, prior_types=None):
+        self.model, self.dim, self.rungs, self.prop, self.prior = model, dim, rungs, prop, prior
+        self.centers = np.full(dim, 0.5) if centers is None else np.asarray(centers, dtype=float)
+        self.halfwidths = np.full(dim, 0.5) if halfwidths is None else np.asarray(halfwidths, dtype=float)
+        self.bound, self.Tmax, self.swap_rate = bound, Tmax, swap_rate
+        self.evolve_rate, self.evolve_lpost_cut, self.save_every = evolve_rate, evolve_lpost_cut, save_every
+        self.de_ni, self.seed = de_ni, seed
+        self.extra = extra or {}
+        self.prior_types = prior_types
+        self.eig = None  # (sigmas, transform) for prop=cov*, filled from the reference dump or by the caller
+
+    # ---------------------------------------------------------------- engine side
+    def config(self, n_ladders=1, **kw):
+        kw.setdefault("n_init", self.de_ni * self.dim)
+        kw.setdefault("save_every", self.save_every)
+        kw.setdefault("swap_rate", self.swap_rate)
+        kw.setdefault("Tmax", self.Tmax)
+        kw.setdefault("evolve_rate", self.evolve_rate)
+        kw.setdefault("evolve_lpost_cut", self.evolve_lpost_cut)
+        return K.make_config(n_ladders, self.rungs, self.dim, **kw)
+
+    def scales(self):
+        return self.halfwidths.copy()  # getScales: uniform half-width or Gaussian sigma
+
+    def bounds(self):
+        code = {"o": K.BOUND_OPEN, "l": K.BOUND_LIMIT, "w": K.BOUND_WRAP, "r": K.BOUND_REFLECT}
+        b = self.bound if len(self.bound) == self.dim and self.dim > 1 else self.bound[0] * self.dim
+        if self.bound == "open":
+            b = "o" * self.dim
+        t = np.array([code[c] for c in b], dtype=np.int32)
+        lo = np.where(t == K.BOUND_OPEN, -np.inf, self.centers - self.halfwidths)
+        hi = np.where(t == K.BOUND_OPEN, np.inf, self.centers + self.halfwidths)
+        return t, lo, hi
+
+    def setup(self, api):
+        d = self.dim
+        t, lo, hi = self.bounds()
+        api.set_space(t, t, lo, hi)
+        if self.prior == "uniform":
+            api.set_prior([K.PRIOR_UNIFORM] * d, self.centers - self.halfwidths, self.centers + self.halfwidths)
+        elif self.prior == "gaussian":
+            api.set_prior([K.PRIOR_GAUSSIAN] * d, self.centers, self.halfwidths)
+        else:
+            types = np.asarray(self.prior_types, dtype=np.int32)
+            a = np.where(types == K.PRIOR_GAUSSIAN, self.centers, self.centers - self.halfwidths)
+            b = np.where(types == K.PRIOR_GAUSSIAN, self.halfwidths, self.centers + self.halfwidths)
+            api.set_prior(types, a, b)
+        e = self.extra
+        if self.model == "gauss":
+            sigma = e.get("sigma", 0.5)
+            tw = 2 * sigma * sigma
+            x0 = np.asarray(e.get("x0", self.centers), dtype=float)
+            api.set_likelihood(K.LIKE_GAUSS_ISO, np.concatenate([[-0.5 * d * np.log(np.pi * tw), tw], x0]))
+        elif self.model == "sines":
+            k = e.get("k", 2)
+            api.set_likelihood(K.LIKE_SINES, np.concatenate([[e.get("height", 64.0), e.get("step_scale", np.log(2.0))],
+                                                             np.full(d, float(k)), self.centers - self.halfwidths,
+                                                             self.centers + self.halfwidths]))
+        elif self.model in ("poly", "sinusoid"):
+            kind = K.LIKE_POLY_CHI2 if self.model == "poly" else K.LIKE_SINUSOID_CHI2
+            dy = np.asarray(e["data_dy"], dtype=float)
+            api.set_likelihood(kind, [0.0], np.concatenate([e["data_x"], e["data_y"], dy * dy]))
+        elif self.model == "fullcov":
+            api.set_likelihood(K.LIKE_GAUSS_FULLCOV, [e.get("like0", 0.0)], np.asarray(e["cinv"], dtype=float).ravel())
+        elif self.model == "flat":
+            api.set_likelihood(K.LIKE_FLAT, [0.0])
+        else:
+            raise ValueError(self.model)
+        sc = self.scales()
+        de = dict(kind=K.PROP_DE, share=1.0, snooker=e.get("de_snooker", 0.1), gamma_one_frac=0.3, b_small=1e-4,
+                  ignore_frac=e.get("de_ignore_frac", 0.0), unlikely_alpha=e.get("de_unlikely_alpha", 0.0), reduce_gamma=4.0)
+        if self.prop == "default":
+            api.set_proposals(default_mix(sc, unlikely_alpha=e.get("de_unlikely_alpha", 0.0)))
+        elif self.prop == "de":
+            api.set_proposals([de], wrap_in_set=False)
+        elif self.prop == "gauss":
+            api.set_proposals([dict(kind=K.PROP_GAUSS, sigmas=sc / e.get("gauss_div", 10.0), one_d_frac=e.get("gauss_1d_frac", 0.5))],
+                              wrap_in_set=False)
+        elif self.prop in ("cov", "covde"):
+            sig, M = self.eig
+            g = dict(kind=K.PROP_GAUSS, sigmas=sig, transform=M, one_d_frac=e.get("gauss_1d_frac", 0.0), share=0.5)
+            if self.prop == "cov":
+                api.set_proposals([g], wrap_in_set=False)
+            else:
+                de2 = dict(de); de2["share"] = 0.5
+                api.set_proposals([g, de2])
+        elif self.prop == "prior":
+            f = e.get("prior_draw_frac", 0.3)
+            de2 = dict(de); de2["share"] = 1 - f
+            api.set_proposals([de2, dict(kind=K.PROP_PRIOR_DRAW, share=f)])
+        else:
+            raise ValueError(self.prop)
+
+    # ---------------------------------------------------------------- reference side
+    def ref_args(self, tmpdir, steps, out):
+        def dump(name, arr):
+            p = os.path.join(tmpdir, name + ".f64")
+            np.asarray(arr, dtype=np.float64).tofile(p)
+            return p
+        a = ["model=%s" % self.model, "dim=%d" % self.dim, "rungs=%d" % self.rungs, "steps=%d" % steps,
+             "save_every=%d" % self.save_every, "seed=%.17g" % self.seed, "Tmax=%.17g" % self.Tmax,
+             "swap_rate=%.17g" % self.swap_rate, "evolve_rate=%.17g" % self.evolve_rate,
+             "evolve_lpost_cut=%.17g" % self.evolve_lpost_cut, "de_ni=%d" % self.de_ni, "prop=%s" % self.prop,
+             "prior=%s" % self.prior, "bound=%s" % self.bound, "out=%s" % out,
+             "centers=" + dump("centers", self.centers), "halfwidths=" + dump("halfwidths", self.halfwidths)]
+        if self.prior == "mixed":
+            a.append("types=" + dump("types", np.asarray(self.prior_types, dtype=float)))
+        for k, v in self.extra.items():
+            if isinstance(v, np.ndarray):
+                a.append("%s=%s" % (k, dump(k, v)))
+            else:
+                a.append("%s=%.17g" % (k, v))
+        return a
+
+
+def read_ref_trace(path):
+    """binary dump written by oracle/ref_drivers/ref_trace.cc"""
+    raw = np.fromfile(path, dtype=np.int64)
+    f64 = raw.view(np.float64)
+    assert raw[0] == 0x7074726566
+    R, d, steps, ninit, save_every = (int(v) for v in raw[1:6])
+    p = 6
+    rungs = []
+    for _ in range(R):
+        nsize, nhist, ntries, naccept, last_type = (int(v) for v in raw[p:p + 5]); p += 5
+        invtemp, lpost, llike, maplpost = (float(v) for v in f64[p:p + 4]); p += 4
+        rec = f64[p:p + nsize * (d + 5)].reshape(nsize, d + 5); p += nsize * (d + 5)
+        rungs.append(dict(nsize=nsize, nhist=nhist, ntries=ntries, naccept=naccept, last_type=last_type, beta=invtemp,
+                          lpost=lpost, llike=llike, map_lpost=maplpost, x=rec[:, :d].copy(), hlpost=rec[:, d].copy(),
+                          hllike=rec[:, d + 1].copy(), hacc=rec[:, d + 2].copy(), hbeta=rec[:, d + 3].copy(),
+                          htype=rec[:, d + 4].astype(np.int32)))
+    sw = raw[p:p + 2 * (R - 1)].reshape(R - 1, 2); p += 2 * (R - 1)
+    misc = raw[p:p + 4 * R].reshape(R, 4)
+    return dict(R=R, dim=d, steps=steps, ninit=ninit, save_every=save_every, rungs=rungs, swap_count=sw[:, 0].copy(),
+                swap_accept=sw[:, 1].copy(), directions=misc[:, 0].copy(), ups=misc[:, 1].copy(), downs=misc[:, 2].copy(),
+                instances=misc[:, 3].copy())
+
+
+def engine_dump(api, ladder=0):
+    """same structure as read_ref_trace, from an engine behind the C ABI"""
+    R, d = api.cfg.n_rungs, api.cfg.dim
+    cnt = api.get_counters(); cur = api.get_current(); sw = api.get_swap_stats()
+    rungs = []
+    for r in range(R):
+        i = ladder * R + r
+        n = int(cnt["nsize"][i])
+        hst = api.get_history(ladder, r, 0, n)
+        rungs.append(dict(nsize=n, nhist=int(cnt["nhist"][i]), ntries=int(cnt["ntries"][i]), naccept=int(cnt["naccept"][i]),
+                          last_type=int(cnt["last_type"][i]), beta=float(cur["beta"][i]), lpost=float(cur["lpost"][i]),
+                          llike=float(cur["llike"][i]), map_lpost=float(cnt["map_lpost"][i]), x=hst["x"], hlpost=hst["lpost"],
+                          hllike=hst["llike"], hacc=hst["acc"], hbeta=hst["beta"], htype=hst["type"]))
+    return dict(R=R, dim=d, rungs=rungs, swap_count=sw["swap_count"][ladder], swap_accept=sw["swap_accept"][ladder],
+                directions=sw["directions"][ladder], ups=sw["ups"][ladder], downs=sw["downs"][ladder],
+                instances=sw["instances"][ladder])
+
+
+def compare_dumps(a, b, rtol=0.0, what="", max_report=5):
+    """bit-exact (rtol=0) or relative comparison of two dumps; returns list of mismatch strings"""
+    bad = []
+
+    def chk(name, u, v, exact=False):
+        u = np.asarray(u); v = np.asarray(v)
+        if u.shape != v.shape:
+            bad.append("%s %s: shape %s vs %s" % (what, name, u.shape, v.shape)); return
+        if rtol == 0.0 or exact or u.dtype.kind in "iu":
+            ok = (u == v) | ((u != u) & (v != v))
+        else:
+            with np.errstate(invalid="ignore"):
+                ok = (np.abs(u - v) <= rtol * np.maximum(np.abs(u), np.abs(v))) | (u == v) | ((u != u) & (v != v))
+        if not np.all(ok):
+            idx = np.argwhere(~ok)[0]
+            bad.append("%s %s: %d mismatches, first at %s: %r vs %r" % (what, name, int((~ok).sum()), tuple(idx), u[tuple(idx)], v[tuple(idx)]))
+
+    for r in range(a["R"]):
+        ra, rb = a["rungs"][r], b["rungs"][r]
+        for k in ("nsize", "nhist", "ntries", "naccept", "last_type"):
+            if ra[k] != rb[k]:
+                bad.append("%s rung %d %s: %r vs %r" % (what, r, k, ra[k], rb[k]))
+        if ra["nsize"] != rb["nsize"]:
+            continue
+        chk("rung %d x" % r, ra["x"], rb["x"], exact=True)
+        chk("rung %d htype" % r, ra["htype"], rb["htype"])
+        chk("rung %d hacc" % r, ra["hacc"], rb["hacc"], exact=True)
+        chk("rung %d hbeta" % r, ra["hbeta"], rb["hbeta"])
+        chk("rung %d hllike" % r, ra["hllike"], rb["hllike"])
+        chk("rung %d hlpost" % r, ra["hlpost"], rb["hlpost"])
+        chk("rung %d beta" % r, ra["beta"], rb["beta"])
+        chk("rung %d map" % r, ra["map_lpost"], rb["map_lpost"])
+    for k in ("swap_count", "swap_accept", "directions", "ups", "downs", "instances"):
+        chk(k, a[k], b[k])
+    return bad[:max_report] if max_report else bad
