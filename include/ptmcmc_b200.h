@@ -121,8 +121,8 @@ int ptg_set_prior(ptg_handle *h, const int32_t *type, const double *a, const dou
 /* device likelihood functor; replaces bayes_likelihood::register_evaluate_log (bayesian.hh:544-552).
  *   GAUSS_ISO      params = [lnnormfac, twosigmasq, x0[dim]]
  *   SINES          params = [height, step_scale, k[dim], min[dim], max[dim]]
- *   POLY_CHI2      params = [like0]; data = [x[N], y[N], var[N]]  (n_data = N)
- *   SINUSOID_CHI2  params = [like0]; data = [t[N], y[N], var[N]]; state = (A,f,phi) triples
+ *   POLY_CHI2      params = [like0]; data = [x[N], y[N], var[N]]  (n_data = 3N doubles)
+ *   SINUSOID_CHI2  params = [like0]; data = [t[N], y[N], var[N]]  (n_data = 3N); state = (A,f,phi) triples
  *   GAUSS_FULLCOV  params = [like0]; data = Cinv[dim*dim] row-major (n_data = dim*dim) */
 int ptg_set_likelihood(ptg_handle *h, int32_t kind, const double *params, int32_t n_params,
                        const double *data, int64_t n_data);
@@ -154,6 +154,7 @@ int ptg_step_host(ptg_handle *h, int64_t n_steps, int32_t n_out, double *x_out, 
 
 /* read-back: chain::getState/getLogPost/getLogLike/invTemp (chain.hh:86-124) ---------------------------- */
 int ptg_get_current(ptg_handle *h, double *x, double *lpost, double *llike, double *beta);
+int ptg_get_lprior(ptg_handle *h, double *lprior);
 int ptg_get_counters(ptg_handle *h, int64_t *nhist, int64_t *nsize, int64_t *ntries, int64_t *naccept,
                      int32_t *last_type, double *map_lpost);
 /* raw-indexed history of one chain, elements [first, first+count); entries older than the ring are an error.
@@ -174,8 +175,16 @@ int ptg_get_trace(ptg_handle *h, int64_t first, int64_t count, double *lhr, int3
 #define PTG_TRACE_NOLIKE 0x800       /* prior gate skipped the likelihood (chain.cc:980-987) */
 /* total history appends (= tempered chain-steps, the BASELINE metric) since init */
 int ptg_get_total_steps(ptg_handle *h, int64_t *total);
-/* device pointer + stream for zero-copy consumers (torch / NCCL gather of cold samples) */
-int ptg_get_device_views(ptg_handle *h, void **hist_x_dev, void **hist_meta_dev, void **cur_x_dev, void **stream);
+/* device pointers + stream for zero-copy consumers (torch / NCCL gather of cold samples): history records
+ * hist_dev[chain][hist_capacity][dim+2] = (x[dim], lpost, llike), *hist_stride = doubles per chain;
+ * cur_x_dev[dim][n_chains] */
+int ptg_get_device_views(ptg_handle *h, void **hist_dev, void **cur_x_dev, void **stream, int64_t *hist_stride);
+/* run all further work of this handle on a caller-owned cudaStream_t (e.g. torch's current stream) */
+int ptg_set_stream(ptg_handle *h, void *cuda_stream);
+/* overwrite the current state of every chain from host arrays x[n_chains][dim], lpost, llike, lprior[n_chains]
+ * (the restart path of MH_chain, chain.cc:691-731; also what a host facade that keeps `state` objects
+ * authoritative does before each block of steps).  Asynchronous on the handle's stream. */
+int ptg_set_current(ptg_handle *h, const double *x, const double *lpost, const double *llike, const double *lprior);
 
 /* checkpoint / restore of the complete engine state (restart.hh semantics; format in DESIGN.md) */
 int ptg_checkpoint(ptg_handle *h, const char *path);

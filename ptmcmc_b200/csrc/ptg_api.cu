@@ -1,0 +1,762 @@
+// ptg_api.cu -- the C ABI of include/ptmcmc_b200.h: handle management, model set-up, kernel dispatch, read-back.
+// Host logic only; all chain arithmetic happens in the kernels of ptg_kernels.cuh / ptg_wide.cuh.
+// There is no CPU fallback: every entry point that computes needs a CUDA device.
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "ptg_launch.h"
+#include "ptg_device.cuh"
+
+static thread_local char g_err[512] = "";
+extern "C" const char *ptg_last_error(void) { return g_err; }
+extern "C" int ptg_abi_version(void) { return PTG_ABI_VERSION; }
+static int fail(int code, const char *fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+  return code;
+}
+#define CUDA_TRY(expr)                                                                                     \
+  do {                                                                                                     \
+    cudaError_t e__ = (expr);                                                                              \
+    if (e__ != cudaSuccess) return fail(PTG_ECUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+struct HostProp {
+  ptg_proposal p;
+  std::vector<double> sigmas, transform;
+};
+
+struct ptg_handle {
+  ptg_config cfg;
+  PtgModel m;
+  PtgState s;
+  cudaStream_t stream;
+  bool own_stream;
+  bool have_space, have_prior, have_like, have_props, inited, model_uploaded;
+  std::vector<HostProp> props;
+  double Tpow;
+  std::vector<double> lparams, ldata, betas;
+  std::vector<void *> allocs;       // every device allocation (freed in destroy)
+  double *d_lparams, *d_ldata, *d_prop_data, *d_bins;
+  double *d_tape_u, *d_tape_z; long long *d_u_end, *d_z_end;
+  long long istep;
+  double *d_scratch; size_t scratch_bytes;
+  double *h_pinned; size_t pinned_bytes;
+};
+
+template <typename T>
+static int dev_alloc(ptg_handle *h, T **p, size_t n, bool zero = true) {
+  void *q = nullptr;
+  size_t bytes = (n ? n : 1) * sizeof(T);
+  cudaError_t e = cudaMalloc(&q, bytes);
+  if (e != cudaSuccess) return fail(PTG_ENOMEM, "cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
+  if (zero) cudaMemsetAsync(q, 0, bytes, h->stream);
+  h->allocs.push_back(q);
+  *p = (T *)q;
+  return 0;
+}
+
+__global__ void ptg_uniform_lprior_kernel(PtgModel m, double *out) {
+  // log(prod_i 1/(b_i-a_i)): same operation order as uniform_dist_product::evaluate (probability_function.cc:156-166)
+  double result = 1;
+  for (int i = 0; i < m.dim; i++) result *= 1 / (m.prior[i].b - m.prior[i].a);
+  *out = log(result);
+}
+__global__ void ptg_fill_kernel(double *p, long long n, double v) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void ptg_fill_ll_kernel(long long *p, long long n, long long v) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void ptg_fill_i_kernel(int32_t *p, long long n, int32_t v) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void ptg_ladder_init_kernel(PtgState s, int R, long long n_chains) {
+  // chain.cc:1345-1358
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_chains) return;
+  int r = (int)(c % R);
+  s.instances[c] = r;
+  s.directions[c] = (r == 0) ? -1 : (r == R - 1 ? 1 : 0);
+  s.ups[c] = 0; s.downs[c] = 0; s.swap_count[c] = 0; s.swap_accept[c] = 0;
+}
+__global__ void ptg_sum_nhist_kernel(const long long *nhist, long long n, unsigned long long *out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long v = (i < n) ? (unsigned long long)nhist[i] : 0ull;
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0 && v) atomicAdd(out, v);
+}
+// newest n_out stored samples of every ladder's cold chain -> out_x[L][n_out][D], out_lp[L][n_out], out_ll[L][n_out]
+__global__ void ptg_gather_cold_kernel(PtgModel m, PtgState s, int n_out, double *out_x, double *out_lp, double *out_ll) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)m.n_ladders * n_out;
+  if (t >= total) return;
+  long long l = t / n_out; int k = (int)(t - l * n_out);
+  long long c = l * m.n_rungs;
+  long long nsize = s.nsize[c];
+  long long logical = nsize - n_out + k; // k-th of the newest n_out
+  const int D = m.dim;
+  if (logical < 0) { for (int i = 0; i < D; i++) out_x[t * D + i] = CUDART_NAN; out_lp[t] = CUDART_NAN; out_ll[t] = CUDART_NAN; return; }
+  const double *h = s.hist + (c * m.hist_cap + (logical % m.hist_cap)) * (D + 2);
+  for (int i = 0; i < D; i++) out_x[t * D + i] = h[i];
+  out_lp[t] = h[D]; out_ll[t] = h[D + 1];
+}
+
+// [chain][dim] -> [dim][chain]
+__global__ void ptg_transpose_kernel(const double *src, double *dst, long long n, int d) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * d) return;
+  long long c = t / d; int k = (int)(t - c * d);
+  dst[(long long)k * n + c] = src[t];
+}
+
+static inline int grid_for(long long n, int b = 256) { return (int)((n + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------------- lifecycle
+extern "C" int ptg_create(const ptg_config *cfg, ptg_handle **out) {
+  if (!cfg || !out) return fail(PTG_EINVAL, "null argument");
+  if (cfg->abi_version != PTG_ABI_VERSION) return fail(PTG_EINVAL, "abi version mismatch (%d != %d)", cfg->abi_version, PTG_ABI_VERSION);
+  if (cfg->dim < 1 || cfg->dim > PTG_MAX_DIM) return fail(PTG_EINVAL, "dim out of range");
+  if (cfg->n_rungs < 1 || cfg->n_rungs > PTG_MAX_RUNGS || cfg->n_ladders < 1) return fail(PTG_EINVAL, "bad ladder shape");
+  if (cfg->save_every < 1 || cfg->n_init < 1) return fail(PTG_EINVAL, "save_every and n_init must be >= 1");
+  if (cfg->swap_mode != PTG_SWAP_REFERENCE && cfg->swap_mode != PTG_SWAP_EVEN_ODD) return fail(PTG_EINVAL, "bad swap_mode");
+  if (cfg->swap_mode == PTG_SWAP_EVEN_ODD && cfg->evolve_rate > 0)
+    return fail(PTG_EINVAL, "temperature evolution is defined for the reference swap schedule only");
+  if (cfg->rng_mode != PTG_RNG_PHILOX && cfg->rng_mode != PTG_RNG_TAPE) return fail(PTG_EINVAL, "bad rng_mode");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(PTG_ECUDA, "no CUDA device: %s (the ptg engine has no CPU fallback)", e != cudaSuccess ? cudaGetErrorString(e) : "count=0");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(PTG_EINVAL, "device %d out of range (%d devices)", cfg->device, ndev);
+  CUDA_TRY(cudaSetDevice(cfg->device));
+  bool supported_dim = false;
+#define X(D) if (cfg->dim == D) supported_dim = true;
+  PTG_DIM_LIST(X)
+#undef X
+  if (!supported_dim) return fail(PTG_EINVAL, "dim=%d: thread-per-chain kernels are instantiated for 1-10,12,16", cfg->dim);
+
+  ptg_handle *h = new ptg_handle();
+  memset(&h->m, 0, sizeof(h->m)); memset(&h->s, 0, sizeof(h->s));
+  h->cfg = *cfg;
+  h->have_space = h->have_prior = h->have_like = h->have_props = h->inited = h->model_uploaded = false;
+  h->d_lparams = h->d_ldata = h->d_prop_data = h->d_bins = nullptr;
+  h->d_tape_u = h->d_tape_z = nullptr; h->d_u_end = h->d_z_end = nullptr;
+  h->istep = 0; h->Tpow = 0; h->d_scratch = nullptr; h->scratch_bytes = 0; h->h_pinned = nullptr; h->pinned_bytes = 0;
+  cudaError_t es = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (es != cudaSuccess) { delete h; return fail(PTG_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(es)); }
+  h->own_stream = true;
+
+  PtgModel &m = h->m;
+  m.dim = cfg->dim; m.n_rungs = cfg->n_rungs; m.n_ladders = cfg->n_ladders;
+  m.n_chains = (int64_t)cfg->n_rungs * cfg->n_ladders;
+  m.save_every = cfg->save_every; m.n_init = cfg->n_init;
+  int cap = cfg->hist_capacity > 0 ? cfg->hist_capacity : cfg->n_init + 1024;
+  if (cap < cfg->n_init) cap = cfg->n_init;
+  m.hist_cap = cap;
+  int maxswaps = (int)(1 + 2 * cfg->swap_rate * cfg->n_rungs); // chain.cc:1192
+  if (maxswaps > PTG_SWAP_SLOTS) maxswaps = PTG_SWAP_SLOTS;
+  if (maxswaps < 1) maxswaps = 1;
+  m.maxswaps = maxswaps;
+  m.swap_mode = cfg->swap_mode; m.record_full = cfg->record_level == PTG_RECORD_FULL; m.wrap_in_set = 1; m.zero_valid = 1;
+  m.trace_steps = cfg->trace_steps;
+  m.swap_rate = cfg->swap_rate; m.dprior_min = cfg->dprior_min; m.evolve_rate = cfg->evolve_rate; m.evolve_lpost_cut = cfg->evolve_lpost_cut;
+  m.seed = cfg->seed; m.ladder_offset = cfg->ladder_offset;
+  for (int i = 0; i < PTG_TPC_MAX_DIM; i++) { m.lower[i] = m.upper[i] = PTG_BOUND_OPEN; m.xmin[i] = -INFINITY; m.xmax[i] = INFINITY; }
+
+  // device state
+  PtgState &s = h->s;
+  const size_t n = (size_t)m.n_chains, d = (size_t)m.dim;
+  int rc = 0;
+  rc |= dev_alloc(h, &s.cur_x, n * d); rc |= dev_alloc(h, &s.lpost, n); rc |= dev_alloc(h, &s.llike, n);
+  rc |= dev_alloc(h, &s.lprior, n); rc |= dev_alloc(h, &s.beta, n); rc |= dev_alloc(h, &s.map_lpost, n); rc |= dev_alloc(h, &s.map_x, n * d);
+  rc |= dev_alloc(h, &s.nhist, n); rc |= dev_alloc(h, &s.nsize, n); rc |= dev_alloc(h, &s.ntries, n); rc |= dev_alloc(h, &s.naccept, n);
+  rc |= dev_alloc(h, &s.last_type, n);
+  rc |= dev_alloc(h, &s.hist, n * (size_t)cap * (d + 2), false);
+  if (m.record_full) {
+    rc |= dev_alloc(h, &s.hist_acc, n * (size_t)cap, false); rc |= dev_alloc(h, &s.hist_beta, n * (size_t)cap, false);
+    rc |= dev_alloc(h, &s.hist_type, n * (size_t)cap, false);
+  }
+  rc |= dev_alloc(h, &s.swap_count, n); rc |= dev_alloc(h, &s.swap_accept, n);
+  rc |= dev_alloc(h, &s.directions, n); rc |= dev_alloc(h, &s.ups, n); rc |= dev_alloc(h, &s.downs, n); rc |= dev_alloc(h, &s.instances, n);
+  rc |= dev_alloc(h, &s.u_pos, n + (size_t)m.n_ladders); rc |= dev_alloc(h, &s.z_pos, n + (size_t)m.n_ladders);
+  rc |= dev_alloc(h, &s.err, 1);
+  if (cfg->trace_steps > 0) { rc |= dev_alloc(h, &s.trace_lhr, n * (size_t)cfg->trace_steps); rc |= dev_alloc(h, &s.trace_code, n * (size_t)cfg->trace_steps); }
+  if (rc) { ptg_destroy(h); return PTG_ENOMEM; }
+
+  // geometric ladder (chain.cc:1181-1183,1339): temps[i]=temps[i-1]*tratio ; invtemp = 1/temps[i]
+  h->betas.resize(n);
+  double tratio = (m.n_rungs > 1) ? exp(log(cfg->Tmax) / (m.n_rungs - 1)) : 1.0;
+  for (int l = 0; l < m.n_ladders; l++) {
+    double temp = 1;
+    for (int r = 0; r < m.n_rungs; r++) { if (r > 0) temp = temp * tratio; h->betas[(size_t)l * m.n_rungs + r] = 1 / temp; }
+  }
+  *out = h;
+  return 0;
+}
+
+extern "C" int ptg_destroy(ptg_handle *h) {
+  if (!h) return 0;
+  cudaSetDevice(h->cfg.device);
+  cudaStreamSynchronize(h->stream);
+  for (void *p : h->allocs) cudaFree(p);
+  if (h->h_pinned) cudaFreeHost(h->h_pinned);
+  if (h->own_stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------- set-up
+extern "C" int ptg_set_space(ptg_handle *h, const int32_t *lt, const int32_t *ut, const double *xmin, const double *xmax) {
+  if (!h || !lt || !ut || !xmin || !xmax) return fail(PTG_EINVAL, "null argument");
+  PtgModel &m = h->m;
+  bool zero_valid = true;
+  for (int i = 0; i < m.dim; i++) {
+    m.lower[i] = lt[i]; m.upper[i] = ut[i]; m.xmin[i] = xmin[i]; m.xmax[i] = xmax[i];
+    // validity of the zero vector decides the validity of every state built by state::add / scalar_mult
+    // (states.cc:168-176,194-204).  Pure comparisons: no arithmetic result is kept.
+    if (zero_valid) {
+      bool wl = lt[i] == PTG_BOUND_WRAP, wu = ut[i] == PTG_BOUND_WRAP;
+      if (wl != wu) zero_valid = false;
+      else if (wl) { if (xmax[i] - xmin[i] <= 0) zero_valid = false; }
+      else if (lt[i] == PTG_BOUND_REFLECT && ut[i] == PTG_BOUND_REFLECT) { if (xmax[i] - xmin[i] <= 0) zero_valid = false; }
+      else {
+        double x = 0;
+        if (lt[i] == PTG_BOUND_REFLECT && x < xmin[i]) x = xmin[i] + (xmin[i] - x);
+        else if (ut[i] == PTG_BOUND_REFLECT && x > xmax[i]) x = xmax[i] - (x - xmax[i]);
+        if (lt[i] == PTG_BOUND_LIMIT && x < xmin[i]) zero_valid = false;
+        if (ut[i] == PTG_BOUND_LIMIT && x > xmax[i]) zero_valid = false;
+      }
+    }
+  }
+  m.zero_valid = zero_valid ? 1 : 0;
+  h->have_space = true;
+  return 0;
+}
+
+extern "C" int ptg_set_prior(ptg_handle *h, const int32_t *type, const double *a, const double *b) {
+  if (!h || !type || !a || !b) return fail(PTG_EINVAL, "null argument");
+  PtgModel &m = h->m;
+  bool all_uniform = true;
+  for (int i = 0; i < m.dim; i++) {
+    PtgPrior1D &p = m.prior[i];
+    p.kind = type[i]; p.pad = 0; p.a = a[i]; p.b = b[i]; p.norm = p.cdfoff = p.la = p.lb = 0;
+    if (p.kind != PTG_PRIOR_UNIFORM) all_uniform = false;
+    if (p.kind == PTG_PRIOR_POLAR) { // ProbabilityDist.h:187-192
+      double lo = a[i], hi = b[i];
+      if (lo < 0) lo = 0;
+      if (hi > M_PI) hi = M_PI;
+      p.norm = -cos(hi) + cos(lo); p.cdfoff = -cos(lo) / p.norm;
+    } else if (p.kind == PTG_PRIOR_COPOLAR) { // ProbabilityDist.h:228-233
+      double lo = a[i], hi = b[i];
+      if (lo < -M_PI / 2) lo = -M_PI / 2;
+      if (hi > M_PI / 2) hi = M_PI / 2;
+      p.norm = sin(hi) - sin(lo); p.cdfoff = sin(lo) / p.norm;
+    } else if (p.kind == PTG_PRIOR_LOG) {
+      if (a[i] <= 0 || b[i] <= a[i]) return fail(PTG_EINVAL, "log prior needs 0 < xmin < xmax");
+      p.la = log(a[i]); p.lb = log(b[i]);
+    } else if (p.kind != PTG_PRIOR_UNIFORM && p.kind != PTG_PRIOR_GAUSSIAN) return fail(PTG_EINVAL, "bad prior type %d", p.kind);
+  }
+  m.all_uniform_prior = all_uniform ? 1 : 0;
+  h->have_prior = true;
+  return 0;
+}
+
+extern "C" int ptg_set_likelihood(ptg_handle *h, int32_t kind, const double *params, int32_t n_params, const double *data, int64_t n_data) {
+  if (!h) return fail(PTG_EINVAL, "null handle");
+  PtgModel &m = h->m;
+  const int d = m.dim;
+  int need = 0;
+  switch (kind) {
+  case PTG_LIKE_FLAT: need = 0; break;
+  case PTG_LIKE_GAUSS_ISO: need = 2 + d; break;
+  case PTG_LIKE_SINES: need = 2 + 3 * d; break;
+  case PTG_LIKE_POLY_CHI2: case PTG_LIKE_SINUSOID_CHI2: case PTG_LIKE_GAUSS_FULLCOV: need = 1; break;
+  default: return fail(PTG_EINVAL, "unknown likelihood kind %d", kind);
+  }
+  if (n_params < need || (need && !params)) return fail(PTG_EINVAL, "likelihood kind %d needs %d params", kind, need);
+  if ((kind == PTG_LIKE_POLY_CHI2 || kind == PTG_LIKE_SINUSOID_CHI2) && (n_data <= 0 || n_data % 3 || !data))
+    return fail(PTG_EINVAL, "chi2 likelihoods need data = [x[N], y[N], var[N]] (n_data = 3N)");
+  if (kind == PTG_LIKE_SINUSOID_CHI2 && d % 3) return fail(PTG_EINVAL, "sinusoid model needs dim = 3k");
+  if (kind == PTG_LIKE_GAUSS_FULLCOV && (n_data != (int64_t)d * d || !data)) return fail(PTG_EINVAL, "fullcov needs Cinv[dim*dim]");
+  h->lparams.assign(params, params + (n_params > 0 ? n_params : 0));
+  if (h->lparams.empty()) h->lparams.push_back(0.0);
+  h->ldata.assign(data ? data : nullptr, data ? data + n_data : nullptr);
+  m.like_kind = kind; m.n_lparams = n_params; m.n_ldata = n_data;
+  m.like_nsum = 0;
+  if (kind == PTG_LIKE_POLY_CHI2 || kind == PTG_LIKE_SINUSOID_CHI2) {
+    // nsum = sum_i log(S_i) (bayesian.hh:613) is independent of the state: evaluated once at set-up
+    int64_t N = n_data / 3; double nsum = 0;
+    for (int64_t i = 0; i < N; i++) nsum += log(data[2 * N + i]);
+    m.like_nsum = nsum;
+  }
+  h->have_like = true;
+  return 0;
+}
+
+extern "C" int ptg_set_proposals(ptg_handle *h, int32_t n, const ptg_proposal *props, double Tpow, int32_t wrap_in_set) {
+  if (!h || !props) return fail(PTG_EINVAL, "null argument");
+  if (n < 1 || n > PTG_MAX_PROPOSALS) return fail(PTG_EINVAL, "bad proposal count %d", n);
+  if (!wrap_in_set && n != 1) return fail(PTG_EINVAL, "a bare proposal must be single");
+  h->props.clear();
+  for (int i = 0; i < n; i++) {
+    HostProp hp; hp.p = props[i];
+    if (props[i].kind == PTG_PROP_GAUSS) {
+      if (!props[i].sigmas) return fail(PTG_EINVAL, "gaussian proposal %d without sigmas", i);
+      hp.sigmas.assign(props[i].sigmas, props[i].sigmas + h->m.dim);
+      if (props[i].transform) hp.transform.assign(props[i].transform, props[i].transform + (size_t)h->m.dim * h->m.dim);
+    } else if (props[i].kind == PTG_PROP_DE) {
+      if (!(props[i].reduce_gamma > 0)) return fail(PTG_EINVAL, "DE proposal %d needs reduce_gamma > 0", i);
+    } else if (props[i].kind != PTG_PROP_PRIOR_DRAW) return fail(PTG_EINVAL, "unknown proposal kind %d", props[i].kind);
+    h->props.push_back(hp);
+  }
+  h->Tpow = Tpow; h->m.wrap_in_set = wrap_in_set ? 1 : 0; h->m.n_props = n;
+  h->have_props = true;
+  return 0;
+}
+
+extern "C" int ptg_set_betas(ptg_handle *h, const double *betas) {
+  if (!h) return fail(PTG_EINVAL, "null handle");
+  if (betas) h->betas.assign(betas, betas + h->m.n_chains);
+  return 0;
+}
+
+extern "C" int ptg_seed(ptg_handle *h, uint64_t seed) {
+  if (!h) return fail(PTG_EINVAL, "null handle");
+  h->cfg.seed = seed; h->m.seed = seed;
+  return 0;
+}
+
+extern "C" int ptg_inject_tapes(ptg_handle *h, const double *u, const int64_t *u_off, const double *z, const int64_t *z_off) {
+  if (!h || !u || !u_off || !z || !z_off) return fail(PTG_EINVAL, "null argument");
+  if (h->cfg.rng_mode != PTG_RNG_TAPE) return fail(PTG_EINVAL, "engine was not created with PTG_RNG_TAPE");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const size_t ns = (size_t)h->m.n_chains + h->m.n_ladders;
+  int rc = 0;
+  rc |= dev_alloc(h, &h->d_tape_u, (size_t)u_off[ns], false); rc |= dev_alloc(h, &h->d_tape_z, (size_t)z_off[ns], false);
+  rc |= dev_alloc(h, &h->d_u_end, ns, false); rc |= dev_alloc(h, &h->d_z_end, ns, false);
+  if (rc) return PTG_ENOMEM;
+  CUDA_TRY(cudaMemcpyAsync(h->d_tape_u, u, (size_t)u_off[ns] * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->d_tape_z, z, (size_t)z_off[ns] * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->s.u_pos, u_off, ns * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->s.z_pos, z_off, ns * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->d_u_end, u_off + 1, ns * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->d_z_end, z_off + 1, ns * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->s.tape_u = h->d_tape_u; h->s.tape_z = h->d_tape_z; h->s.u_end = h->d_u_end; h->s.z_end = h->d_z_end;
+  return 0;
+}
+
+// proposal_distribution_set::reset_bins (proposal_distribution.cc:37-59): run once by the constructor (no chain yet,
+// Tfac = 0) and once more by set_chain on each rung's clone (proposal_distribution.hh:336)
+static void compute_bins(const ptg_handle *h, double beta, double *bin_max) {
+  const int n = (int)h->props.size();
+  double shares[PTG_MAX_PROPOSALS], hot[PTG_MAX_PROPOSALS];
+  for (int i = 0; i < n; i++) { shares[i] = h->props[i].p.share; hot[i] = h->props[i].p.hot_share; }
+  if (h->Tpow > 0) {
+    double sum = 0;
+    for (int i = 0; i < n; i++) sum += hot[i];
+    if (sum <= 0) for (int i = 0; i < n; i++) hot[i] = shares[i];
+    else for (int i = 0; i < n; i++) hot[i] /= sum;
+  }
+  for (int pass = 0; pass < 2; pass++) {
+    double Tfac = 0;
+    if (h->Tpow > 0 && pass == 1) Tfac = 1 - pow(beta, h->Tpow);
+    double sum = 0;
+    for (int i = 0; i < n; i++) sum += shares[i];
+    double last = 0;
+    for (int i = 0; i < n; i++) {
+      shares[i] /= sum;
+      bin_max[i] = last + shares[i];
+      if (h->Tpow > 0) bin_max[i] += (hot[i] - shares[i]) * Tfac;
+      last = bin_max[i];
+    }
+    double back = bin_max[n - 1];
+    for (int i = 0; i < n; i++) bin_max[i] /= back;
+  }
+}
+
+static int upload_model(ptg_handle *h) {
+  PtgModel &m = h->m;
+  if (!h->have_prior || !h->have_like || !h->have_props) return fail(PTG_EINVAL, "set prior, likelihood and proposals before initialising");
+  const int d = m.dim;
+  // proposals
+  std::vector<double> pdata;
+  for (int i = 0; i < m.n_props; i++) {
+    const HostProp &hp = h->props[i];
+    PtgProp &p = m.props[i];
+    memset(&p, 0, sizeof(p));
+    p.kind = hp.p.kind; p.snooker = hp.p.snooker; p.g1frac = hp.p.gamma_one_frac; p.ignore_frac = hp.p.ignore_frac;
+    p.unlikely_alpha = hp.p.unlikely_alpha; p.reduce_gamma = hp.p.reduce_gamma; p.one_d_frac = hp.p.one_d_frac;
+    if (p.kind == PTG_PROP_DE) p.gamma_std = 1.68 / sqrt((double)d) / hp.p.reduce_gamma; // proposal_distribution.cc:495
+    if (p.kind == PTG_PROP_GAUSS) {
+      p.sigma_off = (int)pdata.size(); pdata.insert(pdata.end(), hp.sigmas.begin(), hp.sigmas.end());
+      p.has_transform = hp.transform.empty() ? 0 : 1;
+      if (p.has_transform) { p.trans_off = (int)pdata.size(); pdata.insert(pdata.end(), hp.transform.begin(), hp.transform.end()); }
+    }
+  }
+  if (pdata.empty()) pdata.push_back(0.0);
+  // bins per rung, from ladder 0's initial inverse temperatures
+  std::vector<double> bins((size_t)m.n_rungs * m.n_props);
+  for (int r = 0; r < m.n_rungs; r++) compute_bins(h, h->betas[r], &bins[(size_t)r * m.n_props]);
+  if (h->Tpow > 0)
+    for (int l = 1; l < m.n_ladders; l++)
+      for (int r = 0; r < m.n_rungs; r++)
+        if (h->betas[(size_t)l * m.n_rungs + r] != h->betas[r]) return fail(PTG_EINVAL, "Tpow > 0 needs identical ladders");
+  int rc = 0;
+  rc |= dev_alloc(h, &h->d_lparams, h->lparams.size(), false); rc |= dev_alloc(h, &h->d_ldata, h->ldata.size(), false);
+  rc |= dev_alloc(h, &h->d_prop_data, pdata.size(), false); rc |= dev_alloc(h, &h->d_bins, bins.size(), false);
+  if (rc) return PTG_ENOMEM;
+  CUDA_TRY(cudaMemcpyAsync(h->d_lparams, h->lparams.data(), h->lparams.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (!h->ldata.empty()) CUDA_TRY(cudaMemcpyAsync(h->d_ldata, h->ldata.data(), h->ldata.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->d_prop_data, pdata.data(), pdata.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->d_bins, bins.data(), bins.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  m.lparams = h->d_lparams; m.ldata = h->d_ldata; m.prop_data = h->d_prop_data; m.bins = h->d_bins;
+  m.uniform_lprior = 0;
+  if (m.all_uniform_prior) {
+    double *d_out; rc = dev_alloc(h, &d_out, 1); if (rc) return rc;
+    ptg_uniform_lprior_kernel<<<1, 1, 0, h->stream>>>(m, d_out);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(&m.uniform_lprior, d_out, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  }
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->model_uploaded = true;
+  return 0;
+}
+
+static int check_device_error(ptg_handle *h) {
+  int32_t e = 0;
+  CUDA_TRY(cudaMemcpyAsync(&e, h->s.err, sizeof(e), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (e) CUDA_TRY(cudaMemsetAsync(h->s.err, 0, sizeof(int32_t), h->stream)); // reported once, then cleared
+  if (e == 1) return fail(PTG_ETAPE, "injected tape exhausted");
+  if (e == 2) return fail(PTG_EINVAL, "proposal set: no member ready");
+  if (e == 4) return fail(PTG_ESTUCK, "init: cannot draw a valid state");
+  if (e) return fail(PTG_ECUDA, "device error flag %d", e);
+  return 0;
+}
+
+static int do_init(ptg_handle *h, const double *x_host) {
+  if (!h) return fail(PTG_EINVAL, "null handle");
+  if (h->inited) return fail(PTG_EINVAL, "already initialised (chain.cc:847-850)");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  if (h->cfg.rng_mode == PTG_RNG_TAPE && !h->s.tape_u && !x_host) return fail(PTG_EINVAL, "PTG_RNG_TAPE: inject tapes before init");
+  int rc = upload_model(h); if (rc) return rc;
+  PtgModel &m = h->m; PtgState &s = h->s;
+  const long long n = m.n_chains;
+  CUDA_TRY(cudaMemcpyAsync(s.beta, h->betas.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  ptg_fill_kernel<<<grid_for(n), 256, 0, h->stream>>>(s.map_lpost, n, -1e200);        // chain.hh:69
+  ptg_fill_ll_kernel<<<grid_for(n), 256, 0, h->stream>>>(s.ntries, n, 1);              // chain.cc:649
+  ptg_fill_ll_kernel<<<grid_for(n), 256, 0, h->stream>>>(s.naccept, n, 1);
+  ptg_fill_i_kernel<<<grid_for(n), 256, 0, h->stream>>>(s.last_type, n, -1);
+  ptg_ladder_init_kernel<<<grid_for(n), 256, 0, h->stream>>>(s, m.n_rungs, n);
+  double *d_x = nullptr;
+  if (x_host) {
+    size_t cnt = (size_t)n * m.n_init * m.dim;
+    rc = dev_alloc(h, &d_x, cnt, false); if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(d_x, x_host, cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  }
+  cudaError_t e = cudaErrorInvalidValue;
+  switch (m.dim) {
+#define X(D) case D: e = ptg_launch_init_d##D(h->cfg.rng_mode, m, s, d_x, h->stream); break;
+    PTG_DIM_LIST(X)
+#undef X
+  }
+  CUDA_TRY(e);
+  rc = check_device_error(h); if (rc) return rc;
+  h->inited = true; h->istep = 0;
+  return 0;
+}
+extern "C" int ptg_init_from_prior(ptg_handle *h) { return do_init(h, nullptr); }
+extern "C" int ptg_init_states(ptg_handle *h, const double *x) {
+  if (!x) return fail(PTG_EINVAL, "null states");
+  return do_init(h, x);
+}
+
+// ------------------------------------------------------------------------------------------------- stepping
+static int ladders_per_block(const PtgModel &m) {
+  int lpb = 128 / m.n_rungs;
+  if (lpb < 1) lpb = 1;
+  if (lpb > m.n_ladders) lpb = m.n_ladders;
+  return lpb;
+}
+static size_t ladder_shared_bytes(int D, int R) {
+  size_t b = sizeof(double) * ((size_t)R * D * 2 + (size_t)R * 10 + PTG_SWAP_SLOTS * 3) + sizeof(int) * ((size_t)R * 5 + PTG_SWAP_SLOTS) +
+             sizeof(long long) * (size_t)R * 2;
+  return (b + 15) & ~(size_t)15;
+}
+
+extern "C" int ptg_step(ptg_handle *h, int64_t n_steps) {
+  if (!h) return fail(PTG_EINVAL, "null handle");
+  if (!h->inited) return fail(PTG_EINVAL, "MH_chain:step: Can't step before initializing chain (chain.cc:967-971)");
+  if (n_steps < 0) return fail(PTG_EINVAL, "negative step count");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  PtgModel &m = h->m;
+  const int lpb = ladders_per_block(m);
+  const size_t smem = (size_t)lpb * ladder_shared_bytes(m.dim, m.n_rungs) + (size_t)m.n_rungs * m.n_props * sizeof(double);
+  int64_t left = n_steps;
+  while (left > 0) {
+    int chunk = (int)(left > (1 << 20) ? (1 << 20) : left);
+    cudaError_t e = cudaErrorInvalidValue;
+    switch (m.dim) {
+#define X(D) case D: e = ptg_launch_step_d##D(h->cfg.rng_mode, m, h->s, h->istep, chunk, lpb, smem, h->stream); break;
+      PTG_DIM_LIST(X)
+#undef X
+    }
+    CUDA_TRY(e);
+    h->istep += chunk; left -= chunk;
+  }
+  return 0;
+}
+
+extern "C" int ptg_synchronize(ptg_handle *h) {
+  if (!h) return fail(PTG_EINVAL, "null handle");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return check_device_error(h);
+}
+
+static int ensure_scratch(ptg_handle *h, size_t bytes) {
+  if (bytes <= h->scratch_bytes) return 0;
+  void *p = nullptr;
+  CUDA_TRY(cudaMalloc(&p, bytes));
+  h->allocs.push_back(p); h->d_scratch = (double *)p; h->scratch_bytes = bytes;
+  return 0;
+}
+
+extern "C" int ptg_step_host(ptg_handle *h, int64_t n_steps, int32_t n_out, double *x_out, double *lpost_out, double *llike_out) {
+  int rc = ptg_step(h, n_steps); if (rc) return rc;
+  if (n_out <= 0) return ptg_synchronize(h);
+  if (!x_out || !lpost_out || !llike_out) return fail(PTG_EINVAL, "null output");
+  PtgModel &m = h->m;
+  const long long total = (long long)m.n_ladders * n_out;
+  rc = ensure_scratch(h, (size_t)total * (m.dim + 2) * sizeof(double)); if (rc) return rc;
+  double *dx = h->d_scratch, *dlp = dx + total * m.dim, *dll = dlp + total;
+  ptg_gather_cold_kernel<<<grid_for(total), 256, 0, h->stream>>>(m, h->s, n_out, dx, dlp, dll);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(x_out, dx, (size_t)total * m.dim * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(lpost_out, dlp, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(llike_out, dll, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  return ptg_synchronize(h);
+}
+
+// ------------------------------------------------------------------------------------------------- read-back
+template <typename T>
+static int d2h(ptg_handle *h, T *dst, const T *src, size_t n) {
+  if (!dst) return 0;
+  CUDA_TRY(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+  return 0;
+}
+
+extern "C" int ptg_get_current(ptg_handle *h, double *x, double *lpost, double *llike, double *beta) {
+  if (!h) return fail(PTG_EINVAL, "null handle");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const size_t n = (size_t)h->m.n_chains, d = (size_t)h->m.dim;
+  std::vector<double> tmp;
+  if (x) { tmp.resize(n * d); int rc = d2h(h, tmp.data(), h->s.cur_x, n * d); if (rc) return rc; }
+  int rc = d2h(h, lpost, h->s.lpost, n); if (rc) return rc;
+  rc = d2h(h, llike, h->s.llike, n); if (rc) return rc;
+  rc = d2h(h, beta, h->s.beta, n); if (rc) return rc;
+  rc = ptg_synchronize(h); if (rc) return rc;
+  if (x) for (size_t c = 0; c < n; c++) for (size_t k = 0; k < d; k++) x[c * d + k] = tmp[k * n + c]; // [dim][chain] -> [chain][dim]
+  return 0;
+}
+
+extern "C" int ptg_get_lprior(ptg_handle *h, double *lprior) {
+  if (!h || !lprior) return fail(PTG_EINVAL, "null argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  int rc = d2h(h, lprior, h->s.lprior, (size_t)h->m.n_chains); if (rc) return rc;
+  return ptg_synchronize(h);
+}
+
+extern "C" int ptg_set_current(ptg_handle *h, const double *x, const double *lpost, const double *llike, const double *lprior) {
+  if (!h || !x || !lpost || !llike || !lprior) return fail(PTG_EINVAL, "null argument");
+  if (!h->inited) return fail(PTG_EINVAL, "not initialised");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const size_t n = (size_t)h->m.n_chains, d = (size_t)h->m.dim;
+  // x arrives [chain][dim]; the device layout is [dim][chain]: transpose on the device from a staged copy
+  int rc = ensure_scratch(h, n * d * sizeof(double)); if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(h->d_scratch, x, n * d * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  ptg_transpose_kernel<<<grid_for((long long)(n * d)), 256, 0, h->stream>>>(h->d_scratch, h->s.cur_x, (long long)n, (int)d);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(h->s.lpost, lpost, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->s.llike, llike, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->s.lprior, lprior, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+
+extern "C" int ptg_get_counters(ptg_handle *h, int64_t *nhist, int64_t *nsize, int64_t *ntries, int64_t *naccept, int32_t *last_type, double *map_lpost) {
+  if (!h) return fail(PTG_EINVAL, "null handle");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const size_t n = (size_t)h->m.n_chains;
+  int rc = 0;
+  rc |= d2h(h, (long long *)nhist, h->s.nhist, n); rc |= d2h(h, (long long *)nsize, h->s.nsize, n);
+  rc |= d2h(h, (long long *)ntries, h->s.ntries, n); rc |= d2h(h, (long long *)naccept, h->s.naccept, n);
+  rc |= d2h(h, last_type, h->s.last_type, n); rc |= d2h(h, map_lpost, h->s.map_lpost, n);
+  if (rc) return rc;
+  return ptg_synchronize(h);
+}
+
+extern "C" int ptg_get_history(ptg_handle *h, int32_t ladder, int32_t rung, int64_t first, int64_t count,
+                               double *x, double *lpost, double *llike, double *acc, double *beta, int32_t *type) {
+  if (!h) return fail(PTG_EINVAL, "null handle");
+  PtgModel &m = h->m;
+  if (ladder < 0 || ladder >= m.n_ladders || rung < 0 || rung >= m.n_rungs) return fail(PTG_EINVAL, "bad chain (%d,%d)", ladder, rung);
+  if ((acc || beta || type) && !m.record_full) return fail(PTG_EINVAL, "acc/beta/type need record_level = PTG_RECORD_FULL");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const long long c = (long long)ladder * m.n_rungs + rung;
+  long long nsize = 0;
+  CUDA_TRY(cudaMemcpyAsync(&nsize, h->s.nsize + c, sizeof(nsize), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (first < 0 || count < 0 || first + count > nsize) return fail(PTG_EINVAL, "history range [%lld,%lld) outside [0,%lld)", (long long)first, (long long)(first + count), nsize);
+  if (nsize - first > m.hist_cap) return fail(PTG_EINVAL, "history element %lld already overwritten (ring capacity %d)", (long long)first, m.hist_cap);
+  if (count == 0) return 0;
+  const int D = m.dim;
+  std::vector<double> rec((size_t)count * (D + 2));
+  // the range may wrap around the ring: at most two contiguous pieces
+  long long p0 = first % m.hist_cap, n0 = (p0 + count <= m.hist_cap) ? count : m.hist_cap - p0;
+  const double *base = h->s.hist + c * m.hist_cap * (D + 2);
+  CUDA_TRY(cudaMemcpyAsync(rec.data(), base + p0 * (D + 2), (size_t)n0 * (D + 2) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (n0 < count) CUDA_TRY(cudaMemcpyAsync(rec.data() + n0 * (D + 2), base, (size_t)(count - n0) * (D + 2) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  auto piece = [&](auto *dst, const auto *src) -> int {
+    if (!dst) return 0;
+    CUDA_TRY(cudaMemcpyAsync(dst, src + c * m.hist_cap + p0, (size_t)n0 * sizeof(*dst), cudaMemcpyDeviceToHost, h->stream));
+    if (n0 < count) CUDA_TRY(cudaMemcpyAsync(dst + n0, src + c * m.hist_cap, (size_t)(count - n0) * sizeof(*dst), cudaMemcpyDeviceToHost, h->stream));
+    return 0;
+  };
+  int rc = 0;
+  if (m.record_full) { rc |= piece(acc, h->s.hist_acc); rc |= piece(beta, h->s.hist_beta); rc |= piece(type, h->s.hist_type); }
+  if (rc) return rc;
+  rc = ptg_synchronize(h); if (rc) return rc;
+  for (long long k = 0; k < count; k++) {
+    if (x) for (int i = 0; i < D; i++) x[k * D + i] = rec[k * (D + 2) + i];
+    if (lpost) lpost[k] = rec[k * (D + 2) + D];
+    if (llike) llike[k] = rec[k * (D + 2) + D + 1];
+  }
+  return 0;
+}
+
+extern "C" int ptg_get_swap_stats(ptg_handle *h, int64_t *swap_count, int64_t *swap_accept, int32_t *directions, int32_t *ups, int32_t *downs, int32_t *instances) {
+  if (!h) return fail(PTG_EINVAL, "null handle");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const size_t n = (size_t)h->m.n_chains;
+  const int R = h->m.n_rungs, L = h->m.n_ladders;
+  std::vector<long long> sc(n), sa(n);
+  int rc = 0;
+  rc |= d2h(h, sc.data(), h->s.swap_count, n); rc |= d2h(h, sa.data(), h->s.swap_accept, n);
+  rc |= d2h(h, directions, h->s.directions, n); rc |= d2h(h, ups, h->s.ups, n); rc |= d2h(h, downs, h->s.downs, n); rc |= d2h(h, instances, h->s.instances, n);
+  if (rc) return rc;
+  rc = ptg_synchronize(h); if (rc) return rc;
+  for (int l = 0; l < L; l++)
+    for (int r = 0; r < R - 1; r++) {
+      if (swap_count) swap_count[(size_t)l * (R - 1) + r] = sc[(size_t)l * R + r];
+      if (swap_accept) swap_accept[(size_t)l * (R - 1) + r] = sa[(size_t)l * R + r];
+    }
+  return 0;
+}
+
+extern "C" int ptg_get_trace(ptg_handle *h, int64_t first, int64_t count, double *lhr, int32_t *code) {
+  if (!h) return fail(PTG_EINVAL, "null handle");
+  if (first < 0 || count < 0 || first + count > h->cfg.trace_steps || first + count > h->istep) return fail(PTG_EINVAL, "trace range");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const size_t n = (size_t)h->m.n_chains;
+  int rc = 0;
+  rc |= d2h(h, lhr, h->s.trace_lhr + (size_t)first * n, (size_t)count * n);
+  rc |= d2h(h, code, h->s.trace_code + (size_t)first * n, (size_t)count * n);
+  if (rc) return rc;
+  return ptg_synchronize(h);
+}
+
+extern "C" int ptg_get_total_steps(ptg_handle *h, int64_t *total) {
+  if (!h || !total) return fail(PTG_EINVAL, "null argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  int rc = ensure_scratch(h, sizeof(unsigned long long)); if (rc) return rc;
+  CUDA_TRY(cudaMemsetAsync(h->d_scratch, 0, sizeof(unsigned long long), h->stream));
+  ptg_sum_nhist_kernel<<<grid_for(h->m.n_chains), 256, 0, h->stream>>>(h->s.nhist, h->m.n_chains, (unsigned long long *)h->d_scratch);
+  CUDA_TRY(cudaGetLastError());
+  unsigned long long v = 0;
+  CUDA_TRY(cudaMemcpyAsync(&v, h->d_scratch, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+  rc = ptg_synchronize(h); if (rc) return rc;
+  *total = (int64_t)v;
+  return 0;
+}
+
+extern "C" int ptg_get_device_views(ptg_handle *h, void **hist_dev, void **cur_x_dev, void **stream, int64_t *hist_stride) {
+  if (!h) return fail(PTG_EINVAL, "null handle");
+  if (hist_dev) *hist_dev = h->s.hist;
+  if (cur_x_dev) *cur_x_dev = h->s.cur_x;
+  if (stream) *stream = (void *)h->stream;
+  if (hist_stride) *hist_stride = (int64_t)h->m.hist_cap * (h->m.dim + 2);
+  return 0;
+}
+
+extern "C" int ptg_set_stream(ptg_handle *h, void *cuda_stream) {
+  if (!h) return fail(PTG_EINVAL, "null handle");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (h->own_stream) cudaStreamDestroy(h->stream);
+  h->stream = (cudaStream_t)cuda_stream; h->own_stream = false;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------- checkpoint
+// One binary file: magic, config, istep, then every device array of PtgState in declaration order.
+struct CkArr { void *p; size_t bytes; };
+static std::vector<CkArr> ck_arrays(ptg_handle *h) {
+  PtgModel &m = h->m; PtgState &s = h->s;
+  const size_t n = (size_t)m.n_chains, d = (size_t)m.dim, cap = (size_t)m.hist_cap;
+  std::vector<CkArr> v = {
+      {s.cur_x, n * d * 8}, {s.lpost, n * 8}, {s.llike, n * 8}, {s.lprior, n * 8}, {s.beta, n * 8}, {s.map_lpost, n * 8}, {s.map_x, n * d * 8},
+      {s.nhist, n * 8}, {s.nsize, n * 8}, {s.ntries, n * 8}, {s.naccept, n * 8}, {s.last_type, n * 4}, {s.hist, n * cap * (d + 2) * 8},
+      {s.swap_count, n * 8}, {s.swap_accept, n * 8}, {s.directions, n * 4}, {s.ups, n * 4}, {s.downs, n * 4}, {s.instances, n * 4},
+      {s.u_pos, (n + m.n_ladders) * 8}, {s.z_pos, (n + m.n_ladders) * 8}};
+  if (m.record_full) { v.push_back({s.hist_acc, n * cap * 8}); v.push_back({s.hist_beta, n * cap * 8}); v.push_back({s.hist_type, n * cap * 4}); }
+  return v;
+}
+extern "C" int ptg_checkpoint(ptg_handle *h, const char *path) {
+  if (!h || !path) return fail(PTG_EINVAL, "null argument");
+  if (!h->inited) return fail(PTG_EINVAL, "not initialised");
+  int rc = ptg_synchronize(h); if (rc) return rc;
+  FILE *f = fopen(path, "wb");
+  if (!f) return fail(PTG_EINVAL, "cannot open %s", path);
+  const uint64_t magic = 0x70746763686b3031ull; // "ptgchk01"
+  fwrite(&magic, 8, 1, f); fwrite(&h->cfg, sizeof(h->cfg), 1, f); fwrite(&h->istep, 8, 1, f); fwrite(&h->m.hist_cap, 4, 1, f);
+  std::vector<char> buf;
+  for (const CkArr &a : ck_arrays(h)) {
+    buf.resize(a.bytes);
+    cudaError_t e = cudaMemcpy(buf.data(), a.p, a.bytes, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { fclose(f); return fail(PTG_ECUDA, "checkpoint copy: %s", cudaGetErrorString(e)); }
+    uint64_t nb = a.bytes; fwrite(&nb, 8, 1, f); fwrite(buf.data(), 1, a.bytes, f);
+  }
+  fclose(f);
+  return 0;
+}
+extern "C" int ptg_restore(ptg_handle *h, const char *path) {
+  if (!h || !path) return fail(PTG_EINVAL, "null argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  if (!h->model_uploaded) { int rc = upload_model(h); if (rc) return rc; }
+  FILE *f = fopen(path, "rb");
+  if (!f) return fail(PTG_EINVAL, "cannot open %s", path);
+  uint64_t magic = 0; ptg_config c; long long istep = 0; int32_t cap = 0;
+  bool ok = fread(&magic, 8, 1, f) == 1 && fread(&c, sizeof(c), 1, f) == 1 && fread(&istep, 8, 1, f) == 1 && fread(&cap, 4, 1, f) == 1;
+  if (!ok || magic != 0x70746763686b3031ull) { fclose(f); return fail(PTG_EINVAL, "%s is not a ptg checkpoint", path); }
+  if (c.n_ladders != h->cfg.n_ladders || c.n_rungs != h->cfg.n_rungs || c.dim != h->cfg.dim || cap != h->m.hist_cap ||
+      c.record_level != h->cfg.record_level) { fclose(f); return fail(PTG_EINVAL, "checkpoint shape does not match this engine"); }
+  std::vector<char> buf;
+  for (const CkArr &a : ck_arrays(h)) {
+    uint64_t nb = 0;
+    if (fread(&nb, 8, 1, f) != 1 || nb != a.bytes) { fclose(f); return fail(PTG_EINVAL, "checkpoint array size mismatch"); }
+    buf.resize(a.bytes);
+    if (fread(buf.data(), 1, a.bytes, f) != a.bytes) { fclose(f); return fail(PTG_EINVAL, "checkpoint truncated"); }
+    cudaError_t e = cudaMemcpy(a.p, buf.data(), a.bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { fclose(f); return fail(PTG_ECUDA, "restore copy: %s", cudaGetErrorString(e)); }
+  }
+  fclose(f);
+  h->istep = istep; h->inited = true;
+  return 0;
+}

@@ -1,0 +1,34 @@
+// ptg_inst.cuh -- per-dimension instantiation of the thread-per-chain kernels (one translation unit per D so the
+// build parallelises).  PTG_INSTANTIATE(D) defines the two launchers declared in ptg_launch.h.
+#pragma once
+#include "ptg_kernels.cuh"
+#include "ptg_launch.h"
+
+template <int D, int MODE>
+static cudaError_t launch_step_t(const PtgModel &m, const PtgState &s, long long step0, int n_steps, int lpb, size_t smem, cudaStream_t st) {
+  auto k = ptg_step_kernel<D, MODE>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  int blocks = (int)((m.n_ladders + lpb - 1) / lpb);
+  k<<<blocks, lpb * m.n_rungs, smem, st>>>(m, s, step0, n_steps, lpb);
+  return cudaGetLastError();
+}
+template <int D, int MODE>
+static cudaError_t launch_init_t(const PtgModel &m, const PtgState &s, const double *init_x, cudaStream_t st) {
+  int blocks = (int)((m.n_chains + 127) / 128);
+  ptg_init_kernel<D, MODE><<<blocks, 128, 0, st>>>(m, s, init_x);
+  return cudaGetLastError();
+}
+
+#define PTG_INSTANTIATE(D)                                                                                                   \
+  cudaError_t ptg_launch_step_d##D(int mode, const PtgModel &m, const PtgState &s, long long step0, int n_steps, int lpb,    \
+                                   size_t smem, cudaStream_t st) {                                                           \
+    return mode == PTG_RNG_TAPE ? launch_step_t<D, PTG_RNG_TAPE>(m, s, step0, n_steps, lpb, smem, st)                        \
+                                : launch_step_t<D, PTG_RNG_PHILOX>(m, s, step0, n_steps, lpb, smem, st);                     \
+  }                                                                                                                          \
+  cudaError_t ptg_launch_init_d##D(int mode, const PtgModel &m, const PtgState &s, const double *init_x, cudaStream_t st) {  \
+    return mode == PTG_RNG_TAPE ? launch_init_t<D, PTG_RNG_TAPE>(m, s, init_x, st)                                           \
+                                : launch_init_t<D, PTG_RNG_PHILOX>(m, s, init_x, st);                                        \
+  }

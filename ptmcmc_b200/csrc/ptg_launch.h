@@ -1,0 +1,11 @@
+// ptg_launch.h -- launchers exported by the per-dimension translation units (ptg_inst_dN.cu)
+#pragma once
+#include <cuda_runtime.h>
+#include "ptg_types.h"
+#define PTG_DIM_LIST(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(12) X(16)
+#define PTG_DECLARE(D)                                                                                                      \
+  cudaError_t ptg_launch_step_d##D(int mode, const PtgModel &m, const PtgState &s, long long step0, int n_steps, int lpb,   \
+                                   size_t smem, cudaStream_t st);                                                           \
+  cudaError_t ptg_launch_init_d##D(int mode, const PtgModel &m, const PtgState &s, const double *init_x, cudaStream_t st);
+PTG_DIM_LIST(PTG_DECLARE)
+#undef PTG_DECLARE

@@ -1,0 +1,70 @@
+// ptg_types.h -- host/device shared plain structs of the ptg engine (no CUDA-only constructs).
+#ifndef PTG_TYPES_H
+#define PTG_TYPES_H
+#include <stdint.h>
+#include "../../include/ptmcmc_b200.h"
+
+#define PTG_TPC_MAX_DIM 16   // thread-per-chain kernels
+#define PTG_SWAP_SLOTS 32    // swap trials per PT step: maxswapsperstep = 1+2*swap_rate*Ntemps (chain.cc:1192), capped
+
+// 1-D prior factor (ProbabilityDist.h:76-257)
+struct PtgPrior1D {
+  int32_t kind, pad;
+  double a, b;         // (xmin,xmax) or (x0,sigma)
+  double norm, cdfoff; // polar/copolar
+  double la, lb;       // log
+};
+
+struct PtgProp {
+  int32_t kind, has_transform;
+  double snooker, g1frac, ignore_frac, unlikely_alpha, reduce_gamma, one_d_frac;
+  double gamma_std;           // 1.68/sqrt(d)/reduce_gamma, proposal_distribution.cc:495
+  int32_t sigma_off, trans_off; // offsets (in doubles) into Model::prop_data
+};
+
+// Everything the kernels need to know about the model; passed by value (__grid_constant__).
+struct PtgModel {
+  int32_t dim, n_rungs, n_ladders, n_props;
+  int32_t save_every, hist_cap, n_init, maxswaps;
+  int32_t swap_mode, record_full, wrap_in_set, zero_valid;
+  int32_t like_kind, n_lparams, trace_steps, all_uniform_prior;
+  int64_t n_ldata;
+  int64_t n_chains;
+  double swap_rate, dprior_min, evolve_rate, evolve_lpost_cut;
+  double like_nsum;
+  double uniform_lprior;      // log(prod 1/(b-a)) when every factor is uniform (evaluated once on the device)
+  uint64_t seed;
+  int64_t ladder_offset;
+  int32_t lower[PTG_TPC_MAX_DIM], upper[PTG_TPC_MAX_DIM];
+  double xmin[PTG_TPC_MAX_DIM], xmax[PTG_TPC_MAX_DIM];
+  PtgPrior1D prior[PTG_TPC_MAX_DIM];
+  PtgProp props[PTG_MAX_PROPOSALS];
+  const double *lparams;      // device
+  const double *ldata;        // device
+  const double *prop_data;    // device: sigmas / transforms
+  const double *bins;         // device [n_rungs][n_props] cumulative shares (reset_bins)
+};
+
+// Device-resident chain state (SoA over chains) + history + ladder statistics.
+struct PtgState {
+  double *cur_x;      // [dim][n_chains]
+  double *lpost, *llike, *lprior, *beta; // [n_chains]
+  double *map_lpost;  // [n_chains]
+  double *map_x;      // [dim][n_chains]
+  long long *nhist, *nsize, *ntries, *naccept; // [n_chains]
+  int32_t *last_type; // [n_chains]
+  double *hist;       // [n_chains][hist_cap][dim+2]  record = x[dim], lpost, llike
+  double *hist_acc, *hist_beta; // [n_chains][hist_cap] (record_full)
+  int32_t *hist_type; // [n_chains][hist_cap]        (record_full)
+  long long *swap_count, *swap_accept; // [n_ladders][n_rungs]
+  int32_t *directions, *ups, *downs, *instances; // [n_ladders][n_rungs]
+  // tapes (PTG_RNG_TAPE)
+  const double *tape_u, *tape_z;
+  long long *u_pos, *z_pos;            // [n_streams] cursors
+  const long long *u_end, *z_end;      // [n_streams]
+  // trace
+  double *trace_lhr;  // [trace_steps][n_chains]
+  int32_t *trace_code;
+  int32_t *err;       // device error flag (PTG_ETAPE, PTG_ESTUCK)
+};
+#endif

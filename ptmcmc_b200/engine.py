@@ -1,0 +1,37 @@
+"""`Engine`: one ptg handle (one GPU) behind the C ABI, numpy in / numpy out."""
+import ctypes as C
+import numpy as np
+from . import _capi as K
+from ._lib import load
+
+
+class Engine(K.CApi):
+    """The CUDA engine.  Raises if the shared library or a CUDA device is missing (no CPU fallback)."""
+
+    def __init__(self, cfg):
+        super().__init__(load(), "ptg_", cfg)
+
+    def synchronize(self):
+        self._call("synchronize", self.h)
+
+    def set_stream(self, cuda_stream_ptr):
+        self._call("set_stream", self.h, C.c_void_p(cuda_stream_ptr))
+
+    def get_lprior(self):
+        out = np.empty(self.n_chains)
+        self._call("get_lprior", self.h, K._dp(out))
+        return out
+
+    def set_current(self, x, lpost, llike, lprior):
+        x, lpost, llike, lprior = K._f64(x), K._f64(lpost), K._f64(llike), K._f64(lprior)
+        self._keep = [x, lpost, llike, lprior]  # async copy: keep the buffers alive
+        self._call("set_current", self.h, K._dp(x), K._dp(lpost), K._dp(llike), K._dp(lprior))
+
+    def step_host(self, n_steps, n_out, x_out, lpost_out, llike_out):
+        self._call("step_host", self.h, C.c_int64(n_steps), C.c_int32(n_out), K._dp(x_out), K._dp(lpost_out), K._dp(llike_out))
+
+    def checkpoint(self, path):
+        self._call("checkpoint", self.h, path.encode())
+
+    def restore(self, path):
+        self._call("restore", self.h, path.encode())
