@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py -- tempered chain-steps/s of the PT hot path (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1_sines] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" is one pass of the hot path over the whole resident batch: `--pt-steps` iterations of
+parallel_tempering_chains::step (chain.cc:1393) for every ladder on the GPU, in ONE launch of the fused step kernel.
+`value`  = tempered chain-steps (history appends = Nhist increments) of all ranks / device time (CUDA
+           events on the engine's stream, max over ranks), state resident in HBM.
+`e2e`    = the same metric through the C-ABI calls a host facade makes per block with HOST buffers inside the timed
+           region: ptg_set_current (H2D of every chain's state from pinned memory) -> ptg_step_host (steps + D2H of
+           the cold chains' newest samples).
+The reference arm (`--impl reference`) times the UNMODIFIED reference (oracle/_ref/ref_trace: our driver compiled
+against the reference sources, stepping parallel_tempering_chains through its public API) on the host cores, one
+ladder per process, all cores busy -- the only CPU parallelism that scales for this code.
+Weak scaling: every rank owns `ladders` whole ladders (ladder_offset = rank * ladders); no data-path collective.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# ---------------------------------------------------------------------------------------------------- workloads
+WORKLOADS = {
+    # BASELINE.json configs[2] / SURVEY 8d C1: sines.hh as written, d=3, ks=(2,2,2), default select_proposal mix
+    "c1_sines": dict(model="sines", dim=3, rungs=32, ladders=4096, pt_steps=1000, hist=1024, f_de=0.8, f_sn=0.1,
+                     desc="sines.hh sin^4 surface d=3, 4096 ladders x 32 rungs, default proposal mix (80% DE / 20% 6-scale Gaussian), swap_rate 0.1"),
+    # configs[1] / B: polynomial chi^2, d=5, N=1000, DE only
+    "b_poly": dict(model="poly", dim=5, rungs=16, ladders=1024, pt_steps=20, hist=1024, f_de=1.0, f_sn=0.1,
+                   desc="5-coefficient polynomial chi^2 over 1000 points, 1024 ladders x 16 rungs, DE proposals"),
+    # C2: 3-sinusoid chi^2 over 1e4 samples, d=9
+    "c2_sinusoid": dict(model="sinusoid", dim=9, rungs=32, ladders=4096, pt_steps=1, hist=512, f_de=0.8, f_sn=0.1,
+                        desc="3-sinusoid chi^2 fit to 1e4 samples d=9, 4096 ladders x 32 rungs, default proposal mix"),
+    # configs[0] / A as a throughput batch
+    "a_gauss": dict(model="gauss", dim=2, rungs=8, ladders=16384, pt_steps=1000, hist=1024, f_de=0.8, f_sn=0.1,
+                    desc="2-D isotropic Gaussian, 16384 ladders x 8 rungs, default proposal mix"),
+}
+
+
+def make_spec(w):
+    from tests.models import Spec, poly_data, sinusoid_spec
+    if w["model"] == "sines":
+        return Spec("sines", w["dim"], w["rungs"])
+    if w["model"] == "poly":
+        return Spec("poly", 5, w["rungs"], centers=np.zeros(5), halfwidths=np.full(5, 10.0), prop="de", Tmax=1e6, extra=poly_data())
+    if w["model"] == "sinusoid":
+        return sinusoid_spec(w["rungs"], n=10000)
+    if w["model"] == "gauss":
+        return Spec("gauss", 2, w["rungs"], centers=[2, -3], halfwidths=[2, 3])
+    raise ValueError(w["model"])
+
+
+def algorithmic_bytes_per_chain_step(w, save_every=1):
+    """history append 8(d+2)/s [x, lpost, llike] + DE gathers f_DE (2 + f_sn) 8 d"""
+    d = w["dim"]
+    return 8.0 * (d + 2) / save_every + w["f_de"] * (2 + w["f_sn"]) * 8.0 * d
+
+
+# ---------------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.p = index, [], None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except OSError:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.p:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(2)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), power_w_max=float(max(pw)), samples=len(sm), reasons=sorted(reasons))
+
+
+# ---------------------------------------------------------------------------------------------------- CPU reference arm
+def cpu_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference_sample(w, pt_steps, procs):
+    """`procs` independent processes, each one ladder of the workload stepped `pt_steps` times by the reference itself
+    (oracle/_ref/ref_trace) or, when that binary is absent, by the oracle port.  Returns (chain_steps, seconds, kind)."""
+    spec = make_spec(w)
+    ref = os.path.join(ROOT, "oracle", "_ref", "ref_trace")
+    if os.path.exists(ref):
+        with tempfile.TemporaryDirectory() as td:
+            cmds = []
+            for i in range(procs):
+                spec.seed = 0.05 + 0.9 * (i + 0.5) / procs
+                pd = os.path.join(td, "p%d" % i); os.makedirs(pd)
+                cmds.append([ref] + spec.ref_args(pd, pt_steps, "/dev/null"))
+            t0 = time.perf_counter()
+            ps = [subprocess.Popen(c, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True) for c in cmds]
+            outs = [p.communicate()[0] for p in ps]
+            dt = time.perf_counter() - t0
+        total = 0
+        for o, p in zip(outs, ps):
+            if p.returncode != 0:
+                raise RuntimeError("ref_trace failed")
+            total += int(o.split("total_Nhist=")[1].split()[0])
+        return total, dt, "reference"
+    import multiprocessing as mp
+    t0 = time.perf_counter()
+    with mp.get_context("spawn").Pool(procs) as pool:
+        totals = pool.map(_port_worker, [(w, pt_steps, 0.05 + 0.9 * (i + 0.5) / procs) for i in range(procs)])
+    return sum(totals), time.perf_counter() - t0, "port"
+
+
+def _port_worker(args):
+    w, pt_steps, seed = args
+    from tests.oracle_binding import Oracle
+    spec = make_spec(w)
+    o = Oracle(spec.config(n_ladders=1, rng_mode=2))
+    spec.setup(o); o.seed_newran(seed); o.init_from_prior(); o.step(pt_steps)
+    return o.get_total_steps()
+
+
+def reference_pt_steps(w, seconds=8.0):
+    """PT iterations per process for roughly `seconds` of CPU work (1.6e5 chain-steps/s/core measured for A/C1-like
+    models; chi^2 models scale with the data size)"""
+    per_chain_step = {"sines": 6e-6, "gauss": 6e-6, "poly": 1.2e-5, "sinusoid": 3e-4}[w["model"]]
+    return max(20, int(seconds / (per_chain_step * w["rungs"])))
+
+
+# ---------------------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c1_sines", choices=sorted(WORKLOADS))
+    ap.add_argument("--pt-steps", type=int, default=0, help="PT iterations per bench step (default: per workload)")
+    ap.add_argument("--ladders", type=int, default=0, help="ladders per GPU (default: per workload)")
+    ap.add_argument("--swap-mode", default="reference", choices=["reference", "even_odd"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    w = dict(WORKLOADS[args.workload])
+    if args.pt_steps: w["pt_steps"] = args.pt_steps
+    if args.ladders: w["ladders"] = args.ladders
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    config = dict(workload="%s: %s" % (args.workload, w["desc"]), ladders_per_gpu=w["ladders"], rungs=w["rungs"], dim=w["dim"],
+                  chains_per_gpu=w["ladders"] * w["rungs"], pt_iterations_per_step=w["pt_steps"], save_every=1, hist_capacity=w["hist"],
+                  swap_mode=args.swap_mode, rng="philox4x32-10", parallelism="ladders sharded, %d per GPU, no data-path collective" % w["ladders"],
+                  l2="history ring (%.1f GB per GPU) is larger than L2" % (w["ladders"] * w["rungs"] * w["hist"] * 8.0 * (w["dim"] + 2) / 1e9))
+    metric, unit = "tempered chain-steps/s", "chain-steps/s"
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        procs = cpu_threads()
+        n_pt = reference_pt_steps(w, 6.0)
+        for _ in range(min(args.warmup, 1)):
+            run_reference_sample(w, max(20, n_pt // 10), procs)
+        tot, secs = 0, 0.0
+        for _ in range(args.steps):
+            t, dt, kind = run_reference_sample(w, n_pt, procs)
+            tot += t; secs += dt
+        val = tot / secs
+        sample = "%d processes x 1 ladder x %d rungs x %d PT iterations per step" % (procs, w["rungs"], n_pt)
+        print(json.dumps(dict(metric=metric, value=val, unit=unit, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                              ms_per_step=1e3 * secs / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+                              data="synthetic", impl="reference", config=config,
+                              cpu_baseline=dict(value=val, unit=unit, cores=procs, kind=kind, sample=sample),
+                              e2e=dict(value=val, unit=unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from ptmcmc_b200 import _capi as K
+    from ptmcmc_b200.engine import Engine
+    from ptmcmc_b200.sharding import max_over_ranks, sum_over_ranks
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+
+    spec = make_spec(w)
+    L, R, d, S = w["ladders"], w["rungs"], w["dim"], w["pt_steps"]
+    swap_mode = K.SWAP_REFERENCE if args.swap_mode == "reference" else K.SWAP_EVEN_ODD
+    eng = Engine(spec.config(n_ladders=L, rng_mode=K.RNG_PHILOX, record_level=K.RECORD_BASIC, hist_capacity=w["hist"], swap_mode=swap_mode,
+                             device=local, ladder_offset=rank * L, seed=0xB2000003))
+    spec.setup(eng)
+    stream = torch.cuda.Stream()
+    eng.set_stream(stream.cuda_stream)
+    eng.init_from_prior()
+    eng.synchronize()
+
+    # ---- device-resident throughput
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            eng.step(S)
+        eng.synchronize()
+        n0 = eng.get_total_steps()
+        clocks = ClockSampler(local); clocks.start()
+        barrier(); torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(args.steps):
+            eng.step(S)
+        ev1.record(stream)
+        torch.cuda.synchronize(); barrier()
+        ms = ev0.elapsed_time(ev1)
+        clk = clocks.stop()
+        eng.synchronize()
+        n1 = eng.get_total_steps()
+    ms_max = max_over_ranks(ms)
+    chain_steps = sum_over_ranks(n1 - n0)
+    value = chain_steps / (ms_max * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers
+    n_chains = L * R
+    n_out = min(S, 64)
+    pin = lambda *shape: torch.empty(*shape, dtype=torch.float64).pin_memory().numpy()
+    hx, hlp, hll, hpr = pin(n_chains, d), pin(n_chains), pin(n_chains), pin(n_chains)
+    ox, olp, oll = pin(L, n_out, d), pin(L, n_out), pin(L, n_out)
+    cur = eng.get_current(); hx[:] = cur["x"]; hlp[:] = cur["lpost"]; hll[:] = cur["llike"]; hpr[:] = eng.get_lprior()
+    e2e_steps = max(3, min(args.steps, 10))
+    with torch.cuda.stream(stream):
+        for _ in range(2):
+            eng.set_current(hx, hlp, hll, hpr); eng.step_host(S, n_out, ox, olp, oll)
+        m0 = eng.get_total_steps()
+        barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter(); ev0.record(stream)
+        for _ in range(e2e_steps):
+            eng.set_current(hx, hlp, hll, hpr)
+            eng.step_host(S, n_out, ox, olp, oll)
+        ev1.record(stream); torch.cuda.synchronize(); barrier()
+        e2e_ms = max(ev0.elapsed_time(ev1), 1e3 * (time.perf_counter() - t0))
+        m1 = eng.get_total_steps()
+    e2e_val = sum_over_ranks(m1 - m0) / (max_over_ranks(e2e_ms) * 1e-3)
+    h2d = n_chains * (d + 3) * 8
+    d2h = L * n_out * (d + 2) * 8
+
+    # ---- roofline of the dominant kernel (ptg_step_kernel: one launch per bench step)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    bpcs = algorithmic_bytes_per_chain_step(w)
+    launch_s = ms * 1e-3 / args.steps
+    achieved = bpcs * ((n1 - n0) / args.steps) / launch_s / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.workload)
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic, kernel="ptg_step_kernel",
+                    algorithmic_bytes_per_chain_step=bpcs, chain_steps_per_launch=(n1 - n0) / args.steps, launch_ms=launch_s * 1e3, peak_source=peak_src,
+                    note="latency/ALU-bound fp64+Philox kernel: HBM is the stated roofline, see DESIGN.md section 5")
+
+    out = dict(metric=metric, value=value, unit=unit, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_max / args.steps,
+               higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", config=config, clocks=clk,
+               e2e=dict(value=e2e_val, unit=unit, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=e2e_steps),
+               gpu_launches=args.steps, roofline=roofline)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        procs = cpu_threads()
+        n_pt = reference_pt_steps(w, 10.0)
+        tot, secs, kind = run_reference_sample(w, n_pt, procs)
+        out["cpu_baseline"] = dict(value=tot / secs, unit=unit, cores=procs, kind=kind,
+                                   sample="%d processes x 1 ladder x %d rungs x %d PT iterations of the same workload" % (procs, R, n_pt))
+    if rank == 0:
+        print(json.dumps(out))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

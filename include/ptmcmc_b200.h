@@ -139,6 +139,11 @@ int ptg_seed(ptg_handle *h, uint64_t seed);
  * streams n_chains..n_chains+n_ladders-1 the ladders' (parallel_tempering_chains is itself a chain).
  * u_off/z_off have n_streams+1 entries; the tapes are copied to the device. */
 int ptg_inject_tapes(ptg_handle *h, const double *u, const int64_t *u_off, const double *z, const int64_t *z_off);
+/* optional: absolute tape cursors of every stream at the start of PT step s, [n_steps][n_streams] each.  The engine
+ * re-synchronises to them at every step boundary, so a last-ulp libm difference that changes how many draws one
+ * step CONSUMES (e.g. lhr = -1e-21 vs 0: same decision, one acceptance draw fewer; chain.cc:998-1001) stays local
+ * to that step instead of shifting the rest of the tape. */
+int ptg_inject_tape_marks(ptg_handle *h, int64_t n_steps, const int64_t *u_mark, const int64_t *z_mark);
 
 /* initialisation: MH_chain::initialize (chain.cc:846-876) ------------------------------------------- */
 int ptg_init_from_prior(ptg_handle *h);
@@ -151,6 +156,11 @@ int ptg_synchronize(ptg_handle *h);
 /* same, end-to-end with host buffers: steps, then copies the cold chains' newest `n_out` stored samples
  * of every ladder to host memory x_out[n_ladders][n_out][dim], lpost_out/llike_out[n_ladders][n_out] */
 int ptg_step_host(ptg_handle *h, int64_t n_steps, int32_t n_out, double *x_out, double *lpost_out, double *llike_out);
+
+/* the device functors applied to caller-provided states x[n][dim] (host): log-likelihood (the batched form of
+ * bayes_likelihood::evaluate_log, bayesian.hh:553-581) and log-prior after boundary enforcement
+ * (probability_function.hh:59, states.cc:161-166).  Either output may be NULL.  Needs prior+likelihood+proposals set. */
+int ptg_eval(ptg_handle *h, const double *x, int64_t n, double *loglike, double *logprior);
 
 /* read-back: chain::getState/getLogPost/getLogLike/invTemp (chain.hh:86-124) ---------------------------- */
 int ptg_get_current(ptg_handle *h, double *x, double *lpost, double *llike, double *beta);

@@ -82,6 +82,7 @@ struct pto_handle {
   double *trace_lhr; int32_t *trace_code;
   int record, tape_err;
   double *tape_u, *tape_z; /* owned copies */
+  int64_t *mark_u, *mark_z, n_marks, cap_marks; /* per PT step: draws each stream had consumed when the step began */
 };
 
 /* ---------------------------------------------------------------------------------------------- streams */
@@ -434,6 +435,25 @@ static void de_draw_snooker(pto_handle *h, chain_t *c, const prop_t *p, uint64_t
   r->valid = h->zero_valid;
 }
 
+/* `vec = diagTransform*vec` (proposal_distribution.hh:212) is Eigen 3.3.7's column-major dense GEMV
+ * (Eigen/src/Core/products/GeneralMatrixVector.h): the result starts at zero, columns are consumed four at a time as
+ * res += (a0 v0 + a1 v1) + (a2 v2 + a3 v3) for packet-aligned rows, and the leftover columns one at a time.  With
+ * SSE2 packets of two doubles and 16-byte-aligned heap storage every row of an even-dimensional problem takes the
+ * packet path; an odd trailing row takes the scalar path res += a0 v0; res += a1 v1; ... (same four-column blocks). */
+static void eigen_gemv(const double *M, const double *v, double *t, int d) {
+  const int cb = (d / 4) * 4, even_rows = d & ~1;
+  for (int i = 0; i < d; i++) {
+    const double *a = M + (size_t)i * d;
+    double acc = 0;
+    for (int j = 0; j < cb; j += 4) {
+      if (i < even_rows) acc = acc + ((a[j] * v[j] + a[j + 1] * v[j + 1]) + (a[j + 2] * v[j + 2] + a[j + 3] * v[j + 3]));
+      else { acc = a[j] * v[j] + acc; acc = a[j + 1] * v[j + 1] + acc; acc = a[j + 2] * v[j + 2] + acc; acc = a[j + 3] * v[j + 3] + acc; }
+    }
+    for (int j = cb; j < d; j++) acc += a[j] * v[j];
+    t[i] = acc;
+  }
+}
+
 /* gaussian_prop::draw (proposal_distribution.hh:194-218) */
 static void gauss_draw(pto_handle *h, chain_t *c, const prop_t *p, uint64_t step, double *prop, draw_result_t *r) {
   const int d = h->d;
@@ -449,11 +469,7 @@ static void gauss_draw(pto_handle *h, chain_t *c, const prop_t *p, uint64_t step
   } else r->type = 0;
   if (p->transform) { /* vec = diagTransform*vec */
     double t[PTG_MAX_DIM];
-    for (int i = 0; i < d; i++) {
-      double acc = 0;
-      for (int j = 0; j < d; j++) acc += p->transform[(size_t)i * d + j] * off[j];
-      t[i] = acc;
-    }
+    eigen_gemv(p->transform, off, t, d);
     memcpy(off, t, (size_t)d * sizeof(double));
   }
   for (int i = 0; i < d; i++) prop[i] = c->x[i] + off[i];
@@ -748,7 +764,7 @@ int pto_destroy(pto_handle *h) {
   for (int i = 0; i < h->nprops; i++) { free(h->props[i].sigmas); free(h->props[i].transform); }
   free(h->chains); free(h->lstreams); free(h->lparams); free(h->ldata); free(h->betas0);
   free(h->swap_count); free(h->swap_accept); free(h->directions); free(h->ups); free(h->downs); free(h->instances);
-  free(h->trace_lhr); free(h->trace_code); free(h->tape_u); free(h->tape_z);
+  free(h->trace_lhr); free(h->trace_code); free(h->tape_u); free(h->tape_z); free(h->mark_u); free(h->mark_z);
   free(h);
   return 0;
 }
@@ -877,6 +893,15 @@ int pto_get_tapes(pto_handle *h, double *u, double *z) {
   return 0;
 }
 
+/* per-stream draw counts at the start of each recorded PT step, [n_marks][n_streams]; pass NULLs to query n_marks */
+int pto_get_tape_marks(pto_handle *h, int64_t *n_marks, int64_t *u_mark, int64_t *z_mark) {
+  const int64_t ns = h->nchains + h->L;
+  if (n_marks) *n_marks = h->n_marks;
+  if (u_mark && h->n_marks) memcpy(u_mark, h->mark_u, (size_t)h->n_marks * ns * sizeof(int64_t));
+  if (z_mark && h->n_marks) memcpy(z_mark, h->mark_z, (size_t)h->n_marks * ns * sizeof(int64_t));
+  return 0;
+}
+
 static int finish_init(pto_handle *h) {
   for (int64_t i = 0; i < h->nchains; i++) {
     chain_t *c = &h->chains[i];
@@ -937,6 +962,19 @@ int pto_init_states(pto_handle *h, const double *x) {
 int pto_step(pto_handle *h, int64_t n_steps) {
   if (!h->inited) return fail(PTG_EINVAL, "not initialised");
   for (int64_t s = 0; s < n_steps; s++) {
+    if (h->record) {
+      const int64_t ns = h->nchains + h->L;
+      if (h->n_marks == h->cap_marks) {
+        h->cap_marks = h->cap_marks ? 2 * h->cap_marks : 256;
+        h->mark_u = (int64_t *)realloc(h->mark_u, (size_t)h->cap_marks * ns * sizeof(int64_t));
+        h->mark_z = (int64_t *)realloc(h->mark_z, (size_t)h->cap_marks * ns * sizeof(int64_t));
+      }
+      for (int64_t k = 0; k < ns; k++) {
+        stream_t *st = k < h->nchains ? &h->chains[k].rng : &h->lstreams[k - h->nchains];
+        h->mark_u[h->n_marks * ns + k] = st->nu; h->mark_z[h->n_marks * ns + k] = st->nz;
+      }
+      h->n_marks++;
+    }
     for (int l = 0; l < h->L; l++) { int rc = pt_step_ladder(h, l); if (rc) return rc; }
     h->istep++;
   }

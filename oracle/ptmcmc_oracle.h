@@ -37,6 +37,8 @@ int pto_inject_tapes(pto_handle *h, const double *u, const int64_t *u_off, const
 int pto_record_tapes(pto_handle *h, int on);
 int pto_get_tape_sizes(pto_handle *h, int64_t *u_count, int64_t *z_count); /* [n_streams] each */
 int pto_get_tapes(pto_handle *h, double *u, double *z);                    /* concatenated in stream order */
+/* draws each stream had consumed when each recorded PT step began, [n_marks][n_streams]; NULL arrays = query n_marks */
+int pto_get_tape_marks(pto_handle *h, int64_t *n_marks, int64_t *u_mark, int64_t *z_mark);
 int pto_init_from_prior(pto_handle *h);
 int pto_init_states(pto_handle *h, const double *x);
 int pto_step(pto_handle *h, int64_t n_steps);

@@ -352,6 +352,20 @@ extern "C" int ptg_inject_tapes(ptg_handle *h, const double *u, const int64_t *u
   return 0;
 }
 
+extern "C" int ptg_inject_tape_marks(ptg_handle *h, int64_t n_steps, const int64_t *u_mark, const int64_t *z_mark) {
+  if (!h || !u_mark || !z_mark || n_steps < 1) return fail(PTG_EINVAL, "bad argument");
+  if (h->cfg.rng_mode != PTG_RNG_TAPE || !h->s.tape_u) return fail(PTG_EINVAL, "inject the tapes first");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const size_t cnt = (size_t)n_steps * ((size_t)h->m.n_chains + h->m.n_ladders);
+  long long *du = nullptr, *dz = nullptr;
+  if (dev_alloc(h, &du, cnt, false) || dev_alloc(h, &dz, cnt, false)) return PTG_ENOMEM;
+  CUDA_TRY(cudaMemcpyAsync(du, u_mark, cnt * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(dz, z_mark, cnt * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->s.u_mark = du; h->s.z_mark = dz; h->s.n_mark_steps = n_steps;
+  return 0;
+}
+
 // proposal_distribution_set::reset_bins (proposal_distribution.cc:37-59): run once by the constructor (no chain yet,
 // Tfac = 0) and once more by set_chain on each rung's clone (proposal_distribution.hh:336)
 static void compute_bins(const ptg_handle *h, double beta, double *bin_max) {
@@ -429,6 +443,7 @@ static int upload_model(ptg_handle *h) {
   return 0;
 }
 
+static int ensure_scratch(ptg_handle *h, size_t bytes);
 static int check_device_error(ptg_handle *h) {
   int32_t e = 0;
   CUDA_TRY(cudaMemcpyAsync(&e, h->s.err, sizeof(e), cudaMemcpyDeviceToHost, h->stream));
@@ -543,6 +558,30 @@ extern "C" int ptg_step_host(ptg_handle *h, int64_t n_steps, int32_t n_out, doub
   CUDA_TRY(cudaMemcpyAsync(lpost_out, dlp, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaMemcpyAsync(llike_out, dll, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   return ptg_synchronize(h);
+}
+
+// batched device evaluation of the likelihood functor / the prior at caller-provided states x[n][dim]
+extern "C" int ptg_eval(ptg_handle *h, const double *x, int64_t n, double *loglike, double *logprior) {
+  if (!h || !x || n < 0) return fail(PTG_EINVAL, "bad argument");
+  if (n == 0) return 0;
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  if (!h->model_uploaded) { int rc = upload_model(h); if (rc) return rc; }
+  PtgModel &m = h->m;
+  const size_t d = (size_t)m.dim;
+  int rc = ensure_scratch(h, (size_t)n * (d + 2) * sizeof(double)); if (rc) return rc;
+  double *dx = h->d_scratch, *dll = dx + (size_t)n * d, *dlp = dll + n;
+  CUDA_TRY(cudaMemcpyAsync(dx, x, (size_t)n * d * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  cudaError_t e = cudaErrorInvalidValue;
+  switch (m.dim) {
+#define X(D) case D: e = ptg_launch_eval_d##D(m, dx, n, loglike ? dll : nullptr, logprior ? dlp : nullptr, h->stream); break;
+    PTG_DIM_LIST(X)
+#undef X
+  }
+  CUDA_TRY(e);
+  if (loglike) CUDA_TRY(cudaMemcpyAsync(loglike, dll, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (logprior) CUDA_TRY(cudaMemcpyAsync(logprior, dlp, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------- read-back

@@ -31,4 +31,8 @@ static cudaError_t launch_init_t(const PtgModel &m, const PtgState &s, const dou
   cudaError_t ptg_launch_init_d##D(int mode, const PtgModel &m, const PtgState &s, const double *init_x, cudaStream_t st) {  \
     return mode == PTG_RNG_TAPE ? launch_init_t<D, PTG_RNG_TAPE>(m, s, init_x, st)                                           \
                                 : launch_init_t<D, PTG_RNG_PHILOX>(m, s, init_x, st);                                        \
+  }                                                                                                                          \
+  cudaError_t ptg_launch_eval_d##D(const PtgModel &m, const double *x, long long n, double *ll, double *lp, cudaStream_t st) { \
+    ptg_eval_kernel<D><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(m, x, n, ll, lp);                                        \
+    return cudaGetLastError();                                                                                               \
   }

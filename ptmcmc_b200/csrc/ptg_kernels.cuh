@@ -228,11 +228,21 @@ __device__ __forceinline__ MhOut mh_step(const PtgModel &m, const PtgState &s, C
     if (p.has_transform) {
       const double *__restrict__ M = m.prop_data + p.trans_off;
       double t[D];
+      // summation order of Eigen 3.3.7's column-major GEMV, which is what `vec=diagTransform*vec`
+      // (proposal_distribution.hh:212) runs: four columns at a time as (a0v0+a1v1)+(a2v2+a3v3) on packet rows,
+      // sequentially on an odd trailing row, leftover columns one by one
+      constexpr int CB = (D / 4) * 4, EVEN_ROWS = D & ~1;
 #pragma unroll
       for (int i = 0; i < D; i++) {
+        const double *__restrict__ a = M + i * D;
         double acc = 0;
 #pragma unroll
-        for (int j = 0; j < D; j++) acc += __ldg(M + i * D + j) * off[j];
+        for (int j = 0; j < CB; j += 4) {
+          if (i < EVEN_ROWS) acc = acc + ((__ldg(a + j) * off[j] + __ldg(a + j + 1) * off[j + 1]) + (__ldg(a + j + 2) * off[j + 2] + __ldg(a + j + 3) * off[j + 3]));
+          else { acc = __ldg(a + j) * off[j] + acc; acc = __ldg(a + j + 1) * off[j + 1] + acc; acc = __ldg(a + j + 2) * off[j + 2] + acc; acc = __ldg(a + j + 3) * off[j + 3] + acc; }
+        }
+#pragma unroll
+        for (int j = CB; j < D; j++) acc += __ldg(a + j) * off[j];
         t[i] = acc;
       }
 #pragma unroll
@@ -343,6 +353,25 @@ __global__ void __launch_bounds__(128) ptg_init_kernel(const __grid_constant__ P
   ch.nhist = 0; ch.since_save = 0;
   chain_store<D>(m, s, ch);
   stream_close<MODE>(s, rs, c);
+}
+
+// ------------------------------------------------------------------------------------------------- batch evaluation
+// the device likelihood / prior functors applied to caller-provided states x[n][D] (row-major): the batched form of
+// bayes_likelihood::evaluate_log (bayesian.hh:553-581) and sampleable_probability_function::evaluate_log after
+// state::enforce (probability_function.hh:59, states.cc:161-166)
+template <int D>
+__global__ void __launch_bounds__(128) ptg_eval_kernel(const __grid_constant__ PtgModel m, const double *__restrict__ x, long long n,
+                                                       double *__restrict__ out_ll, double *__restrict__ out_lp) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double v[D];
+#pragma unroll
+  for (int k = 0; k < D; k++) v[k] = x[i * D + k];
+  if (out_ll) out_ll[i] = like_eval<D>(m, v);
+  if (out_lp) {
+    bool valid = space_enforce<D>(m, v);
+    out_lp[i] = prior_eval_log<D>(m, v, valid);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------- PT step
@@ -483,6 +512,15 @@ __global__ void __launch_bounds__(256) ptg_step_kernel(const __grid_constant__ P
 
   for (int it = 0; it < n_steps; it++) {
     const uint64_t step = (uint64_t)(step0 + it);
+    if constexpr (MODE == PTG_RNG_TAPE) {
+      // re-synchronise the cursors with the recorded run at every step boundary, so that a last-ulp libm difference
+      // that changes HOW MANY draws one step consumes (lhr = -1e-21 vs 0: same decision, one draw fewer) stays local
+      if (active && s.u_mark && (long long)step < s.n_mark_steps) {
+        const long long ns = m.n_chains + m.n_ladders, row = (long long)step * ns;
+        rs.upos = s.u_mark[row + chain]; rs.zpos = s.z_mark[row + chain];
+        ls.upos = s.u_mark[row + m.n_chains + ladder]; ls.zpos = s.z_mark[row + m.n_chains + ladder];
+      }
+    }
     if (active) {
       // 1. publish
 #pragma unroll

@@ -6,6 +6,7 @@
 #define PTG_DECLARE(D)                                                                                                      \
   cudaError_t ptg_launch_step_d##D(int mode, const PtgModel &m, const PtgState &s, long long step0, int n_steps, int lpb,   \
                                    size_t smem, cudaStream_t st);                                                           \
-  cudaError_t ptg_launch_init_d##D(int mode, const PtgModel &m, const PtgState &s, const double *init_x, cudaStream_t st);
+  cudaError_t ptg_launch_init_d##D(int mode, const PtgModel &m, const PtgState &s, const double *init_x, cudaStream_t st);       \
+  cudaError_t ptg_launch_eval_d##D(const PtgModel &m, const double *x, long long n, double *ll, double *lp, cudaStream_t st);
 PTG_DIM_LIST(PTG_DECLARE)
 #undef PTG_DECLARE

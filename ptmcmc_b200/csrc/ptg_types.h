@@ -62,6 +62,8 @@ struct PtgState {
   const double *tape_u, *tape_z;
   long long *u_pos, *z_pos;            // [n_streams] cursors
   const long long *u_end, *z_end;      // [n_streams]
+  const long long *u_mark, *z_mark;    // optional [n_mark_steps][n_streams]: cursor of every stream at the start of PT step s
+  long long n_mark_steps;
   // trace
   double *trace_lhr;  // [trace_steps][n_chains]
   int32_t *trace_code;

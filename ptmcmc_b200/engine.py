@@ -17,6 +17,21 @@ class Engine(K.CApi):
     def set_stream(self, cuda_stream_ptr):
         self._call("set_stream", self.h, C.c_void_p(cuda_stream_ptr))
 
+    def inject_tape_marks(self, u_mark, z_mark):
+        um = np.ascontiguousarray(u_mark, dtype=np.int64); zm = np.ascontiguousarray(z_mark, dtype=np.int64)
+        assert um.shape == zm.shape and um.shape[1] == self.n_chains + self.cfg.n_ladders
+        self._call("inject_tape_marks", self.h, C.c_int64(um.shape[0]), K._ip(um, C.c_int64), K._ip(zm, C.c_int64))
+
+    def eval_loglike(self, x):
+        x = K._f64(x).reshape(-1, self.dim); out = np.empty(len(x))
+        self._call("eval", self.h, K._dp(x), C.c_int64(len(x)), K._dp(out), None)
+        return out
+
+    def eval_logprior(self, x):
+        x = K._f64(x).reshape(-1, self.dim); out = np.empty(len(x))
+        self._call("eval", self.h, K._dp(x), C.c_int64(len(x)), None, K._dp(out))
+        return out
+
     def get_lprior(self):
         out = np.empty(self.n_chains)
         self._call("get_lprior", self.h, K._dp(out))

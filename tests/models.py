@@ -185,8 +185,9 @@ def engine_dump(api, ladder=0):
                 instances=sw["instances"][ladder])
 
 
-def compare_dumps(a, b, rtol=0.0, what="", max_report=5):
-    """bit-exact (rtol=0) or relative comparison of two dumps; returns list of mismatch strings"""
+def compare_dumps(a, b, rtol=0.0, what="", max_report=5, exact_x=True):
+    """bit-exact (rtol=0) or relative comparison of two dumps; returns list of mismatch strings.
+    exact_x: positions and acceptance ratios must be bit-identical even when rtol > 0 (tape parity)"""
     bad = []
 
     def chk(name, u, v, exact=False):
@@ -209,9 +210,9 @@ def compare_dumps(a, b, rtol=0.0, what="", max_report=5):
                 bad.append("%s rung %d %s: %r vs %r" % (what, r, k, ra[k], rb[k]))
         if ra["nsize"] != rb["nsize"]:
             continue
-        chk("rung %d x" % r, ra["x"], rb["x"], exact=True)
+        chk("rung %d x" % r, ra["x"], rb["x"], exact=exact_x)
         chk("rung %d htype" % r, ra["htype"], rb["htype"])
-        chk("rung %d hacc" % r, ra["hacc"], rb["hacc"], exact=True)
+        chk("rung %d hacc" % r, ra["hacc"], rb["hacc"], exact=exact_x)
         chk("rung %d hbeta" % r, ra["hbeta"], rb["hbeta"])
         chk("rung %d hllike" % r, ra["hllike"], rb["hllike"])
         chk("rung %d hlpost" % r, ra["hlpost"], rb["hlpost"])
@@ -220,3 +221,64 @@ def compare_dumps(a, b, rtol=0.0, what="", max_report=5):
     for k in ("swap_count", "swap_accept", "directions", "ups", "downs", "instances"):
         chk(k, a[k], b[k])
     return bad[:max_report] if max_report else bad
+
+
+# ---------------------------------------------------------------------------------------------------- named cases
+def poly_data(n=1000, d=5, seed=5):
+    """config B: x_k = -10 + 0.02 (k + 1/2), truth c ~ U(-10,10)^d, unit noise"""
+    rng = np.random.default_rng(seed)
+    xs = -10 + 0.02 * (np.arange(n) + 0.5)
+    truth = rng.uniform(-10, 10, d)
+    ys = sum(truth[j] * xs ** j for j in range(d)) + rng.normal(size=n)
+    return dict(data_x=xs, data_y=ys, data_dy=np.ones(n))
+
+
+def sinusoid_data(n=10000, dt=1e-3, seed=7):
+    """config C2: y(t) = sum_k A_k sin(2 pi f_k t + phi_k) + N(0,1)"""
+    rng = np.random.default_rng(seed)
+    t = np.arange(n) * dt
+    A, f, ph = [1, 0.7, 0.4], [1.3, 3.1, 7.7], [0.3, 1.1, 2.0]
+    y = sum(A[k] * np.sin(2 * np.pi * f[k] * t + ph[k]) for k in range(3)) + rng.normal(size=n)
+    return dict(data_x=t, data_y=y, data_dy=np.ones(n))
+
+
+def sinusoid_spec(rungs, n=10000, dt=1e-3, **kw):
+    c = np.array([1, 5, np.pi] * 3, dtype=float)
+    return Spec("sinusoid", 9, rungs, centers=c, halfwidths=c.copy(), bound="oowoowoow", extra=sinusoid_data(n, dt), **kw)
+
+
+def fullcov_spec(d, rungs, seed=100, prop="covde", **kw):
+    """config D: C = Wishart(nu = d+5, I) sample (cython/exampleGaussian.py:181-182); prior +-100 sqrt(C_ii);
+    Gaussian proposal with covariance 2.38^2/d C, eigen-rotated (exampleGaussian.py:88,95)"""
+    rng = np.random.default_rng(seed)
+    A = rng.normal(size=(d + 5, d))
+    Cm = A.T @ A
+    cinv = np.linalg.inv(Cm)
+    like0 = -0.5 * (d * np.log(2 * np.pi) + np.linalg.slogdet(Cm)[1])
+    sp = Spec("fullcov", d, rungs, centers=np.zeros(d), halfwidths=100 * np.sqrt(np.diag(Cm)), prop=prop,
+              extra=dict(cinv=cinv.ravel(), like0=like0), **kw)
+    w, V = np.linalg.eigh(2.38 ** 2 / d * Cm)
+    sp.eig = (np.sqrt(w), V)
+    sp.extra["prop_cov"] = (2.38 ** 2 / d * Cm).ravel()
+    return sp
+
+
+def parity_cases():
+    """(name, spec, steps, n_ladders): small versions of BASELINE configs A-D plus the reference's edge cases"""
+    return [
+        ("A_gauss2d_default", Spec("gauss", 2, 8, centers=[2, -3], halfwidths=[2, 3]), 1000, 3),
+        ("C1_sines_d3_R32", Spec("sines", 3, 32, seed=0.1234), 400, 2),
+        ("sines_evolve", Spec("sines", 2, 8, seed=0.012556, evolve_rate=0.01), 1500, 1),
+        ("sines_evolve_cut", Spec("sines", 2, 8, seed=0.012556, evolve_rate=0.01, evolve_lpost_cut=0.5), 1500, 2),
+        ("gauss3_de_save3", Spec("gauss", 3, 6, centers=[2, -3, 5], halfwidths=[2, 3, 5], prop="de", save_every=3), 1500, 1),
+        ("wrap", Spec("gauss", 2, 5, centers=[2, -3], halfwidths=[2, 3], bound="w", extra=dict(sigma=3.0)), 1000, 1),
+        ("reflect", Spec("gauss", 2, 5, centers=[2, -3], halfwidths=[2, 3], bound="r", extra=dict(sigma=3.0)), 1000, 1),
+        ("limit_gauss", Spec("gauss", 3, 6, centers=[2, -3, 5], halfwidths=[2, 3, 5], prop="gauss", bound="l"), 1000, 1),
+        ("prior_draw_mixed", Spec("gauss", 2, 5, centers=[2, -3], halfwidths=[2, 3], prop="prior", prior="mixed", prior_types=[1, 2]), 1000, 1),
+        ("gaussian_prior", Spec("gauss", 4, 4, centers=[0, 1, 2, 3], halfwidths=[1, 2, 3, 4], prior="gaussian", Tmax=100, extra=dict(sigma=0.7)), 800, 1),
+        ("unlikely_alpha", Spec("gauss", 2, 5, centers=[2, -3], halfwidths=[2, 3], extra=dict(de_unlikely_alpha=0.5)), 1000, 1),
+        ("single_MH_chain", Spec("sines", 2, 1, prop="de", seed=0.1234), 2000, 2),
+        ("B_poly", Spec("poly", 5, 4, centers=np.zeros(5), halfwidths=np.full(5, 10.0), prop="de", Tmax=1e6, extra=poly_data()), 200, 1),
+        ("C2_sinusoid", sinusoid_spec(4, n=500, dt=0.02), 150, 1),
+        ("D_fullcov_d6", fullcov_spec(6, 4, Tmax=100), 800, 1),
+    ]

@@ -42,6 +42,15 @@ class Oracle(K.CApi):
         z_off = np.concatenate([[0], np.cumsum(zc)]).astype(np.int64)
         return u[:int(uc.sum())], u_off, z[:int(zc.sum())], z_off
 
+    def get_tape_marks(self):
+        """draws each stream had consumed at the start of every recorded PT step: (u_mark, z_mark), [n_steps][n_streams]"""
+        ns = self.n_chains + self.cfg.n_ladders
+        n = C.c_int64()
+        self._call("get_tape_marks", self.h, C.byref(n), None, None)
+        um = np.zeros((max(n.value, 1), ns), dtype=np.int64); zm = np.zeros_like(um)
+        self._call("get_tape_marks", self.h, None, K._ip(um, C.c_int64), K._ip(zm, C.c_int64))
+        return um[:n.value], zm[:n.value]
+
     def eval_loglike(self, x):
         x = K._f64(x).reshape(-1, self.dim); out = np.empty(len(x))
         self._call("eval_loglike", self.h, K._dp(x), C.c_int64(len(x)), K._dp(out)); return out

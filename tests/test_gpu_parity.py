@@ -1,0 +1,127 @@
+"""Parity tests proper: the CUDA engine (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Tape parity = BASELINE.json's correctness bar (1): given identical injected uniform / normal draws, accept / reject and
+swap decisions, proposal types, history indices and positions are bit-exact with the reference (whose RNG the oracle
+restates and whose histories the oracle reproduces bit for bit, tests/test_oracle_ref.py); log-likelihoods and
+log-posteriors agree to 1e-12 relative."""
+import os
+import numpy as np
+import pytest
+from ptmcmc_b200 import _capi as K
+from tests.models import Spec, parity_cases, poly_data, sinusoid_spec, fullcov_spec, engine_dump, compare_dumps
+from tests.parity import tape_parity, philox_parity, RTOL
+
+pytestmark = pytest.mark.gpu
+CASES = parity_cases()
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("name,spec,steps,L", CASES, ids=[c[0] for c in CASES])
+def test_tape_parity(name, spec, steps, L, oracle_cls, engine_cls):
+    assert tape_parity(oracle_cls, engine_cls, spec, steps, L, what=name) == []
+
+
+@pytest.mark.parametrize("name,spec,steps,L", CASES, ids=[c[0] for c in CASES])
+def test_philox_consistency(name, spec, steps, L, oracle_cls, engine_cls):
+    assert philox_parity(oracle_cls, engine_cls, spec, min(steps, 400), L, what=name) == []
+
+
+@pytest.mark.parametrize("name", ["A_gauss2d_default", "C1_sines_d3_R32", "sines_evolve_cut", "B_poly", "D_fullcov_d6"])
+def test_engine_matches_golden_reference_histories(name, oracle_cls, engine_cls):
+    """engine (tape mode, draws recorded from the oracle's reference-RNG run) vs the COMMITTED histories of the unmodified
+    reference: cold-chain positions bit-exact, lpost / llike to 1e-12"""
+    from tests.parity import record_reference_run
+    case = [c for c in CASES if c[0] == name][0]
+    _, spec, steps, _L = case
+    g = np.load(os.path.join(GOLDEN, "ref_%s.npz" % name))
+    if spec.prop in ("cov", "covde"):
+        d = spec.dim
+        spec.eig = (g["eig"][:d].copy(), g["eig"][d:].reshape(d, d).copy())
+    cap = spec.de_ni * spec.dim + 2 * steps + 8
+    o, tapes, marks = record_reference_run(oracle_cls, spec, steps, 1, hist_capacity=cap)
+    e = engine_cls(spec.config(n_ladders=1, rng_mode=K.RNG_TAPE, hist_capacity=cap))
+    spec.setup(e); e.inject_tapes(*tapes); e.inject_tape_marks(*marks); e.init_from_prior(); e.step(steps); e.synchronize()
+    n = int(e.get_counters()["nsize"][0])
+    assert n == int(g["counters"][0, 0])
+    h = e.get_history(0, 0, 0, n)
+    assert h["x"].tobytes() == g["cold_x"].tobytes()
+    assert (h["type"] == g["cold_type"]).all()
+    assert h["acc"].tobytes() == g["cold_acc"].tobytes()
+    assert np.allclose(h["llike"], g["cold_llike"], rtol=RTOL, atol=0)
+    assert np.allclose(h["lpost"], g["cold_lpost"], rtol=RTOL, atol=0)
+    cnt = e.get_counters()
+    got = np.stack([cnt[k] for k in ("nsize", "nhist", "ntries", "naccept", "last_type")], axis=1)
+    assert (got == g["counters"]).all()
+    sw = e.get_swap_stats()
+    assert (sw["swap_count"][0] == g["swap_count"]).all() and (sw["swap_accept"][0] == g["swap_accept"]).all()
+
+
+def test_tape_parity_with_wrapping_ring(oracle_cls, engine_cls):
+    """history ring smaller than the run (H3): DE draws from the newest `capacity` samples; indices must still agree"""
+    spec = Spec("gauss", 2, 6, centers=[2, -3], halfwidths=[2, 3])
+    o_cfg = dict(hist_capacity=160)
+    from tests.parity import record_reference_run, compare_runs
+    steps, L = 900, 2
+    o, tapes, marks = record_reference_run(oracle_cls, spec, steps, L, **o_cfg)
+    g = engine_cls(spec.config(n_ladders=L, rng_mode=K.RNG_TAPE, trace_steps=steps, hist_capacity=160))
+    spec.setup(g); g.inject_tapes(*tapes); g.inject_tape_marks(*marks); g.init_from_prior(); g.step(steps); g.synchronize()
+    lo, co = o.get_trace(0, steps); lg, cg = g.get_trace(0, steps)
+    assert (co == cg).all()
+    co_, cg_ = o.get_current(), g.get_current()
+    assert co_["x"].tobytes() == cg_["x"].tobytes()
+    cnt_o, cnt_g = o.get_counters(), g.get_counters()
+    for k in ("nhist", "nsize", "ntries", "naccept", "last_type"):
+        assert (cnt_o[k] == cnt_g[k]).all()
+    # the newest 160 samples of every chain are in the ring and equal the oracle's
+    for l in range(L):
+        for r in range(6):
+            n = int(cnt_g["nsize"][l * 6 + r])
+            ho = o.get_history(l, r, n - 160, 160); hg = g.get_history(l, r, n - 160, 160)
+            assert ho["x"].tobytes() == hg["x"].tobytes()
+            assert np.allclose(ho["lpost"], hg["lpost"], rtol=RTOL, atol=0)
+    with pytest.raises(K.CApiError, match="overwritten"):
+        g.get_history(0, 0, 0, 10)
+
+
+def eval_cases():
+    rng = np.random.default_rng(11)
+    out = []
+    sp = Spec("sines", 3, 2); out.append(("sines", sp, rng.uniform(-0.2, 1.2, (4000, 3))))
+    sp = Spec("gauss", 3, 2, centers=[2, -3, 5], halfwidths=[2, 3, 5]); out.append(("gauss", sp, rng.normal(size=(4000, 3)) * 3))
+    sp = Spec("poly", 5, 2, centers=np.zeros(5), halfwidths=np.full(5, 10.0), prop="de", extra=poly_data())
+    out.append(("poly", sp, rng.uniform(-10, 10, (500, 5))))
+    sp = sinusoid_spec(2, n=10000)
+    c = np.array([1, 5, np.pi] * 3)
+    out.append(("sinusoid_N1e4", sp, rng.uniform(0, 2, (64, 9)) * c))
+    sp = fullcov_spec(16, 2); out.append(("fullcov16", sp, rng.normal(size=(2000, 16)) * 5))
+    sp = Spec("flat", 4, 2, centers=[0, 1, 2, 3], halfwidths=[1, 2, 3, 4], prior="mixed", prior_types=[1, 2, 1, 2], prop="gauss", bound="owrl")
+    out.append(("mixed_prior_bounds", sp, rng.normal(size=(4000, 4)) * 4 + 1))
+    return out
+
+
+@pytest.mark.parametrize("name,spec,x", eval_cases(), ids=[c[0] for c in eval_cases()])
+def test_device_functors_match_oracle(name, spec, x, oracle_cls, engine_cls):
+    """log-likelihoods (and log-priors after boundary enforcement) to 1e-12 relative, infinities in the same places"""
+    o = oracle_cls(spec.config(n_ladders=1)); spec.setup(o)
+    g = engine_cls(spec.config(n_ladders=1)); spec.setup(g)
+    for fo, fg in ((o.eval_loglike, g.eval_loglike), (o.eval_logprior, g.eval_logprior)):
+        a, b = fo(x), fg(x)
+        assert (np.isfinite(a) == np.isfinite(b)).all()
+        fin = np.isfinite(a)
+        assert (a[~fin] == b[~fin]).all()
+        assert np.allclose(a[fin], b[fin], rtol=RTOL, atol=1e-300)
+    # the sinusoid chi^2 over 1e4 samples sums ~1e4 terms of libm sin: tolerance is on the SUM (relative), as above
+
+
+def test_init_states_path(oracle_cls, engine_cls):
+    """ptg_init_states (chain_init_file path): caller-provided initial histories, then Philox stepping"""
+    spec = Spec("gauss", 2, 4, centers=[2, -3], halfwidths=[2, 3])
+    L, ninit = 3, 100
+    x0 = np.random.default_rng(3).uniform([0, -6], [4, 0], (L * 4 * ninit, 2))
+    runs = []
+    for cls in (oracle_cls, engine_cls):
+        e = cls(spec.config(n_ladders=L, rng_mode=K.RNG_PHILOX, trace_steps=50, hist_capacity=400))
+        spec.setup(e); e.init_states(x0); e.step(50); runs.append(e)
+    from tests.parity import compare_runs, PHILOX_RTOL
+    runs[1].synchronize()
+    assert compare_runs(runs[0], runs[1], 50, L, "init_states", rtol=PHILOX_RTOL, exact_x=False) == []

@@ -1,0 +1,137 @@
+"""Size-independent properties of the CUDA path at BASELINE.json's full sizes, plus the C-ABI error behaviour."""
+import os
+import numpy as np
+import pytest
+from ptmcmc_b200 import _capi as K
+from tests.models import Spec, engine_dump, compare_dumps
+
+pytestmark = pytest.mark.gpu
+
+
+def c1(engine_cls, L, steps, chunks=None, ladder_offset=0, cap=512, **kw):
+    """config C1 (sines.hh as written, d=3, 32 rungs, default proposal mix)"""
+    spec = Spec("sines", 3, 32)
+    e = engine_cls(spec.config(n_ladders=L, rng_mode=K.RNG_PHILOX, hist_capacity=cap, ladder_offset=ladder_offset, **kw))
+    spec.setup(e); e.init_from_prior()
+    for n in (chunks or [steps]):
+        e.step(n)
+    e.synchronize()
+    return e
+
+
+def same_ladder(a, la, b, lb, n_last=300):
+    R, ca, cb = a.cfg.n_rungs, a.get_counters(), b.get_counters()
+    for r in range(R):
+        ia, ib = la * R + r, lb * R + r
+        for k in ("nhist", "nsize", "ntries", "naccept", "last_type"):
+            assert ca[k][ia] == cb[k][ib], (k, r)
+        n = int(ca["nsize"][ia])
+        ha = a.get_history(la, r, n - n_last, n_last); hb = b.get_history(lb, r, n - n_last, n_last)
+        for k in ("x", "lpost", "llike", "acc", "beta"):
+            assert ha[k].tobytes() == hb[k].tobytes(), (k, r)
+        assert (ha["type"] == hb["type"]).all()
+
+
+def test_full_size_batch_is_invariant_to_sharding(engine_cls):
+    """BASELINE config 3 size (4096 ladders x 32 rungs = 131072 chains): ladder g of the batch is bit-identical to the
+    same ladder run alone with ladder_offset = g -- results do not depend on batch size, CTA packing or GPU count"""
+    steps = 400
+    big = c1(engine_cls, 4096, steps)
+    assert big.get_total_steps() == big.get_counters()["nhist"].sum()
+    for g in (0, 1337, 4095):
+        one = c1(engine_cls, 1, steps, ladder_offset=g)
+        same_ladder(big, g, one, 0)
+    # a shard of 512 ladders starting at global ladder 1024 == the corresponding slice of the full batch
+    shard = c1(engine_cls, 512, steps, ladder_offset=1024)
+    same_ladder(big, 1024 + 77, shard, 77)
+
+
+def test_step_chunking_and_checkpoint_roundtrip(engine_cls, tmp_path):
+    a = c1(engine_cls, 64, 300, evolve_rate=0.01)
+    b = c1(engine_cls, 64, 300, chunks=[1, 2, 97, 200], evolve_rate=0.01)
+    for l in (0, 63):
+        same_ladder(a, l, b, l)
+    # checkpoint after 120 steps, restore into a fresh engine, continue: equals the uninterrupted run
+    spec = Spec("sines", 3, 32)
+    c = c1(engine_cls, 64, 120, evolve_rate=0.01)
+    path = os.path.join(str(tmp_path), "ptg.ckpt")
+    c.checkpoint(path)
+    d = engine_cls(spec.config(n_ladders=64, rng_mode=K.RNG_PHILOX, hist_capacity=512, evolve_rate=0.01))
+    spec.setup(d); d.restore(path); d.step(180); d.synchronize()
+    for l in (0, 31, 63):
+        same_ladder(a, l, d, l)
+    assert a.get_current()["x"].tobytes() == d.get_current()["x"].tobytes()
+
+
+def test_step_host_returns_newest_cold_samples(engine_cls):
+    spec = Spec("sines", 3, 32)
+    L, nout = 256, 16
+    e = engine_cls(spec.config(n_ladders=L, rng_mode=K.RNG_PHILOX, hist_capacity=512, record_level=K.RECORD_BASIC))
+    spec.setup(e); e.init_from_prior()
+    x = np.empty((L, nout, 3)); lp = np.empty((L, nout)); ll = np.empty((L, nout))
+    e.step_host(100, nout, x, lp, ll)
+    cnt = e.get_counters()
+    for l in (0, 100, 255):
+        n = int(cnt["nsize"][l * 32])
+        h = e.get_history(l, 0, n - nout, nout, full=False)
+        assert h["x"].tobytes() == x[l].tobytes() and h["lpost"].tobytes() == lp[l].tobytes() and h["llike"].tobytes() == ll[l].tobytes()
+
+
+def test_posterior_statistics_full_size(engine_cls):
+    """sines 2x2x2 surface: peak occupation of the cold chains -> exp(-sum idx ln2) weights (testMH.cpp:186,195)"""
+    e = c1(engine_cls, 2048, 1500, cap=1024)
+    spec_d, nout = 3, 200
+    x = np.empty((2048, nout, spec_d)); lp = np.empty((2048, nout)); ll = np.empty((2048, nout))
+    e.step_host(0, nout, x, lp, ll)
+    idx = (x.reshape(-1, 3) * 2).astype(int).clip(0, 1).sum(axis=1)
+    p = np.bincount(idx, minlength=4) / idx.size
+    w = np.array([1, 3 * 0.5, 3 * 0.25, 0.125]); w /= w.sum()
+    assert np.allclose(p, w, atol=0.02), (p, w)
+
+
+def test_swap_modes_agree_statistically(engine_cls):
+    """even/odd performance mode vs the reference swap schedule: same cold-chain peak occupation"""
+    spec = Spec("sines", 3, 16, Tmax=1e4)
+    ps = []
+    for mode in (K.SWAP_REFERENCE, K.SWAP_EVEN_ODD):
+        e = engine_cls(spec.config(n_ladders=2048, rng_mode=K.RNG_PHILOX, hist_capacity=1024, swap_mode=mode, record_level=K.RECORD_BASIC))
+        spec.setup(e); e.init_from_prior()
+        nout = 200
+        x = np.empty((2048, nout, 3)); lp = np.empty((2048, nout)); ll = np.empty((2048, nout))
+        e.step_host(1500, nout, x, lp, ll)
+        idx = (x.reshape(-1, 3) * 2).astype(int).clip(0, 1).sum(axis=1)
+        ps.append(np.bincount(idx, minlength=4) / idx.size)
+    assert np.allclose(ps[0], ps[1], atol=0.02), ps
+
+
+def test_error_behaviour(engine_cls):
+    spec = Spec("gauss", 2, 4, centers=[2, -3], halfwidths=[2, 3])
+    e = engine_cls(spec.config(n_ladders=1))
+    with pytest.raises(K.CApiError, match="before initializing|initialis"):
+        e.step(1)
+    with pytest.raises(K.CApiError, match="set prior"):
+        e.init_from_prior()
+    spec.setup(e); e.init_from_prior()
+    with pytest.raises(K.CApiError, match="already initialised"):
+        e.init_from_prior()
+    # tape mode without tapes / exhausted tapes
+    t = engine_cls(spec.config(n_ladders=1, rng_mode=K.RNG_TAPE)); spec.setup(t)
+    with pytest.raises(K.CApiError, match="inject tapes"):
+        t.init_from_prior()
+    ns = 5
+    t.inject_tapes(np.full(10, 0.5), np.arange(ns + 1) * 2, np.zeros(10), np.arange(ns + 1) * 2)
+    with pytest.raises(K.CApiError, match="tape exhausted"):
+        t.init_from_prior()
+    with pytest.raises(K.CApiError, match="dim="):
+        engine_cls(K.make_config(1, 4, 11))
+
+
+def test_set_current_roundtrip(engine_cls):
+    spec = Spec("gauss", 2, 4, centers=[2, -3], halfwidths=[2, 3])
+    e = engine_cls(spec.config(n_ladders=8)); spec.setup(e); e.init_from_prior(); e.step(10)
+    cur = e.get_current(); lpr = e.get_lprior()
+    x2 = cur["x"][::-1].copy()
+    e.set_current(x2, cur["lpost"][::-1].copy(), cur["llike"][::-1].copy(), lpr[::-1].copy())
+    e.synchronize()
+    got = e.get_current()
+    assert got["x"].tobytes() == x2.tobytes() and got["llike"].tobytes() == cur["llike"][::-1].tobytes()
