@@ -153,6 +153,13 @@ int ptg_init_states(ptg_handle *h, const double *x);
 /* the hot path: n_steps iterations of parallel_tempering_chains::step for every ladder ------------------ */
 int ptg_step(ptg_handle *h, int64_t n_steps);
 int ptg_synchronize(ptg_handle *h);
+/* Kernel selection is automatic: ladders of <= 32 rungs run register-resident warp-shuffle kernels (PTG_KERNEL_FAST for
+ * Philox draws, PTG_KERNEL_WARP for tape replay), longer ladders the shared-memory kernel (PTG_KERNEL_SHARED).
+ * ptg_select_kernel pins PTG_KERNEL_WARP or PTG_KERNEL_SHARED where they apply (tests / profiling: in Philox mode all
+ * three produce bit-identical chains); ptg_get_launch_count reports how many step kernels this handle has launched. */
+enum { PTG_KERNEL_AUTO = 0, PTG_KERNEL_SHARED = 1, PTG_KERNEL_WARP = 2, PTG_KERNEL_FAST = 3 };
+int ptg_select_kernel(ptg_handle *h, int32_t kernel);
+int ptg_get_launch_count(ptg_handle *h, int64_t *n);
 /* same, end-to-end with host buffers: steps, then copies the cold chains' newest `n_out` stored samples
  * of every ladder to host memory x_out[n_ladders][n_out][dim], lpost_out/llike_out[n_ladders][n_out] */
 int ptg_step_host(ptg_handle *h, int64_t n_steps, int32_t n_out, double *x_out, double *lpost_out, double *llike_out);

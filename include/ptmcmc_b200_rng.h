@@ -28,10 +28,13 @@
 #define PTG_DOMAIN_STEP 0
 #define PTG_DOMAIN_INIT 1
 
-/* blocks of a chain's stream within one MH step (domain 0) */
-#define PTG_BLK_SELECT 0      /* w0 u_sel | DE: w1 u_snooker, w2 u_gamma | GAUSS: w1 u_1d, w2 u_axis      (u32) */
-#define PTG_BLK_INDEX 1       /* DE history indices, attempt 0: w0 z, w1 s1, w2 s2                        (u32) */
-#define PTG_BLK_ACCEPT 2      /* (w0,w1) u_acc                                                            (u52) */
+/* blocks of a chain's stream within one MH step (domain 0): two blocks carry every draw of a common step */
+#define PTG_BLK_A 0           /* w0 u_sel | w1 u_snooker (DE) / u_1d (GAUSS) | w2 u_gamma (DE) / u_axis (GAUSS) | w3 DE index s1  (u32) */
+#define PTG_BLK_B 1           /* w0 DE index s2 | w1 DE index z (snooker), attempt 0                                    (u32)
+                                 (w2,w3) u_acc, the Metropolis draw                                                      (u52) */
+/* DE history index `which` (0 = z, 1 = s1, 2 = s2), attempt 0: block and word */
+#define PTG_IDX_BLK(which) ((which) == 1 ? PTG_BLK_A : PTG_BLK_B)
+#define PTG_IDX_WORD(which) ((which) == 1 ? 3 : ((which) == 2 ? 0 : 1))
 #define PTG_BLK_NORMAL 0x100  /* + j/2 : Box-Muller pair -> normals j, j+1 ; (w0,w1)=u_a (w2,w3)=u_b      (u52) */
 #define PTG_BLK_RETRY 0x200   /* + which*0x100 + a : DE index attempt a>=1 (w0) and unlikely-alpha test (w1) (u32) */
 #define PTG_BLK_PRIOR 0x600   /* + i : prior draw of dimension i; (w0,w1)=u (w2,w3)=u_b for Gaussian dims  (u52) */

@@ -364,7 +364,7 @@ static int64_t de_draw_index(pto_handle *h, chain_t *c, const prop_t *p, uint64_
   double alpha = p->unlikely_alpha;
   while (1) {
     int a = *attempt;
-    double xrnd = (a == 0) ? draw_u32(h, &c->rng, PTG_DOMAIN_STEP, step, PTG_BLK_INDEX, which)
+    double xrnd = (a == 0) ? draw_u32(h, &c->rng, PTG_DOMAIN_STEP, step, PTG_IDX_BLK(which), PTG_IDX_WORD(which))
                            : draw_u32(h, &c->rng, PTG_DOMAIN_STEP, step, PTG_BLK_RETRY + which * 0x100 + (a & 0xff), 0);
     (*attempt)++;
     int index = (int)(start + (size - start) * xrnd);
@@ -382,7 +382,7 @@ static int64_t de_draw_index(pto_handle *h, chain_t *c, const prop_t *p, uint64_
 static void de_draw_standard(pto_handle *h, chain_t *c, const prop_t *p, uint64_t step, double *prop, draw_result_t *r) {
   const int d = h->d;
   double gamma = 1.68 / sqrt(d) / p->reduce_gamma;
-  double xgamma = draw_u32(h, &c->rng, PTG_DOMAIN_STEP, step, PTG_BLK_SELECT, 2);
+  double xgamma = draw_u32(h, &c->rng, PTG_DOMAIN_STEP, step, PTG_BLK_A, 2);
   if (xgamma < p->g1frac) gamma = 1;
   int a1 = 0, a2 = 0;
   int64_t i1 = de_draw_index(h, c, p, step, 1, &a1);
@@ -402,7 +402,7 @@ static void de_draw_standard(pto_handle *h, chain_t *c, const prop_t *p, uint64_
 /* differential_evolution::draw_snooker (proposal_distribution.cc:538-591) */
 static void de_draw_snooker(pto_handle *h, chain_t *c, const prop_t *p, uint64_t step, double *prop, draw_result_t *r) {
   const int d = h->d;
-  double xgamma = draw_u32(h, &c->rng, PTG_DOMAIN_STEP, step, PTG_BLK_SELECT, 2);
+  double xgamma = draw_u32(h, &c->rng, PTG_DOMAIN_STEP, step, PTG_BLK_A, 2);
   double gamma = (1.2 + xgamma) / p->reduce_gamma;
   double smznorm2 = 0, minusz[PTG_MAX_DIM], smz[PTG_MAX_DIM];
   int az = 0, isafe = 0;
@@ -461,9 +461,9 @@ static void gauss_draw(pto_handle *h, chain_t *c, const prop_t *p, uint64_t step
   draw_normals(h, &c->rng, step, d, z);
   for (int i = 0; i < d; i++) off[i] = z[i] * p->sigmas[i] + 0.0; /* GaussianDist::draw: normal*sigma+x0 */
   double x = 1;
-  if (p->one_d_frac > 0) x = draw_u32(h, &c->rng, PTG_DOMAIN_STEP, step, PTG_BLK_SELECT, 1);
+  if (p->one_d_frac > 0) x = draw_u32(h, &c->rng, PTG_DOMAIN_STEP, step, PTG_BLK_A, 1);
   if (p->one_d_frac > 0 && x < p->one_d_frac) {
-    int i = (int)(d * draw_u32(h, &c->rng, PTG_DOMAIN_STEP, step, PTG_BLK_SELECT, 2));
+    int i = (int)(d * draw_u32(h, &c->rng, PTG_DOMAIN_STEP, step, PTG_BLK_A, 2));
     for (int j = 0; j < d; j++) if (j != i) off[j] = 0.0;
     r->type = 1;
   } else r->type = 0;
@@ -496,7 +496,7 @@ static int prop_ready(const pto_handle *h, const chain_t *c, const prop_t *p) {
 static void member_draw(pto_handle *h, chain_t *c, const prop_t *p, uint64_t step, double *prop, draw_result_t *r) {
   switch (p->kind) {
   case PTG_PROP_DE: { /* differential_evolution::draw (proposal_distribution.cc:790-801) */
-    double x = draw_u32(h, &c->rng, PTG_DOMAIN_STEP, step, PTG_BLK_SELECT, 1);
+    double x = draw_u32(h, &c->rng, PTG_DOMAIN_STEP, step, PTG_BLK_A, 1);
     if (p->snooker > x) de_draw_snooker(h, c, p, step, prop, r);
     else de_draw_standard(h, c, p, step, prop, r);
     break;
@@ -512,7 +512,7 @@ static int set_draw(pto_handle *h, chain_t *c, uint64_t step, double *prop, draw
   int count = 0;
   while (1) {
     double x;
-    if (h->nprops > 1) x = draw_u32(h, &c->rng, PTG_DOMAIN_STEP, step, PTG_BLK_SELECT, 0);
+    if (h->nprops > 1) x = draw_u32(h, &c->rng, PTG_DOMAIN_STEP, step, PTG_BLK_A, 0);
     else x = 0;
     for (int i = 0; i < h->nprops; i++) {
       if (prop_ready(h, c, &h->props[i]) && x < c->bin_max[i]) {
@@ -581,7 +581,7 @@ static int mh_step(pto_handle *h, chain_t *c, uint64_t step, double *lhr_out, in
   lhr += newlpost - c->lpost;
   if (!valid) { accept = 0; code |= PTG_TRACE_INVALID; }
   if (accept && lhr < 0) {
-    double x = draw_u52(h, &c->rng, PTG_DOMAIN_STEP, step, PTG_BLK_ACCEPT, 0);
+    double x = draw_u52(h, &c->rng, PTG_DOMAIN_STEP, step, PTG_BLK_B, 1);
     accept = (log(x) < lhr);
   }
   c->ntries++;

@@ -21,6 +21,7 @@ PROP_DE, PROP_GAUSS, PROP_PRIOR_DRAW = 1, 2, 3
 SWAP_REFERENCE, SWAP_EVEN_ODD = 0, 1
 RNG_PHILOX, RNG_TAPE = 0, 1
 RECORD_BASIC, RECORD_FULL = 0, 1
+KERNEL_AUTO, KERNEL_SHARED, KERNEL_WARP, KERNEL_FAST = 0, 1, 2, 3
 TRACE_TYPE_MASK, TRACE_ACCEPT, TRACE_INVALID, TRACE_SWAPPED, TRACE_NOLIKE = 0xFF, 0x100, 0x200, 0x400, 0x800
 
 

@@ -4,7 +4,7 @@ import os
 import subprocess
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
-SO = os.path.join(CSRC, "libptmcmc_b200.so")
+SO = os.environ.get("PTMCMC_B200_LIB") or os.path.join(CSRC, "libptmcmc_b200.so")  # env override: developer builds
 _lib = None
 
 

@@ -45,6 +45,7 @@ struct ptg_handle {
   long long istep;
   double *d_scratch; size_t scratch_bytes;
   double *h_pinned; size_t pinned_bytes;
+  int kernel_choice; long long launches;
 };
 
 template <typename T>
@@ -129,6 +130,8 @@ extern "C" int ptg_create(const ptg_config *cfg, ptg_handle **out) {
   if (cfg->swap_mode == PTG_SWAP_EVEN_ODD && cfg->evolve_rate > 0)
     return fail(PTG_EINVAL, "temperature evolution is defined for the reference swap schedule only");
   if (cfg->rng_mode != PTG_RNG_PHILOX && cfg->rng_mode != PTG_RNG_TAPE) return fail(PTG_EINVAL, "bad rng_mode");
+  if ((int64_t)cfg->n_ladders * cfg->n_rungs >= (1ll << 31) || cfg->ladder_offset < 0 || cfg->ladder_offset + cfg->n_ladders >= (1ll << 31))
+    return fail(PTG_EINVAL, "chain and global ladder ids must stay below 2^31");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -147,7 +150,7 @@ extern "C" int ptg_create(const ptg_config *cfg, ptg_handle **out) {
   h->have_space = h->have_prior = h->have_like = h->have_props = h->inited = h->model_uploaded = false;
   h->d_lparams = h->d_ldata = h->d_prop_data = h->d_bins = nullptr;
   h->d_tape_u = h->d_tape_z = nullptr; h->d_u_end = h->d_z_end = nullptr;
-  h->istep = 0; h->Tpow = 0; h->d_scratch = nullptr; h->scratch_bytes = 0; h->h_pinned = nullptr; h->pinned_bytes = 0;
+  h->kernel_choice = PTG_KERNEL_AUTO; h->launches = 0; h->istep = 0; h->Tpow = 0; h->d_scratch = nullptr; h->scratch_bytes = 0; h->h_pinned = nullptr; h->pinned_bytes = 0;
   cudaError_t es = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (es != cudaSuccess) { delete h; return fail(PTG_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(es)); }
   h->own_stream = true;
@@ -235,6 +238,8 @@ extern "C" int ptg_set_space(ptg_handle *h, const int32_t *lt, const int32_t *ut
     }
   }
   m.zero_valid = zero_valid ? 1 : 0;
+  m.any_bound = 0;
+  for (int i = 0; i < m.dim; i++) if (lt[i] != PTG_BOUND_OPEN || ut[i] != PTG_BOUND_OPEN) m.any_bound = 1;
   h->have_space = true;
   return 0;
 }
@@ -506,26 +511,67 @@ static size_t ladder_shared_bytes(int D, int R) {
   return (b + 15) & ~(size_t)15;
 }
 
+// lanes per ladder of the warp kernels: the smallest power of two that holds n_rungs; 0 = the ladder does not fit one
+// warp (or has more swap trials per step than lanes) and the shared-memory kernel runs instead
+static int warp_kernel_width(const ptg_handle *h) {
+  const PtgModel &m = h->m;
+  if (m.n_rungs > 32) return 0;
+  int W = 1;
+  while (W < m.n_rungs) W <<= 1;
+  if (m.swap_mode == PTG_SWAP_REFERENCE && m.maxswaps > W) return 0;
+  return W;
+}
+// which step kernel runs: PTG_KERNEL_FAST (Philox draws, <= 32 rungs), PTG_KERNEL_WARP (tape replay, <= 32 rungs),
+// PTG_KERNEL_SHARED otherwise; ptg_select_kernel can pin WARP or SHARED where they apply
+static int pick_kernel(const ptg_handle *h, int *W) {
+  *W = warp_kernel_width(h);
+  int k = PTG_KERNEL_SHARED;
+  if (*W) k = (h->cfg.rng_mode == PTG_RNG_PHILOX) ? PTG_KERNEL_FAST : PTG_KERNEL_WARP;
+  if (h->kernel_choice == PTG_KERNEL_SHARED) k = PTG_KERNEL_SHARED;
+  if (h->kernel_choice == PTG_KERNEL_WARP && *W) k = PTG_KERNEL_WARP;
+  return k;
+}
+
 extern "C" int ptg_step(ptg_handle *h, int64_t n_steps) {
   if (!h) return fail(PTG_EINVAL, "null handle");
   if (!h->inited) return fail(PTG_EINVAL, "MH_chain:step: Can't step before initializing chain (chain.cc:967-971)");
   if (n_steps < 0) return fail(PTG_EINVAL, "negative step count");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   PtgModel &m = h->m;
+  int W = 0;
+  const int kern = pick_kernel(h, &W);
   const int lpb = ladders_per_block(m);
   const size_t smem = (size_t)lpb * ladder_shared_bytes(m.dim, m.n_rungs) + (size_t)m.n_rungs * m.n_props * sizeof(double);
+  const int max_chunk = (kern == PTG_KERNEL_FAST) ? 16384 : (1 << 20); // the fast kernel keeps 16-bit launch-local statistics
   int64_t left = n_steps;
   while (left > 0) {
-    int chunk = (int)(left > (1 << 20) ? (1 << 20) : left);
+    int chunk = (int)(left > max_chunk ? max_chunk : left);
     cudaError_t e = cudaErrorInvalidValue;
     switch (m.dim) {
-#define X(D) case D: e = ptg_launch_step_d##D(h->cfg.rng_mode, m, h->s, h->istep, chunk, lpb, smem, h->stream); break;
+#define X(D) case D:                                                                                                       \
+      if (kern == PTG_KERNEL_FAST) e = ptg_launch_fstep_d##D(m, h->s, h->istep, chunk, W, h->stream);                       \
+      else if (kern == PTG_KERNEL_WARP) e = ptg_launch_wstep_d##D(h->cfg.rng_mode, m, h->s, h->istep, chunk, W, h->stream); \
+      else e = ptg_launch_step_d##D(h->cfg.rng_mode, m, h->s, h->istep, chunk, lpb, smem, h->stream);                       \
+      break;
       PTG_DIM_LIST(X)
 #undef X
     }
     CUDA_TRY(e);
-    h->istep += chunk; left -= chunk;
+    h->istep += chunk; left -= chunk; h->launches++;
   }
+  return 0;
+}
+
+extern "C" int ptg_select_kernel(ptg_handle *h, int32_t kernel) {
+  if (!h) return fail(PTG_EINVAL, "null handle");
+  if (kernel < PTG_KERNEL_AUTO || kernel > PTG_KERNEL_FAST) return fail(PTG_EINVAL, "bad kernel id %d", kernel);
+  h->kernel_choice = kernel;
+  return 0;
+}
+/* number of step-kernel launches issued since creation */
+extern "C" int ptg_get_launch_count(ptg_handle *h, int64_t *n) {
+  if (!h || !n) return fail(PTG_EINVAL, "null argument");
+  *n = h->launches;
   return 0;
 }
 

@@ -199,11 +199,20 @@ __device__ __forceinline__ double like_eval(const PtgModel &m, const double x[D]
   case PTG_LIKE_SINES: { // sines.hh:22-54
     const double height = __ldg(P), step_scale = __ldg(P + 1);
     double lprod = 0; int isum = 0;
+    // rolled on purpose: ONE copy of sin() in the instruction stream and one set of temporaries (register budget and
+    // instruction-cache footprint of the step kernels); x[i] is picked with selects, not by indexing (no local memory)
+#ifndef PTG_SINES_UNROLLED
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
     for (int i = 0; i < D; i++) {
-      int k = (int)__ldg(P + 2 + i);
-      double mn = __ldg(P + 2 + D + i), mx = __ldg(P + 2 + 2 * D + i);
-      double xx = (x[i] - mn) / (mx - mn);
+      double xi = x[0];
+#pragma unroll
+      for (int j = 1; j < D; j++) if (i == j) xi = x[j];
+      const int k = (int)__ldg(P + 2 + i);
+      const double mn = __ldg(P + 2 + D + i), mx = __ldg(P + 2 + 2 * D + i);
+      const double xx = (xi - mn) / (mx - mn);
       double s = sin(k * PTG_PI * xx);
       s = s * s;
       lprod += (s * s - 1) * height;

@@ -2,6 +2,8 @@
 // build parallelises).  PTG_INSTANTIATE(D) defines the two launchers declared in ptg_launch.h.
 #pragma once
 #include "ptg_kernels.cuh"
+#include "ptg_warp.cuh"
+#include "ptg_fast.cuh"
 #include "ptg_launch.h"
 
 template <int D, int MODE>
@@ -13,6 +15,24 @@ static cudaError_t launch_step_t(const PtgModel &m, const PtgState &s, long long
   }
   int blocks = (int)((m.n_ladders + lpb - 1) / lpb);
   k<<<blocks, lpb * m.n_rungs, smem, st>>>(m, s, step0, n_steps, lpb);
+  return cudaGetLastError();
+}
+// second-generation kernel: ladder-in-a-warp (n_rungs <= W <= 32), 4 warps per CTA
+template <int D, int MODE>
+static cudaError_t launch_wstep_t(const PtgModel &m, const PtgState &s, long long step0, int n_steps, int W, cudaStream_t st) {
+  const long long warps = (m.n_ladders + (32 / W) - 1) / (32 / W);
+  const int blocks = (int)((warps + 3) / 4);
+  const size_t smem = (size_t)m.n_rungs * m.n_props * sizeof(double);
+  ptg_wstep_kernel<D, MODE><<<blocks, 128, smem, st>>>(m, s, step0, n_steps, W);
+  return cudaGetLastError();
+}
+// production kernel (Philox draws): same geometry as the warp kernel, proposal table + bins in shared memory
+template <int D>
+static cudaError_t launch_fstep_t(const PtgModel &m, const PtgState &s, long long step0, int n_steps, int W, cudaStream_t st) {
+  const long long warps = (m.n_ladders + (32 / W) - 1) / (32 / W);
+  const int blocks = (int)((warps + 3) / 4);
+  const size_t smem = (size_t)m.n_rungs * m.n_props * sizeof(double) + (size_t)m.n_props * sizeof(FProp) + FC_COUNT * 128 * sizeof(int);
+  ptg_fstep_kernel<D><<<blocks, 128, smem, st>>>(m, s, step0, n_steps, W);
   return cudaGetLastError();
 }
 template <int D, int MODE>
@@ -27,6 +47,14 @@ static cudaError_t launch_init_t(const PtgModel &m, const PtgState &s, const dou
                                    size_t smem, cudaStream_t st) {                                                           \
     return mode == PTG_RNG_TAPE ? launch_step_t<D, PTG_RNG_TAPE>(m, s, step0, n_steps, lpb, smem, st)                        \
                                 : launch_step_t<D, PTG_RNG_PHILOX>(m, s, step0, n_steps, lpb, smem, st);                     \
+  }                                                                                                                          \
+  cudaError_t ptg_launch_wstep_d##D(int mode, const PtgModel &m, const PtgState &s, long long step0, int n_steps, int W,     \
+                                    cudaStream_t st) {                                                                       \
+    return mode == PTG_RNG_TAPE ? launch_wstep_t<D, PTG_RNG_TAPE>(m, s, step0, n_steps, W, st)                               \
+                                : launch_wstep_t<D, PTG_RNG_PHILOX>(m, s, step0, n_steps, W, st);                            \
+  }                                                                                                                          \
+  cudaError_t ptg_launch_fstep_d##D(const PtgModel &m, const PtgState &s, long long step0, int n_steps, int W, cudaStream_t st) { \
+    return launch_fstep_t<D>(m, s, step0, n_steps, W, st);                                                                   \
   }                                                                                                                          \
   cudaError_t ptg_launch_init_d##D(int mode, const PtgModel &m, const PtgState &s, const double *init_x, cudaStream_t st) {  \
     return mode == PTG_RNG_TAPE ? launch_init_t<D, PTG_RNG_TAPE>(m, s, init_x, st)                                           \

@@ -89,7 +89,8 @@ __device__ __forceinline__ const double *hist_elem(const PtgModel &m, const PtgS
 // differential_evolution::draw_i_from_chain (proposal_distribution.cc:744-778)
 template <int D, int MODE>
 __device__ __forceinline__ int de_draw_index(const PtgModel &m, const PtgState &s, const Chain<D> &ch, const PtgProp &p,
-                                             Stream<MODE> &rs, const uint32_t widx[4], int which, int &attempt) {
+                                             Stream<MODE> &rs, const uint32_t wA[4], const uint32_t wB[4], int which, int &attempt) {
+  const uint32_t w0 = (which == 1) ? wA[3] : (which == 2 ? wB[0] : wB[1]); // PTG_IDX_BLK / PTG_IDX_WORD
   int size = (int)(ch.nsize > m.hist_cap ? (long long)m.hist_cap : ch.nsize);
   int start = 0, mins = D * 10, minc = D * 100;
   if ((size - minc) * (1 - p.ignore_frac) > mins) start = (int)((size - minc) * p.ignore_frac);
@@ -99,11 +100,11 @@ __device__ __forceinline__ int de_draw_index(const PtgModel &m, const PtgState &
     int a = attempt;
     uint32_t wr[4];
     double xrnd;
-    if (a == 0 && alpha <= 0) xrnd = rs.u32(widx, which);
+    if (a == 0 && alpha <= 0) { if constexpr (MODE == PTG_RNG_PHILOX) xrnd = ptg_u32_to_unit(w0); else xrnd = rs.next_u(); }
     else {
       if constexpr (MODE == PTG_RNG_PHILOX) {
         rs.fetch(PTG_BLK_RETRY + which * 0x100 + (a & 0xff), wr);
-        xrnd = (a == 0) ? ptg_u32_to_unit(widx[which]) : ptg_u32_to_unit(wr[0]);
+        xrnd = (a == 0) ? ptg_u32_to_unit(w0) : ptg_u32_to_unit(wr[0]);
       } else xrnd = rs.next_u();
     }
     attempt++;
@@ -134,8 +135,9 @@ __device__ __forceinline__ MhOut mh_step(const PtgModel &m, const PtgState &s, C
   bool valid = m.zero_valid != 0;
   const double oldlprior = ch.lpost - ch.beta * ch.llike;
 
-  uint32_t wsel[4];
-  rs.fetch(PTG_BLK_SELECT, wsel);
+  uint32_t wsel[4], widx[4]; // blocks A and B of this step (include/ptmcmc_b200_rng.h)
+  rs.fetch(PTG_BLK_A, wsel);
+  rs.fetch(PTG_BLK_B, widx);
   // ---- member selection
   int member = 0;
   if (m.wrap_in_set) {
@@ -156,15 +158,13 @@ __device__ __forceinline__ MhOut mh_step(const PtgModel &m, const PtgState &s, C
     // differential_evolution::draw (proposal_distribution.cc:790-801)
     double usnk = rs.u32(wsel, 1);
     double ug = rs.u32(wsel, 2);
-    uint32_t widx[4];
-    rs.fetch(PTG_BLK_INDEX, widx);
     if (!(p.snooker > usnk)) {
       // draw_standard (proposal_distribution.cc:489-535)
       double gamma = p.gamma_std;
       if (ug < p.g1frac) gamma = 1;
       int a1 = 0, a2 = 0;
-      int i1 = de_draw_index<D, MODE>(m, s, ch, p, rs, widx, 1, a1);
-      int i2 = de_draw_index<D, MODE>(m, s, ch, p, rs, widx, 2, a2);
+      int i1 = de_draw_index<D, MODE>(m, s, ch, p, rs, wsel, widx, 1, a1);
+      int i2 = de_draw_index<D, MODE>(m, s, ch, p, rs, wsel, widx, 2, a2);
       const double *s1 = hist_elem<D>(m, s, ch, i1), *s2 = hist_elem<D>(m, s, ch, i2);
       if constexpr (MODE == PTG_RNG_TAPE) { // the d normals of the discarded jitter are still consumed (H8-1)
         for (int j = 0; j < D; j++) (void)rs.next_z();
@@ -181,7 +181,7 @@ __device__ __forceinline__ MhOut mh_step(const PtgModel &m, const PtgState &s, C
       double smznorm2 = 0, minusz[D], smz[D];
       int az = 0, isafe = 0;
       while (smznorm2 == 0) {
-        int iz = de_draw_index<D, MODE>(m, s, ch, p, rs, widx, 0, az);
+        int iz = de_draw_index<D, MODE>(m, s, ch, p, rs, wsel, widx, 0, az);
         const double *z = hist_elem<D>(m, s, ch, iz);
         smznorm2 = 0;
 #pragma unroll
@@ -191,8 +191,8 @@ __device__ __forceinline__ MhOut mh_step(const PtgModel &m, const PtgState &s, C
         if (++isafe > 1000) break;
       }
       int a1 = 0, a2 = 0;
-      int i1 = de_draw_index<D, MODE>(m, s, ch, p, rs, widx, 1, a1);
-      int i2 = de_draw_index<D, MODE>(m, s, ch, p, rs, widx, 2, a2);
+      int i1 = de_draw_index<D, MODE>(m, s, ch, p, rs, wsel, widx, 1, a1);
+      int i2 = de_draw_index<D, MODE>(m, s, ch, p, rs, wsel, widx, 2, a2);
       const double *s1 = hist_elem<D>(m, s, ch, i1), *s2 = hist_elem<D>(m, s, ch, i2);
       double dot = 0;
 #pragma unroll
@@ -277,9 +277,7 @@ __device__ __forceinline__ MhOut mh_step(const PtgModel &m, const PtgState &s, C
   lhr += newlpost - ch.lpost;
   if (!valid) { accept = false; code |= PTG_TRACE_INVALID; }
   if (accept && lhr < 0) {
-    uint32_t wacc[4];
-    rs.fetch(PTG_BLK_ACCEPT, wacc);
-    double u = rs.u52(wacc, 0);
+    double u = rs.u52(widx, 1);
     accept = (log(u) < lhr);
   }
   ch.ntries++;
@@ -306,6 +304,12 @@ __device__ __forceinline__ void stream_open(const PtgModel &m, const PtgState &s
     rs.upos = s.u_pos[stream_index]; rs.uend = s.u_end[stream_index];
     rs.zpos = s.z_pos[stream_index]; rs.zend = s.z_end[stream_index];
   } else { rs.ut = rs.zt = nullptr; rs.upos = rs.uend = rs.zpos = rs.zend = 0; }
+}
+// a stream that addresses nothing (ghost lanes of the warp kernel)
+template <int MODE>
+__device__ __forceinline__ void stream_blank(const PtgModel &m, Stream<MODE> &rs) {
+  rs.seed = m.seed; rs.id = 0; rs.step = 0; rs.domain = PTG_DOMAIN_STEP; rs.err = 0;
+  rs.ut = rs.zt = nullptr; rs.upos = rs.uend = rs.zpos = rs.zend = 0;
 }
 template <int MODE>
 __device__ __forceinline__ void stream_close(const PtgState &s, Stream<MODE> &rs, long long stream_index) {

@@ -2,10 +2,17 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "ptg_types.h"
+#ifdef PTG_DEV_DIM3  // developer build: `make DEV=1` compiles only dim=3 (seconds instead of minutes)
+#define PTG_DIM_LIST(X) X(3)
+#else
 #define PTG_DIM_LIST(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(12) X(16)
+#endif
 #define PTG_DECLARE(D)                                                                                                      \
   cudaError_t ptg_launch_step_d##D(int mode, const PtgModel &m, const PtgState &s, long long step0, int n_steps, int lpb,   \
                                    size_t smem, cudaStream_t st);                                                           \
+  cudaError_t ptg_launch_wstep_d##D(int mode, const PtgModel &m, const PtgState &s, long long step0, int n_steps, int W,    \
+                                    cudaStream_t st);                                                                       \
+  cudaError_t ptg_launch_fstep_d##D(const PtgModel &m, const PtgState &s, long long step0, int n_steps, int W, cudaStream_t st); \
   cudaError_t ptg_launch_init_d##D(int mode, const PtgModel &m, const PtgState &s, const double *init_x, cudaStream_t st);       \
   cudaError_t ptg_launch_eval_d##D(const PtgModel &m, const double *x, long long n, double *ll, double *lp, cudaStream_t st);
 PTG_DIM_LIST(PTG_DECLARE)

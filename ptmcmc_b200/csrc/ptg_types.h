@@ -28,6 +28,7 @@ struct PtgModel {
   int32_t save_every, hist_cap, n_init, maxswaps;
   int32_t swap_mode, record_full, wrap_in_set, zero_valid;
   int32_t like_kind, n_lparams, trace_steps, all_uniform_prior;
+  int32_t any_bound, pad0;    // any_bound: some dimension has a non-open boundary (state::enforce does work)
   int64_t n_ldata;
   int64_t n_chains;
   double swap_rate, dprior_min, evolve_rate, evolve_lpost_cut;

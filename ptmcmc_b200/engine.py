@@ -14,6 +14,13 @@ class Engine(K.CApi):
     def synchronize(self):
         self._call("synchronize", self.h)
 
+    def select_kernel(self, kernel):
+        """K.KERNEL_AUTO / KERNEL_SHARED / KERNEL_WARP / KERNEL_FAST (include/ptmcmc_b200.h)"""
+        self._call("select_kernel", self.h, C.c_int32(kernel))
+
+    def launch_count(self):
+        n = C.c_int64(); self._call("get_launch_count", self.h, C.byref(n)); return n.value
+
     def set_stream(self, cuda_stream_ptr):
         self._call("set_stream", self.h, C.c_void_p(cuda_stream_ptr))
 

@@ -281,4 +281,8 @@ def parity_cases():
         ("B_poly", Spec("poly", 5, 4, centers=np.zeros(5), halfwidths=np.full(5, 10.0), prop="de", Tmax=1e6, extra=poly_data()), 200, 1),
         ("C2_sinusoid", sinusoid_spec(4, n=500, dt=0.02), 150, 1),
         ("D_fullcov_d6", fullcov_spec(6, 4, Tmax=100), 800, 1),
+        # ladder widths of the warp kernel: 24 rungs in a 32-lane group (ghost lanes), 40 rungs (shared-memory kernel)
+        ("R24_evolve", Spec("sines", 2, 24, seed=0.31, evolve_rate=0.01, swap_rate=0.2), 500, 2),
+        ("R40_two_warps", Spec("gauss", 2, 40, centers=[2, -3], halfwidths=[2, 3], seed=0.77), 300, 1),
+        ("R3_high_swap_rate", Spec("gauss", 2, 3, centers=[2, -3], halfwidths=[2, 3], seed=0.41, swap_rate=0.9, Tmax=50), 800, 5),
     ]

@@ -56,6 +56,17 @@ def test_engine_matches_golden_reference_histories(name, oracle_cls, engine_cls)
     assert (sw["swap_count"][0] == g["swap_count"]).all() and (sw["swap_accept"][0] == g["swap_accept"]).all()
 
 
+@pytest.mark.parametrize("name", ["A_gauss2d_default", "sines_evolve_cut", "C1_sines_d3_R32", "unlikely_alpha"])
+def test_tape_parity_first_generation_kernel(name, oracle_cls, engine_cls):
+    """the shared-memory kernel (used for ladders of more than 32 rungs) forced onto small ladders"""
+    class Gen1(engine_cls):
+        def __init__(self, cfg):
+            super().__init__(cfg)
+            self.select_kernel(K.KERNEL_SHARED)
+    _, spec, steps, L = [c for c in CASES if c[0] == name][0]
+    assert tape_parity(oracle_cls, Gen1, spec, steps, L, what=name) == []
+
+
 def test_tape_parity_with_wrapping_ring(oracle_cls, engine_cls):
     """history ring smaller than the run (H3): DE draws from the newest `capacity` samples; indices must still agree"""
     spec = Spec("gauss", 2, 6, centers=[2, -3], halfwidths=[2, 3])
