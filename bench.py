@@ -278,6 +278,21 @@ def main():
     h2d = n_chains * (d + 3) * 8
     d2h = L * n_out * (d + 2) * 8
 
+    # ---- ESS/s (second half of BASELINE.json's metric): integrated autocorrelation time of the cold chains over the newest
+    # history-ring window of a sample of ladders; ESS/s = (cold-chain steps per second over all ladders) / tau
+    ess = None
+    try:
+        from ptmcmc_b200.analysis import ess_per_sample
+        nl, nh = min(L, 256), min(w["hist"] - 8, 1000)
+        cnt = eng.get_counters()
+        cold = np.stack([eng.get_history(l, 0, int(cnt["nsize"][l * R]) - nh, nh, full=False)["x"] for l in range(nl)])
+        eps, taus = ess_per_sample(cold)
+        pt_iter_per_s = args.steps * S / (ms_max * 1e-3)
+        ess = dict(value=eps * pt_iter_per_s * L * world, unit="ESS/s", tau_pt_iterations=float(taus.max()), window=nh, ladders_sampled=nl,
+                   estimator="min over parameters of N/tau, Sokal-windowed integrated autocorrelation time (ptmcmc_b200/analysis.py)")
+    except Exception as exc:  # analysis is not part of the timed path
+        ess = dict(value=None, error=repr(exc))
+
     # ---- roofline of the dominant kernel (ptg_step_kernel: one launch per bench step)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -299,7 +314,7 @@ def main():
     out = dict(metric=metric, value=value, unit=unit, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_max / args.steps,
                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", config=config, clocks=clk,
                e2e=dict(value=e2e_val, unit=unit, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=e2e_steps),
-               gpu_launches=args.steps, roofline=roofline)
+               gpu_launches=args.steps, roofline=roofline, ess=ess)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         procs = cpu_threads()
         n_pt = reference_pt_steps(w, 10.0)
