@@ -41,6 +41,12 @@ WORKLOADS = {
     # C2: 3-sinusoid chi^2 over 1e4 samples, d=9
     "c2_sinusoid": dict(model="sinusoid", dim=9, rungs=32, ladders=4096, pt_steps=1, hist=512, f_de=0.8, f_sn=0.1,
                         desc="3-sinusoid chi^2 fit to 1e4 samples d=9, 4096 ladders x 32 rungs, default proposal mix"),
+    # configs[3] / D: correlated Gaussian d=100, full covariance; "65536 chains x 24 rungs" read as 65 544 chains in total
+    # (2731 ladders x 24 rungs; the 1.57 M-chain reading leaves < 100 history slots per chain in 180 GB, SURVEY.md 8d, and the
+    # reference's DE member needs >= 10 d = 1000 stored samples to be ready).  Ninit = 11 d prior draws per chain (de_ni = 11).
+    "d_fullcov": dict(model="fullcov", dim=100, rungs=24, ladders=2731, pt_steps=50, hist=1280, f_de=0.5, f_sn=0.1,
+                      desc="correlated Gaussian d=100 full covariance (DMMA batched quadratic form + proposal rotation), 2731 ladders x 24 rungs, "
+                           "50% eigen-rotated Gaussian proposal (2.38^2/d C) + 50% DE"),
     # configs[0] / A as a throughput batch
     "a_gauss": dict(model="gauss", dim=2, rungs=8, ladders=16384, pt_steps=1000, hist=1024, f_de=0.8, f_sn=0.1,
                     desc="2-D isotropic Gaussian, 16384 ladders x 8 rungs, default proposal mix"),
@@ -57,6 +63,9 @@ def make_spec(w):
         return sinusoid_spec(w["rungs"], n=10000)
     if w["model"] == "gauss":
         return Spec("gauss", 2, w["rungs"], centers=[2, -3], halfwidths=[2, 3])
+    if w["model"] == "fullcov":
+        from tests.models import fullcov_spec
+        return fullcov_spec(w["dim"], w["rungs"], de_ni=11)
     raise ValueError(w["model"])
 
 
@@ -158,7 +167,7 @@ def _port_worker(args):
 def reference_pt_steps(w, seconds=8.0):
     """PT iterations per process for roughly `seconds` of CPU work (1.6e5 chain-steps/s/core measured for A/C1-like
     models; chi^2 models scale with the data size)"""
-    per_chain_step = {"sines": 6e-6, "gauss": 6e-6, "poly": 1.2e-5, "sinusoid": 3e-4}[w["model"]]
+    per_chain_step = {"sines": 6e-6, "gauss": 6e-6, "poly": 1.2e-5, "sinusoid": 3e-4, "fullcov": 6e-5}[w["model"]]
     return max(20, int(seconds / (per_chain_step * w["rungs"])))
 
 

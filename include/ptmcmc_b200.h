@@ -31,7 +31,8 @@ extern "C" {
 #endif
 
 #define PTG_ABI_VERSION 1
-#define PTG_MAX_DIM 128        /* thread-per-chain kernels cover dim<=16, the warp-per-chain kernel dim<=128 */
+#define PTG_MAX_DIM 128        /* thread-per-chain kernels: dim 1-10, 12, 16; warp-per-chain kernels: dim 17-128 (n_rungs <= 32;
+                                  likelihoods flat / gaussian / full-covariance gaussian, no prior-draw member) */
 #define PTG_MAX_PROPOSALS 16
 #define PTG_MAX_RUNGS 64
 

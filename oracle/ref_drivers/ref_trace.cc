@@ -26,6 +26,7 @@
 #include <sstream>
 #include <fstream>
 #include <memory>
+#include <new>
 #include "chain.hh"
 #include "proposal_distribution.hh"
 #include "probability_function.hh"
@@ -227,7 +228,12 @@ int main(int argc, char **argv) {
     Eigen::MatrixXd covar(d, d);
     for (int i = 0; i < d; i++) for (int j = 0; j < d; j++) covar(i, j) = c[(size_t)i * d + j];
     streambuf *old = cout.rdbuf(); ostringstream sink; cout.rdbuf(sink.rdbuf()); // constructor is chatty
-    gaussian_prop *g = new gaussian_prop(covar, D("gauss_1d_frac", 0.0), false);
+    // The reference's covariance constructor self-initialises a member (`:sigmas(sigmas)`, proposal_distribution.hh:164),
+    // i.e. copy-constructs a valarray from its own uninitialised storage: undefined behaviour that throws bad_alloc whenever
+    // the heap garbage looks like a huge size (seen for d >= 28).  Constructing the object in ZEROED storage makes that
+    // self-copy see an empty valarray, which is what the author evidently relied on; nothing else changes.
+    void *gmem = calloc(1, sizeof(gaussian_prop));
+    gaussian_prop *g = new (gmem) gaussian_prop(covar, D("gauss_1d_frac", 0.0), false);
     cout.rdbuf(old);
     { // dump the eigen-decomposition the reference actually uses (proposal_distribution.hh:173-176)
       FILE *f = fopen((out + ".eig").c_str(), "wb");

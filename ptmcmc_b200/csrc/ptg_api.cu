@@ -39,6 +39,9 @@ struct ptg_handle {
   std::vector<HostProp> props;
   double Tpow;
   std::vector<double> lparams, ldata, betas;
+  std::vector<int32_t> lower, upper; std::vector<double> xmin, xmax; std::vector<PtgPrior1D> prior; // every dimension (dim may exceed 16)
+  int wide_trans_off;              // offset of the (first) eigen-rotation matrix in prop_data, -1 = none
+  bool wide;                       // dim > 16: warp-per-chain kernels (ptg_wide.cuh)
   std::vector<void *> allocs;       // every device allocation (freed in destroy)
   double *d_lparams, *d_ldata, *d_prop_data, *d_bins;
   double *d_tape_u, *d_tape_z; long long *d_u_end, *d_z_end;
@@ -60,10 +63,10 @@ static int dev_alloc(ptg_handle *h, T **p, size_t n, bool zero = true) {
   return 0;
 }
 
-__global__ void ptg_uniform_lprior_kernel(PtgModel m, double *out) {
+__global__ void ptg_uniform_lprior_kernel(const PtgPrior1D *prior, int dim, double *out) {
   // log(prod_i 1/(b_i-a_i)): same operation order as uniform_dist_product::evaluate (probability_function.cc:156-166)
   double result = 1;
-  for (int i = 0; i < m.dim; i++) result *= 1 / (m.prior[i].b - m.prior[i].a);
+  for (int i = 0; i < dim; i++) result *= 1 / (prior[i].b - prior[i].a);
   *out = log(result);
 }
 __global__ void ptg_fill_kernel(double *p, long long n, double v) {
@@ -142,11 +145,16 @@ extern "C" int ptg_create(const ptg_config *cfg, ptg_handle **out) {
 #define X(D) if (cfg->dim == D) supported_dim = true;
   PTG_DIM_LIST(X)
 #undef X
-  if (!supported_dim) return fail(PTG_EINVAL, "dim=%d: thread-per-chain kernels are instantiated for 1-10,12,16", cfg->dim);
+  if (!supported_dim && cfg->dim <= PTG_TPC_MAX_DIM)
+    return fail(PTG_EINVAL, "dim=%d: thread-per-chain kernels are instantiated for 1-10,12,16; dims 17-128 run the warp-per-chain kernels", cfg->dim);
+  if (cfg->dim > PTG_TPC_MAX_DIM && cfg->n_rungs > 32) return fail(PTG_EINVAL, "dim > 16 needs n_rungs <= 32 (one CTA per ladder, one warp per rung)");
 
   ptg_handle *h = new ptg_handle();
   memset(&h->m, 0, sizeof(h->m)); memset(&h->s, 0, sizeof(h->s));
   h->cfg = *cfg;
+  h->wide = cfg->dim > PTG_TPC_MAX_DIM; h->wide_trans_off = -1;
+  h->lower.assign(cfg->dim, PTG_BOUND_OPEN); h->upper.assign(cfg->dim, PTG_BOUND_OPEN);
+  h->xmin.assign(cfg->dim, -INFINITY); h->xmax.assign(cfg->dim, INFINITY); h->prior.resize(cfg->dim);
   h->have_space = h->have_prior = h->have_like = h->have_props = h->inited = h->model_uploaded = false;
   h->d_lparams = h->d_ldata = h->d_prop_data = h->d_bins = nullptr;
   h->d_tape_u = h->d_tape_z = nullptr; h->d_u_end = h->d_z_end = nullptr;
@@ -220,7 +228,8 @@ extern "C" int ptg_set_space(ptg_handle *h, const int32_t *lt, const int32_t *ut
   PtgModel &m = h->m;
   bool zero_valid = true;
   for (int i = 0; i < m.dim; i++) {
-    m.lower[i] = lt[i]; m.upper[i] = ut[i]; m.xmin[i] = xmin[i]; m.xmax[i] = xmax[i];
+    h->lower[i] = lt[i]; h->upper[i] = ut[i]; h->xmin[i] = xmin[i]; h->xmax[i] = xmax[i];
+    if (i < PTG_TPC_MAX_DIM) { m.lower[i] = lt[i]; m.upper[i] = ut[i]; m.xmin[i] = xmin[i]; m.xmax[i] = xmax[i]; }
     // validity of the zero vector decides the validity of every state built by state::add / scalar_mult
     // (states.cc:168-176,194-204).  Pure comparisons: no arithmetic result is kept.
     if (zero_valid) {
@@ -249,7 +258,7 @@ extern "C" int ptg_set_prior(ptg_handle *h, const int32_t *type, const double *a
   PtgModel &m = h->m;
   bool all_uniform = true;
   for (int i = 0; i < m.dim; i++) {
-    PtgPrior1D &p = m.prior[i];
+    PtgPrior1D &p = h->prior[i];
     p.kind = type[i]; p.pad = 0; p.a = a[i]; p.b = b[i]; p.norm = p.cdfoff = p.la = p.lb = 0;
     if (p.kind != PTG_PRIOR_UNIFORM) all_uniform = false;
     if (p.kind == PTG_PRIOR_POLAR) { // ProbabilityDist.h:187-192
@@ -267,6 +276,7 @@ extern "C" int ptg_set_prior(ptg_handle *h, const int32_t *type, const double *a
       p.la = log(a[i]); p.lb = log(b[i]);
     } else if (p.kind != PTG_PRIOR_UNIFORM && p.kind != PTG_PRIOR_GAUSSIAN) return fail(PTG_EINVAL, "bad prior type %d", p.kind);
   }
+  for (int i = 0; i < m.dim && i < PTG_TPC_MAX_DIM; i++) m.prior[i] = h->prior[i];
   m.all_uniform_prior = all_uniform ? 1 : 0;
   h->have_prior = true;
   return 0;
@@ -404,7 +414,14 @@ static int upload_model(ptg_handle *h) {
   PtgModel &m = h->m;
   if (!h->have_prior || !h->have_like || !h->have_props) return fail(PTG_EINVAL, "set prior, likelihood and proposals before initialising");
   const int d = m.dim;
+  if (h->wide) {
+    if (m.like_kind != PTG_LIKE_FLAT && m.like_kind != PTG_LIKE_GAUSS_ISO && m.like_kind != PTG_LIKE_GAUSS_FULLCOV)
+      return fail(PTG_EINVAL, "dim > 16: likelihood functors flat, gaussian and full-covariance gaussian are available");
+    for (const HostProp &hp : h->props)
+      if (hp.p.kind == PTG_PROP_PRIOR_DRAW) return fail(PTG_EINVAL, "dim > 16: the prior-draw proposal member is not available");
+  }
   // proposals
+  h->wide_trans_off = -1;
   std::vector<double> pdata;
   for (int i = 0; i < m.n_props; i++) {
     const HostProp &hp = h->props[i];
@@ -416,7 +433,10 @@ static int upload_model(ptg_handle *h) {
     if (p.kind == PTG_PROP_GAUSS) {
       p.sigma_off = (int)pdata.size(); pdata.insert(pdata.end(), hp.sigmas.begin(), hp.sigmas.end());
       p.has_transform = hp.transform.empty() ? 0 : 1;
-      if (p.has_transform) { p.trans_off = (int)pdata.size(); pdata.insert(pdata.end(), hp.transform.begin(), hp.transform.end()); }
+      if (p.has_transform) {
+        p.trans_off = (int)pdata.size(); pdata.insert(pdata.end(), hp.transform.begin(), hp.transform.end());
+        if (h->wide_trans_off < 0) h->wide_trans_off = p.trans_off;
+      }
     }
   }
   if (pdata.empty()) pdata.push_back(0.0);
@@ -436,10 +456,21 @@ static int upload_model(ptg_handle *h) {
   CUDA_TRY(cudaMemcpyAsync(h->d_prop_data, pdata.data(), pdata.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(cudaMemcpyAsync(h->d_bins, bins.data(), bins.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   m.lparams = h->d_lparams; m.ldata = h->d_ldata; m.prop_data = h->d_prop_data; m.bins = h->d_bins;
+  {
+    int32_t *dl = nullptr, *du = nullptr; double *dmin = nullptr, *dmax = nullptr; PtgPrior1D *dp = nullptr;
+    if (dev_alloc(h, &dl, (size_t)d, false) || dev_alloc(h, &du, (size_t)d, false) || dev_alloc(h, &dmin, (size_t)d, false) ||
+        dev_alloc(h, &dmax, (size_t)d, false) || dev_alloc(h, &dp, (size_t)d, false)) return PTG_ENOMEM;
+    CUDA_TRY(cudaMemcpyAsync(dl, h->lower.data(), d * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(du, h->upper.data(), d * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(dmin, h->xmin.data(), d * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(dmax, h->xmax.data(), d * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(dp, h->prior.data(), d * sizeof(PtgPrior1D), cudaMemcpyHostToDevice, h->stream));
+    m.lower_w = dl; m.upper_w = du; m.xmin_w = dmin; m.xmax_w = dmax; m.prior_w = dp;
+  }
   m.uniform_lprior = 0;
   if (m.all_uniform_prior) {
     double *d_out; rc = dev_alloc(h, &d_out, 1); if (rc) return rc;
-    ptg_uniform_lprior_kernel<<<1, 1, 0, h->stream>>>(m, d_out);
+    ptg_uniform_lprior_kernel<<<1, 1, 0, h->stream>>>(m.prior_w, m.dim, d_out);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(&m.uniform_lprior, d_out, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   }
@@ -482,7 +513,8 @@ static int do_init(ptg_handle *h, const double *x_host) {
     CUDA_TRY(cudaMemcpyAsync(d_x, x_host, cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   }
   cudaError_t e = cudaErrorInvalidValue;
-  switch (m.dim) {
+  if (h->wide) e = ptg_launch_xinit(h->cfg.rng_mode, m, s, d_x, h->stream);
+  else switch (m.dim) {
 #define X(D) case D: e = ptg_launch_init_d##D(h->cfg.rng_mode, m, s, d_x, h->stream); break;
     PTG_DIM_LIST(X)
 #undef X
@@ -547,7 +579,12 @@ extern "C" int ptg_step(ptg_handle *h, int64_t n_steps) {
   while (left > 0) {
     int chunk = (int)(left > max_chunk ? max_chunk : left);
     cudaError_t e = cudaErrorInvalidValue;
-    switch (m.dim) {
+    if (h->wide) {
+      // Philox runs take the DMMA-batched kernel; tape replay (and PTG_KERNEL_WARP) the exact-summation-order kernel
+      if (h->cfg.rng_mode == PTG_RNG_PHILOX && h->kernel_choice != PTG_KERNEL_WARP) e = ptg_launch_xmstep(m, h->s, h->istep, chunk, h->wide_trans_off, h->stream);
+      else e = ptg_launch_xstep(h->cfg.rng_mode, m, h->s, h->istep, chunk, h->stream);
+    }
+    else switch (m.dim) {
 #define X(D) case D:                                                                                                       \
       if (kern == PTG_KERNEL_FAST) e = ptg_launch_fstep_d##D(m, h->s, h->istep, chunk, W, h->stream);                       \
       else if (kern == PTG_KERNEL_WARP) e = ptg_launch_wstep_d##D(h->cfg.rng_mode, m, h->s, h->istep, chunk, W, h->stream); \
@@ -618,7 +655,8 @@ extern "C" int ptg_eval(ptg_handle *h, const double *x, int64_t n, double *logli
   double *dx = h->d_scratch, *dll = dx + (size_t)n * d, *dlp = dll + n;
   CUDA_TRY(cudaMemcpyAsync(dx, x, (size_t)n * d * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   cudaError_t e = cudaErrorInvalidValue;
-  switch (m.dim) {
+  if (h->wide) e = ptg_launch_xeval(m, dx, n, loglike ? dll : nullptr, logprior ? dlp : nullptr, h->stream);
+  else switch (m.dim) {
 #define X(D) case D: e = ptg_launch_eval_d##D(m, dx, n, loglike ? dll : nullptr, logprior ? dlp : nullptr, h->stream); break;
     PTG_DIM_LIST(X)
 #undef X

@@ -17,3 +17,9 @@
   cudaError_t ptg_launch_eval_d##D(const PtgModel &m, const double *x, long long n, double *ll, double *lp, cudaStream_t st);
 PTG_DIM_LIST(PTG_DECLARE)
 #undef PTG_DECLARE
+
+// warp-per-chain kernels for 17 <= dim <= 128 (ptg_wide.cu)
+cudaError_t ptg_launch_xstep(int mode, const PtgModel &m, const PtgState &s, long long step0, int n_steps, cudaStream_t st);
+cudaError_t ptg_launch_xmstep(const PtgModel &m, const PtgState &s, long long step0, int n_steps, int trans_off, cudaStream_t st);
+cudaError_t ptg_launch_xinit(int mode, const PtgModel &m, const PtgState &s, const double *init_x, cudaStream_t st);
+cudaError_t ptg_launch_xeval(const PtgModel &m, const double *x, long long n, double *ll, double *lp, cudaStream_t st);

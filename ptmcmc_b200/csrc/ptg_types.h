@@ -40,6 +40,11 @@ struct PtgModel {
   double xmin[PTG_TPC_MAX_DIM], xmax[PTG_TPC_MAX_DIM];
   PtgPrior1D prior[PTG_TPC_MAX_DIM];
   PtgProp props[PTG_MAX_PROPOSALS];
+  // per-dimension tables in device memory for every dim (the wide, warp-per-chain kernels index these; dim <= 16 kernels
+  // use the by-value copies above)
+  const int32_t *lower_w, *upper_w;
+  const double *xmin_w, *xmax_w;
+  const PtgPrior1D *prior_w;
   const double *lparams;      // device
   const double *ldata;        // device
   const double *prop_data;    // device: sigmas / transforms

@@ -38,11 +38,14 @@ def main():
             ref = read_ref_trace(out)
             eig = np.fromfile(out + ".eig") if spec.prop in ("cov", "covde") else np.zeros(0)
         cold = ref["rungs"][0]
+        keep = 150 if spec.dim > 16 else cold["nsize"]   # wide cases: newest 150 cold samples + digests of everything
+        cold_from = max(0, cold["nsize"] - keep)
         counters = np.array([[r[k] for k in ("nsize", "nhist", "ntries", "naccept", "last_type")] for r in ref["rungs"]], dtype=np.int64)
         finals = np.array([[r[k] for k in ("beta", "lpost", "llike", "map_lpost")] for r in ref["rungs"]])
         np.savez_compressed(os.path.join(HERE, "ref_%s.npz" % name), steps=steps, counters=counters, finals=finals,
-                            digests=np.array([rung_digest(r) for r in ref["rungs"]]), cold_x=cold["x"], cold_lpost=cold["hlpost"],
-                            cold_llike=cold["hllike"], cold_acc=cold["hacc"], cold_beta=cold["hbeta"], cold_type=cold["htype"],
+                            digests=np.array([rung_digest(r) for r in ref["rungs"]]), cold_from=cold_from, cold_x=cold["x"][cold_from:],
+                            cold_lpost=cold["hlpost"][cold_from:], cold_llike=cold["hllike"][cold_from:], cold_acc=cold["hacc"][cold_from:],
+                            cold_beta=cold["hbeta"][cold_from:], cold_type=cold["htype"][cold_from:],
                             swap_count=ref["swap_count"], swap_accept=ref["swap_accept"], directions=ref["directions"],
                             ups=ref["ups"], downs=ref["downs"], instances=ref["instances"], eig=eig)
         print("golden:", name, "cold_nsize", cold["nsize"])

@@ -285,4 +285,20 @@ def parity_cases():
         ("R24_evolve", Spec("sines", 2, 24, seed=0.31, evolve_rate=0.01, swap_rate=0.2), 500, 2),
         ("R40_two_warps", Spec("gauss", 2, 40, centers=[2, -3], halfwidths=[2, 3], seed=0.77), 300, 1),
         ("R3_high_swap_rate", Spec("gauss", 2, 3, centers=[2, -3], halfwidths=[2, 3], seed=0.41, swap_rate=0.9, Tmax=50), 800, 5),
+    ] + wide_cases()
+
+
+def wide_cases():
+    """dim > 16: the warp-per-chain kernels (BASELINE config D in small: full-covariance Gaussian, eigen-rotated proposal + DE)"""
+    d1 = fullcov_spec(100, 24, Tmax=1e4, de_ni=11, prop="covde", swap_rate=0.2)
+    d1.extra["gauss_1d_frac"] = 0.3
+    return [
+        ("W_fullcov_d20_R4", fullcov_spec(20, 4, Tmax=100), 300, 2),
+        ("W_fullcov_d40_R6_evolve", fullcov_spec(40, 6, Tmax=100, evolve_rate=0.01), 200, 1),
+        ("W_D_fullcov_d100_R8", fullcov_spec(100, 8, Tmax=1e4, de_ni=12), 120, 1),
+        ("W_gauss_d33_default_wrap", Spec("gauss", 33, 5, centers=np.linspace(-1, 1, 33), halfwidths=np.full(33, 3.0), bound="w",
+                                          extra=dict(sigma=1.5), de_ni=12), 200, 2),
+        ("W_gauss_d24_gaussprior_de", Spec("gauss", 24, 4, centers=np.zeros(24), halfwidths=np.full(24, 2.0), prior="gaussian", prop="de",
+                                           Tmax=100, extra=dict(sigma=1.0, de_unlikely_alpha=0.3), de_ni=12), 200, 1),
+        ("W_D_fullcov_d100_R24_cov1d", d1, 60, 1),
     ]

@@ -26,7 +26,8 @@ def test_philox_consistency(name, spec, steps, L, oracle_cls, engine_cls):
     assert philox_parity(oracle_cls, engine_cls, spec, min(steps, 400), L, what=name) == []
 
 
-@pytest.mark.parametrize("name", ["A_gauss2d_default", "C1_sines_d3_R32", "sines_evolve_cut", "B_poly", "D_fullcov_d6"])
+@pytest.mark.parametrize("name", ["A_gauss2d_default", "C1_sines_d3_R32", "sines_evolve_cut", "B_poly", "D_fullcov_d6", "W_D_fullcov_d100_R8",
+                                  "W_D_fullcov_d100_R24_cov1d"])
 def test_engine_matches_golden_reference_histories(name, oracle_cls, engine_cls):
     """engine (tape mode, draws recorded from the oracle's reference-RNG run) vs the COMMITTED histories of the unmodified
     reference: cold-chain positions bit-exact, lpost / llike to 1e-12"""
@@ -43,7 +44,8 @@ def test_engine_matches_golden_reference_histories(name, oracle_cls, engine_cls)
     spec.setup(e); e.inject_tapes(*tapes); e.inject_tape_marks(*marks); e.init_from_prior(); e.step(steps); e.synchronize()
     n = int(e.get_counters()["nsize"][0])
     assert n == int(g["counters"][0, 0])
-    h = e.get_history(0, 0, 0, n)
+    f = int(g["cold_from"])
+    h = e.get_history(0, 0, f, n - f)
     assert h["x"].tobytes() == g["cold_x"].tobytes()
     assert (h["type"] == g["cold_type"]).all()
     assert h["acc"].tobytes() == g["cold_acc"].tobytes()
@@ -65,6 +67,19 @@ def test_tape_parity_first_generation_kernel(name, oracle_cls, engine_cls):
             self.select_kernel(K.KERNEL_SHARED)
     _, spec, steps, L = [c for c in CASES if c[0] == name][0]
     assert tape_parity(oracle_cls, Gen1, spec, steps, L, what=name) == []
+
+
+WIDE = [c for c in CASES if c[0].startswith("W_")]
+
+
+@pytest.mark.parametrize("name,spec,steps,L", WIDE, ids=[c[0] for c in WIDE])
+def test_philox_consistency_wide_exact_kernel(name, spec, steps, L, oracle_cls, engine_cls):
+    """dim > 16, Philox draws through the exact-summation-order kernel (test_philox_consistency runs the DMMA-batched one)"""
+    class Exact(engine_cls):
+        def __init__(self, cfg):
+            super().__init__(cfg)
+            self.select_kernel(K.KERNEL_WARP)
+    assert philox_parity(oracle_cls, Exact, spec, steps, L, what=name) == []
 
 
 def test_tape_parity_with_wrapping_ring(oracle_cls, engine_cls):
@@ -105,6 +120,8 @@ def eval_cases():
     c = np.array([1, 5, np.pi] * 3)
     out.append(("sinusoid_N1e4", sp, rng.uniform(0, 2, (64, 9)) * c))
     sp = fullcov_spec(16, 2); out.append(("fullcov16", sp, rng.normal(size=(2000, 16)) * 5))
+    sp = fullcov_spec(100, 2); out.append(("fullcov100_wide", sp, rng.normal(size=(500, 100)) * 5))
+    sp = Spec("gauss", 40, 2, centers=np.zeros(40), halfwidths=np.full(40, 2.0), prior="gaussian", bound="r"); out.append(("gauss40_wide_gaussprior_reflect", sp, rng.normal(size=(500, 40)) * 3))
     sp = Spec("flat", 4, 2, centers=[0, 1, 2, 3], halfwidths=[1, 2, 3, 4], prior="mixed", prior_types=[1, 2, 1, 2], prop="gauss", bound="owrl")
     out.append(("mixed_prior_bounds", sp, rng.normal(size=(4000, 4)) * 4 + 1))
     return out
