@@ -315,8 +315,9 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.workload)
     if os.path.exists(tpath):
         t = json.load(open(tpath))  # ncu capture of the same kernel at 100 PT iterations per launch, scaled to this launch
-        traffic = t["dram_bytes_per_pt_iteration"] * S * (L * R) / 131072.0
-    roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic, kernel="ptg_step_kernel",
+        traffic = t["dram_bytes_per_pt_iteration"] * S * (L * R) / float(t.get("chains_profiled", 131072))
+    kernel_name = "ptg_xmstep_kernel" if d > 16 else ("ptg_fstep_kernel" if R <= 32 else "ptg_step_kernel")
+    roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic, kernel=kernel_name,
                     algorithmic_bytes_per_chain_step=bpcs, chain_steps_per_launch=(n1 - n0) / args.steps, launch_ms=launch_s * 1e3, peak_source=peak_src,
                     note="latency/ALU-bound fp64+Philox kernel: HBM is the stated roofline, see DESIGN.md section 5")
 
