@@ -325,6 +325,16 @@ def main():
                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", config=config, clocks=clk,
                e2e=dict(value=e2e_val, unit=unit, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=e2e_steps),
                gpu_launches=args.steps, roofline=roofline, ess=ess)
+    # ---- N > 1: the one collective of the ladder-sharded layout, the gather of cold-chain samples to rank 0 (off the hot path)
+    if world > 1:
+        from ptmcmc_b200.sharding import gather_cold_samples
+        local_t = torch.from_numpy(np.ascontiguousarray(ox)).cuda(local)
+        torch.cuda.synchronize(); tg = time.perf_counter()
+        full = gather_cold_samples(local_t, L * world, device=torch.device("cuda", local))
+        torch.cuda.synchronize(); tg = time.perf_counter() - tg
+        if rank == 0:
+            assert tuple(full.shape) == (L * world, n_out, d)
+            out["cold_gather"] = dict(ms=1e3 * tg, bytes=int(full.numel() * 8), backend="nccl", samples_per_ladder=n_out)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         procs = cpu_threads()
         n_pt = reference_pt_steps(w, 10.0)
