@@ -69,6 +69,23 @@ def test_tape_parity_first_generation_kernel(name, oracle_cls, engine_cls):
     assert tape_parity(oracle_cls, Gen1, spec, steps, L, what=name) == []
 
 
+def max_size_cases():
+    """the limits of every kernel family: dim 16 (thread-per-chain), dim 128 x 32 rungs (warp-per-chain, 1024-thread CTAs),
+    64 rungs (shared-memory kernel, two warps per ladder), 1 rung x dim 1"""
+    return [
+        ("max_dim16_R8", fullcov_spec(16, 8, Tmax=1e3, de_ni=12), 150, 2),
+        ("max_dim128_R32", fullcov_spec(128, 32, Tmax=1e4, de_ni=11, swap_rate=0.05), 40, 1),
+        ("max_R64", Spec("gauss", 2, 64, centers=[2, -3], halfwidths=[2, 3], seed=0.55, swap_rate=0.05), 200, 1),
+        ("min_dim1_R1", Spec("gauss", 1, 1, centers=[0.5], halfwidths=[2.0], prop="gauss", seed=0.66), 500, 3),
+    ]
+
+
+@pytest.mark.parametrize("name,spec,steps,L", max_size_cases(), ids=[c[0] for c in max_size_cases()])
+def test_parity_at_size_limits(name, spec, steps, L, oracle_cls, engine_cls):
+    assert tape_parity(oracle_cls, engine_cls, spec, steps, L, what=name) == []
+    assert philox_parity(oracle_cls, engine_cls, spec, steps, L, what=name) == []
+
+
 WIDE = [c for c in CASES if c[0].startswith("W_")]
 
 
