@@ -579,7 +579,15 @@ extern "C" int ptg_step(ptg_handle *h, int64_t n_steps) {
   while (left > 0) {
     int chunk = (int)(left > max_chunk ? max_chunk : left);
     cudaError_t e = cudaErrorInvalidValue;
-    if (h->wide) {
+    // Data chi-squared likelihoods on a batch too small to fill the GPU with one thread per chain (BASELINE config B: 16 384
+    // chains): one WARP per chain, the data loop spread over its lanes (ptg_wide_mma.cuh).  Philox runs, automatic selection only.
+    const bool data_like = m.like_kind == PTG_LIKE_POLY_CHI2 || m.like_kind == PTG_LIKE_SINUSOID_CHI2;
+    bool has_prior_draw = false;
+    for (const HostProp &hp : h->props) if (hp.p.kind == PTG_PROP_PRIOR_DRAW) has_prior_draw = true;
+    const bool warp_per_chain = !h->wide && data_like && !has_prior_draw && h->cfg.rng_mode == PTG_RNG_PHILOX && h->kernel_choice == PTG_KERNEL_AUTO && m.n_rungs <= 32 &&
+                                m.dim <= (m.like_kind == PTG_LIKE_POLY_CHI2 ? 16 : 18) && m.n_chains <= 48 * 1024;
+    if (warp_per_chain) e = ptg_launch_xmstep(m, h->s, h->istep, chunk, -1, h->stream);
+    else if (h->wide) {
       // Philox runs take the DMMA-batched kernel; tape replay (and PTG_KERNEL_WARP) the exact-summation-order kernel
       if (h->cfg.rng_mode == PTG_RNG_PHILOX && h->kernel_choice != PTG_KERNEL_WARP) e = ptg_launch_xmstep(m, h->s, h->istep, chunk, h->wide_trans_off, h->stream);
       else e = ptg_launch_xstep(h->cfg.rng_mode, m, h->s, h->istep, chunk, h->stream);

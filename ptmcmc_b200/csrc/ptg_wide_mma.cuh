@@ -32,6 +32,131 @@ __device__ __forceinline__ void xcta_dmma(const double *In, const double *__rest
   }
 }
 
+// Swap phase of one ladder on the 32 lanes of warp 0 (Philox draws): lane r holds rung r's scalars and the INDEX of the state
+// it carries; the trial logic is the shuffle version of ptg_fast.cuh (every lane prepares its own trial, bit-mask de-dup,
+// one shuffle round per surviving trial, shuffle-scan pry_temps).  Reads the published scalars, writes the same outcome
+// arrays as the serial leader of ptg_wide.cuh (perm, napp, app_*, n_lpost, n_beta, ladder statistics).
+__device__ __forceinline__ void xswap_warp(const PtgModel &m, XShared &L, uint64_t ladder_stream, uint64_t step, int lane, int maxswaps, double swap_thresh,
+                                           double ptry) {
+  const int R = m.n_rungs;
+  const unsigned gm = 0xffffffffu;
+  const bool act = lane < R;
+  double ll = act ? L.sll[lane] : 0.0, lprior = act ? L.slprior[lane] : 0.0, beta = act ? L.sbeta[lane] : 1.0, lpost = act ? L.slpost[lane] : 0.0;
+  int perm = lane, napp = 0, as0 = 0, as1 = 0;
+  double al0 = 0, al1 = 0, ab0 = 0, ab1 = 0;
+  int dir = act ? L.dir[lane] : 0, inst = act ? L.inst[lane] : 0, ups = 0, downs = 0, sc = 0, sa = 0;
+  auto record = [&]() {
+    if (napp == 0) { as0 = perm; al0 = lpost; ab0 = beta; } else if (napp == 1) { as1 = perm; al1 = lpost; ab1 = beta; }
+    napp++;
+  };
+  if (m.swap_mode == PTG_SWAP_REFERENCE) {
+    int raw = -2;
+    double logu = 0;
+    if (lane < maxswaps) {
+      uint32_t q[4];
+      ptg_philox_draw(m.seed, ladder_stream, PTG_DOMAIN_STEP, step, (uint32_t)lane, q);
+      if (ptg_u32_to_unit(q[0]) < swap_thresh) {
+        raw = (int)(ptg_u32_to_unit(q[1]) * (R - 1));
+        logu = log(ptg_u52_to_unit(q[2], q[3]));
+      }
+    }
+    unsigned used = 0, live = 0;
+    unsigned cand = __ballot_sync(gm, raw >= 0);
+    while (cand) {
+      const int i = __ffs(cand) - 1;
+      cand &= cand - 1;
+      const int c = __shfl_sync(gm, raw, i);
+      if (!((used >> c) & 1u) && !(c > 0 && ((used >> (c - 1)) & 1u))) { used |= 1u << c; live |= 1u << i; }
+    }
+    while (live) {
+      const int j = __ffs(live) - 1;
+      live &= live - 1;
+      const int c = __shfl_sync(gm, raw, j);
+      const double lu = __shfl_sync(gm, logu, j);
+      const double ll_up = __shfl_down_sync(gm, ll, 1), b_up = __shfl_down_sync(gm, beta, 1);
+      double lla = ll; if (!(lla > -1e200)) lla = -1e200;
+      double llb = ll_up; if (!(llb > -1e200)) llb = -1e200;
+      const double lhr = -(b_up - beta) * (llb - lla);
+      int acc_mine = 1;
+      if (lhr < 0) acc_mine = (lu < lhr) ? 1 : 0;
+      const bool accept = __shfl_sync(gm, acc_mine, c) != 0;
+      const bool is_lo = (lane == c), is_hi = (lane == c + 1), involved = is_lo || is_hi;
+      if (is_lo && c > 0) { if (dir > 0) ups++; if (dir < 0) downs++; }
+      const int partner = is_lo ? c + 1 : (is_hi ? c : lane);
+      if (accept) {
+        { const double v = __shfl_sync(gm, ll, partner); ll = v; }
+        { const double v = __shfl_sync(gm, lprior, partner); lprior = v; }
+        { const int v = __shfl_sync(gm, perm, partner); perm = v; }
+        if (involved) lpost = lprior + beta * ll;
+      }
+      if (involved) record();
+      if (accept) {
+        { const int v = __shfl_sync(gm, dir, partner); dir = v; }
+        { const int v = __shfl_sync(gm, inst, partner); inst = v; }
+        if (c == 0 && is_lo) dir = 1;
+        if (c + 1 == R - 1 && is_hi) dir = -1;
+        if (is_lo) sa++;
+        if (m.evolve_rate > 0) {
+          const double rate = m.evolve_rate;
+          const double b_next = __shfl_down_sync(gm, beta, 1), lp_next = __shfl_down_sync(gm, lpost, 1);
+          double sp = beta - b_next;
+          if (m.evolve_lpost_cut >= 0 && lpost - lp_next > m.evolve_lpost_cut * beta) sp *= (1.0 + rate);
+          if (is_lo) sp *= 1.0 + rate;
+          double sum = 0;
+          for (int k = 0; k < R - 1; k++) sum += __shfl_sync(gm, sp, k);
+          const double norm = sum / (1 - __shfl_sync(gm, beta, R - 1));
+          const double qn = sp / norm;
+          double invtemp = 1, mine = beta;
+          for (int k = 1; k < R - 1; k++) {
+            invtemp -= __shfl_sync(gm, qn, k - 1);
+            if (lane == k) mine = invtemp;
+          }
+          if (lane >= 1 && lane < R - 1) { beta = mine; lpost = lprior + mine * ll; }
+        }
+      }
+      if (is_lo) sc++;
+    }
+  } else {
+    const int parity = (int)(step & 1);
+    const bool is_lo = ((lane & 1) == parity) && (lane + 1 < R);
+    const bool is_hi = (lane >= 1) && (((lane - 1) & 1) == parity) && (lane < R);
+    const int partner = is_lo ? lane + 1 : (is_hi ? lane - 1 : lane);
+    const double ll_p = __shfl_sync(gm, ll, partner), b_p = __shfl_sync(gm, beta, partner);
+    int flags = 0;
+    if (is_lo) {
+      uint32_t q[4];
+      ptg_philox_draw(m.seed, ladder_stream, PTG_DOMAIN_STEP, step, PTG_BLK_SWAP_EVENODD + (uint32_t)lane, q);
+      if (ptg_u52_to_unit(q[0], q[1]) < ptry) {
+        double lla = ll; if (!(lla > -1e200)) lla = -1e200;
+        double llb = ll_p; if (!(llb > -1e200)) llb = -1e200;
+        const double lhr = -(b_p - beta) * (llb - lla);
+        bool accept = true;
+        if (lhr < 0) accept = (log(ptg_u52_to_unit(q[2], q[3])) < lhr);
+        flags = 1 | (accept ? 2 : 0);
+        if (lane > 0) { if (dir > 0) ups++; if (dir < 0) downs++; }
+        sc++; if (accept) sa++;
+      }
+    }
+    const int pflags = __shfl_sync(gm, flags, partner);
+    if (is_hi) flags = pflags;
+    const bool tried = (flags & 1) != 0, accept = (flags & 2) != 0;
+    const double nll = __shfl_sync(gm, ll, partner), nlp = __shfl_sync(gm, lprior, partner);
+    const int nperm = __shfl_sync(gm, perm, partner), ndir = __shfl_sync(gm, dir, partner), ninst = __shfl_sync(gm, inst, partner);
+    if (tried && accept) {
+      ll = nll; lprior = nlp; perm = nperm; lpost = lprior + beta * ll; dir = ndir; inst = ninst;
+      if (lane == 0) dir = 1;
+      if (lane == R - 1) dir = -1;
+    }
+    if (tried) record();
+  }
+  if (act) {
+    L.perm[lane] = perm; L.napp[lane] = napp; L.n_lpost[lane] = lpost; L.n_beta[lane] = beta;
+    L.app_src[2 * lane] = as0; L.app_src[2 * lane + 1] = as1;
+    L.app_lpost[2 * lane] = al0; L.app_lpost[2 * lane + 1] = al1; L.app_beta[2 * lane] = ab0; L.app_beta[2 * lane + 1] = ab1;
+    L.dir[lane] = dir; L.inst[lane] = inst; L.ups[lane] += ups; L.downs[lane] += downs; L.scount[lane] += sc; L.saccept[lane] += sa;
+  }
+}
+
 template <int CPL>
 __device__ __forceinline__ double xsum_tree(const double v[CPL]) {
   double a = 0;
@@ -40,6 +165,59 @@ __device__ __forceinline__ double xsum_tree(const double v[CPL]) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
   return a;
+}
+
+// chi-squared likelihoods over data (bayesian.hh:595-622; polynomial model poly_example.cc:85-106, sum of sinusoids) with the
+// DATA loop spread over the lanes of the chain's warp: lane l takes points l, l+32, ...; the partial sums meet in a shuffle
+// tree.  Used when the batch has too few chains to fill the GPU with one thread per chain (BASELINE config B: 16 384 chains).
+// dim <= 32 (CPL = 1): parameter j lives in lane j.
+__device__ __forceinline__ double xlike_data_parallel(const PtgModel &m, double xmine, int lane) {
+  const int D = m.dim;
+  const long long N = m.n_ldata / 3;
+  const double *__restrict__ xs = m.ldata, *__restrict__ ys = m.ldata + N, *__restrict__ S = m.ldata + 2 * N;
+  double part = 0;
+  if (m.like_kind == PTG_LIKE_POLY_CHI2) {
+    // D is small (5 in config B): coefficients are pulled once per step; the inner loop is the reference's `y+=xn*c_j; xn*=x_k`
+    double cj[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) cj[j] = __shfl_sync(0xffffffffu, xmine, j);
+    // four independent partial sums per lane: the per-point work (D multiply-adds and an fp64 division) pipelines
+    double p4[4] = {0, 0, 0, 0};
+    for (long long i0 = lane; i0 < N; i0 += 128) {
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const long long i = i0 + 32 * u;
+        if (i < N) {
+          const double xi = __ldg(xs + i);
+          double y = 0, xn = 1;
+#pragma unroll
+          for (int j = 0; j < 16; j++) if (j < D) { y += xn * cj[j]; xn *= xi; }
+          const double dd = y - __ldg(ys + i);
+          p4[u] += dd * dd / __ldg(S + i);
+        }
+      }
+    }
+    part = (p4[0] + p4[1]) + (p4[2] + p4[3]);
+  } else {
+    double cj[18];
+#pragma unroll
+    for (int j = 0; j < 18; j++) cj[j] = __shfl_sync(0xffffffffu, xmine, j);
+    for (long long i = lane; i < N; i += 32) {
+      const double ti = __ldg(xs + i);
+      double y = 0;
+#pragma unroll
+      for (int k = 0; k + 2 < 18; k += 3) if (k + 2 < D) y += cj[k] * sin(2 * PTG_PI * cj[k + 1] * ti + cj[k + 2]);
+      const double dd = y - __ldg(ys + i);
+      part += dd * dd / __ldg(S + i);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  double sum = part + m.like_nsum;
+  sum /= -2;
+  double result = sum - __ldg(m.lparams);
+  if (!isfinite(result)) result = -CUDART_INF;
+  return result;
 }
 
 template <int CPL, int MAXT>
@@ -79,7 +257,20 @@ __global__ void __launch_bounds__(MAXT) ptg_xmstep_kernel(const __grid_constant_
 
   for (int it = 0; it < n_steps; it++) {
     const uint64_t step = (uint64_t)(step0 + it);
-    xpublish_and_swap<CPL, MODE>(m, L, ch, ls, step, myx, lane, rung, maxswaps, swap_thresh, ptry);
+    // publish, then warp 0 runs the ladder's swap phase on shuffles (falls back to the serial leader if a step has more
+    // trials than lanes)
+    if (maxswaps <= 32) {
+#pragma unroll
+      for (int k = 0; k < CPL; k++) { const int c = CPL * lane + k; if (c < D) myx[c] = ch.x[k]; }
+      if (lane == 0) {
+        L.sll[rung] = ch.llike; L.slpost[rung] = ch.lpost; L.slprior[rung] = ch.lprior; L.sbeta[rung] = ch.beta;
+        L.n_lpost[rung] = ch.lpost; L.n_beta[rung] = ch.beta; L.perm[rung] = rung; L.napp[rung] = 0;
+      }
+      __syncthreads();
+      if (R > 1 && rung == 0)
+        xswap_warp(m, L, (uint64_t)(m.ladder_offset + ladder) * PTG_STREAM_STRIDE + PTG_STREAM_LADDER, step, lane, maxswaps, swap_thresh, ptry);
+      __syncthreads();
+    } else xpublish_and_swap<CPL, MODE>(m, L, ch, ls, step, myx, lane, rung, maxswaps, swap_thresh, ptry);
     const int na = L.napp[rung];
     ch.beta = L.n_beta[rung];
     const bool mh = (na == 0);
@@ -212,7 +403,10 @@ __global__ void __launch_bounds__(MAXT) ptg_xmstep_kernel(const __grid_constant_
           if (!isfinite(newlike)) newlike = -CUDART_INF;
         }
       }
-    } else if (mh && gate) newlike = xlike<CPL>(m, newx, rowA, rowB, lane);
+    } else if (mh && gate) {
+      if (m.like_kind == PTG_LIKE_POLY_CHI2 || m.like_kind == PTG_LIKE_SINUSOID_CHI2) newlike = xlike_data_parallel(m, newx[0], lane);
+      else newlike = xlike<CPL>(m, newx, rowA, rowB, lane);
+    }
     // ---------------------------------------------------------------- phase C: Metropolis test, append
     double lhr = 0; int code = PTG_TRACE_SWAPPED;
     if (mh) {

@@ -284,6 +284,9 @@ def parity_cases():
         # ladder widths of the warp kernel: 24 rungs in a 32-lane group (ghost lanes), 40 rungs (shared-memory kernel)
         ("R24_evolve", Spec("sines", 2, 24, seed=0.31, evolve_rate=0.01, swap_rate=0.2), 500, 2),
         ("R40_two_warps", Spec("gauss", 2, 40, centers=[2, -3], halfwidths=[2, 3], seed=0.77), 300, 1),
+        # history shorter than 10 d at the start: differential evolution is not ready and the set falls through to the next
+        # ready member whose bin covers the draw (proposal_distribution.cc:105-112, proposal_distribution.hh:399-407)
+        ("de_not_ready", Spec("gauss", 2, 4, centers=[2, -3], halfwidths=[2, 3], seed=0.83, de_ni=3, Tmax=100), 300, 3),
         ("R3_high_swap_rate", Spec("gauss", 2, 3, centers=[2, -3], halfwidths=[2, 3], seed=0.41, swap_rate=0.9, Tmax=50), 800, 5),
     ] + wide_cases()
 

@@ -55,6 +55,7 @@ KERNEL_CASES = [
     ("bounded_unlikely_alpha", Spec("gauss", 3, 6, centers=[2, -3, 5], halfwidths=[2, 3, 5], bound="w", extra=dict(sigma=3.0, de_unlikely_alpha=0.5)), {}),
     ("gaussian_prior_prior_draw", Spec("gauss", 2, 5, centers=[2, -3], halfwidths=[2, 3], prop="prior", prior="mixed", prior_types=[1, 2]), {}),
     ("single_chain", Spec("sines", 2, 1, prop="de"), {}),
+    ("de_not_ready_at_start", Spec("gauss", 2, 4, centers=[2, -3], halfwidths=[2, 3], de_ni=3, Tmax=100), {}),
 ]
 
 
@@ -133,6 +134,28 @@ def test_swap_modes_agree_statistically(engine_cls):
         idx = (x.reshape(-1, 3) * 2).astype(int).clip(0, 1).sum(axis=1)
         ps.append(np.bincount(idx, minlength=4) / idx.size)
     assert np.allclose(ps[0], ps[1], atol=0.02), ps
+
+
+def test_api_edge_cases(engine_cls):
+    """zero-length steps, default / too-small ring capacity, pure-DE set before its history is ready"""
+    spec = Spec("gauss", 2, 4, centers=[2, -3], halfwidths=[2, 3])
+    e = engine_cls(spec.config(n_ladders=2, hist_capacity=10))   # smaller than n_init = 100: raised to n_init
+    spec.setup(e); e.init_from_prior()
+    e.step(0); e.synchronize()
+    assert e.get_total_steps() == 0 and (e.get_counters()["nsize"] == 100).all()
+    e.step(30); e.synchronize()
+    cnt = e.get_counters()
+    assert (cnt["nhist"] >= 30).all()
+    h = e.get_history(0, 0, int(cnt["nsize"][0]) - 100, 100)     # the newest `capacity` samples are readable
+    assert np.isfinite(h["x"]).all()
+    # a bare differential_evolution before 10 d samples exist: the reference's set would find no ready member
+    spec2 = Spec("gauss", 2, 4, centers=[2, -3], halfwidths=[2, 3], de_ni=3, extra=dict())
+    e2 = engine_cls(spec2.config(n_ladders=1))
+    spec2.setup(e2)
+    e2.set_proposals([dict(kind=K.PROP_DE, share=1.0)], wrap_in_set=True)
+    e2.init_from_prior(); e2.step(5)
+    with pytest.raises(K.CApiError, match="no member ready"):
+        e2.synchronize()
 
 
 def test_error_behaviour(engine_cls):
