@@ -183,7 +183,17 @@ def main():
     ap.add_argument("--ladders", type=int, default=0, help="ladders per GPU (default: per workload)")
     ap.add_argument("--swap-mode", default="reference", choices=["reference", "even_odd"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--peaks", action="store_true", help="measure the FP64 peaks (DFMA, DMUL+DADD, DMMA) of cuda:0, print them as JSON and exit")
     args = ap.parse_args()
+    if args.peaks:
+        import ctypes as C
+        from ptmcmc_b200._lib import load
+        out = (C.c_double * 4)()
+        rc = load().ptg_measure_fp64_peaks(C.c_int32(0), out)
+        assert rc == 0, rc
+        print(json.dumps(dict(fp64_dfma_tflops=out[0], fp64_dmul_dadd_tflops=out[1], fp64_dmma_tflops=out[2], sm_count=int(out[3]),
+                              how="ptmcmc_b200/csrc/ptg_peaks.cu: 8 independent chains per thread x 20000 iterations, 148x8 CTAs x 256 threads, best of 3, CUDA events")))
+        return 0
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     w = dict(WORKLOADS[args.workload])

@@ -204,6 +204,10 @@ int ptg_set_stream(ptg_handle *h, void *cuda_stream);
  * authoritative does before each block of steps).  Asynchronous on the handle's stream. */
 int ptg_set_current(ptg_handle *h, const double *x, const double *lpost, const double *llike, const double *lprior);
 
+/* FP64 peak microbenchmarks on `device` (the FP64 roofline denominators): out[0] = DFMA TFLOP/s,
+ * out[1] = DMUL+DADD pairs (the engine's unfused arithmetic) TFLOP/s, out[2] = DMMA (mma.sync.m8n8k4.f64) TFLOP/s, out[3] = SM count */
+int ptg_measure_fp64_peaks(int32_t device, double *out);
+
 /* checkpoint / restore of the complete engine state (restart.hh semantics; format in DESIGN.md) */
 int ptg_checkpoint(ptg_handle *h, const char *path);
 int ptg_restore(ptg_handle *h, const char *path);

@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(128, PTG_FSTEP_MINB) ptg_fstep_kernel(const __
       const double *s1 = fhist<D>(m, ch, hbase, i1), *s2 = fhist<D>(m, ch, hbase, i2);
       double a[D], b[D];
 #pragma unroll
-      for (int i = 0; i < D; i++) { a[i] = s1[i]; b[i] = s2[i]; }
+      for (int i = 0; i < D; i++) { a[i] = __ldcg(s1 + i); b[i] = __ldcg(s2 + i); } // random records: no reuse, keep them out of L1
       if (!snooker) {
         // draw_standard: prop = (s + gamma s1) + (-gamma s2); the jitter drawn by the reference is discarded (H8-1)
         double gamma = p.gamma_std;

@@ -2,8 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "ptg_types.h"
-#ifdef PTG_DEV_DIM3  // developer build: `make DEV=1` compiles only dim=3 (seconds instead of minutes)
-#define PTG_DIM_LIST(X) X(3)
+#ifdef PTG_DEV_DIM3  // developer build: `make DEV=1` compiles only dim = 3, 5, 9 (seconds instead of minutes)
+#define PTG_DIM_LIST(X) X(3) X(5) X(9)
 #else
 #define PTG_DIM_LIST(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(12) X(16)
 #endif
