@@ -183,6 +183,8 @@ def main():
     ap.add_argument("--ladders", type=int, default=0, help="ladders per GPU (default: per workload)")
     ap.add_argument("--swap-mode", default="reference", choices=["reference", "even_odd"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rung-sharded", type=int, default=0, metavar="K",
+                    help="optional layout: ONE (n_gpus x rungs)-rung ladder family sharded by rung blocks, cross-GPU boundary swaps over NCCL every K PT iterations")
     ap.add_argument("--peaks", action="store_true", help="measure the FP64 peaks (DFMA, DMUL+DADD, DMMA) of cuda:0, print them as JSON and exit")
     args = ap.parse_args()
     if args.peaks:
@@ -242,6 +244,45 @@ def main():
 
     spec = make_spec(w)
     L, R, d, S = w["ladders"], w["rungs"], w["dim"], w["pt_steps"]
+    if args.rung_sharded:
+        # ---- optional rung-sharded layout (ptmcmc_b200/rung_sharding.py): the same ladders on every rank, a different rung block
+        from ptmcmc_b200.rung_sharding import RungShardedLadders, rank_betas
+        eng = Engine(spec.config(n_ladders=L, rng_mode=K.RNG_PHILOX, record_level=K.RECORD_BASIC, hist_capacity=w["hist"], device=local,
+                                 seed=0xB2000003 + 977 * rank))
+        spec.setup(eng)
+        eng.set_betas(rank_betas(L, R, rank, world, spec.Tmax))
+        stream = torch.cuda.Stream()
+        eng.set_stream(stream.cuda_stream)
+        with torch.cuda.stream(stream):
+            eng.init_from_prior(); eng.synchronize()
+            drv = RungShardedLadders(eng, rank, world, 0xB2005EED, exchange_every=args.rung_sharded, device="cuda:%d" % local)
+            for _ in range(args.warmup):
+                drv.run(S)
+            eng.synchronize(); n0 = eng.get_total_steps()
+            barrier(); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                drv.run(S)
+            eng.synchronize(); torch.cuda.synchronize(); barrier()
+            dt = time.perf_counter() - t0
+            n1 = eng.get_total_steps()
+            # cost of the exchange step alone
+            torch.cuda.synchronize(); t1 = time.perf_counter()
+            for _ in range(20):
+                drv.exchange()
+            eng.synchronize(); torch.cuda.synchronize(); ex_ms = 1e3 * (time.perf_counter() - t1) / 20
+        val = sum_over_ranks(n1 - n0) / max_over_ranks(dt)
+        config["parallelism"] = "rung-sharded: %d ladders x (%d GPUs x %d rungs), boundary swaps over NCCL every %d PT iterations" % (L, world, R, args.rung_sharded)
+        ms_step = 1e3 * max_over_ranks(dt) / args.steps
+        if rank == 0:
+            print(json.dumps(dict(metric=metric, value=val, unit=unit, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_step,
+                                  higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", config=config,
+                                  exchange=dict(ms=ex_ms, bytes_per_rank=int(2 * L * (d + 3) * 8), collective="2 x all_gather_into_tensor (NCCL)"),
+                                  gpu_launches=args.steps * ((S + args.rung_sharded - 1) // args.rung_sharded) * 5)))
+        eng.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
     swap_mode = K.SWAP_REFERENCE if args.swap_mode == "reference" else K.SWAP_EVEN_ODD
     eng = Engine(spec.config(n_ladders=L, rng_mode=K.RNG_PHILOX, record_level=K.RECORD_BASIC, hist_capacity=w["hist"], swap_mode=swap_mode,
                              device=local, ladder_offset=rank * L, seed=0xB2000003))

@@ -204,6 +204,22 @@ int ptg_set_stream(ptg_handle *h, void *cuda_stream);
  * authoritative does before each block of steps).  Asynchronous on the handle's stream. */
 int ptg_set_current(ptg_handle *h, const double *x, const double *lpost, const double *llike, const double *lprior);
 
+/* Rung-sharded ladders (the reference's MPI layout, chain.cc:1290-1311,1433-1435, with block rung assignment): every GPU holds
+ * a contiguous block of rungs of EVERY ladder (explicit betas via ptg_set_betas); replica swaps inside a block run in the step
+ * kernels, swaps ACROSS a block boundary are a separate exchange step between launches:
+ *   ptg_boundary_pack  writes rung `rung` of every ladder as rec[ladder] = (x[dim], llike, lprior, beta) into DEVICE memory
+ *                      `out_dev` ([n_ladders][dim+3] doubles) -- the payload that crosses NVLink (NCCL or peer copy);
+ *   ptg_boundary_swap  performs the swap trial (chain.cc:1459-1490) between this engine's rung `my_rung` and the neighbour's packed
+ *                      rung for every ladder and appends the outcome to this chain's history (both chains of a trial append,
+ *                      chain.cc:1487-1534).  Both sides call it with each other's packs; the acceptance draw comes from the ladder's
+ *                      Philox stream under `shared_seed` (domain PTG_DOMAIN_BOUNDARY, step = exchange_index, block = boundary_id),
+ *                      so they reach the same decision without communicating it -- as the reference replicates swap decisions
+ *                      from the shared seed (ptmcmc.cc:263-268).  Engines of different ranks must use different `seed`s for
+ *                      their chains' own streams. */
+int ptg_boundary_pack(ptg_handle *h, int32_t rung, void *out_dev);
+int ptg_boundary_swap(ptg_handle *h, int32_t my_rung, const void *neighbour_pack_dev, int32_t i_am_lower, uint64_t shared_seed,
+                      int64_t boundary_id, int64_t exchange_index);
+
 /* FP64 peak microbenchmarks on `device` (the FP64 roofline denominators): out[0] = DFMA TFLOP/s,
  * out[1] = DMUL+DADD pairs (the engine's unfused arithmetic) TFLOP/s, out[2] = DMMA (mma.sync.m8n8k4.f64) TFLOP/s, out[3] = SM count */
 int ptg_measure_fp64_peaks(int32_t device, double *out);

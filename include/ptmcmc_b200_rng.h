@@ -14,7 +14,7 @@
  *                ((step >> 32) & 0xfff) << 20 | domain << 16 | ((stream >> 32) & 0xffff) )
  *   stream   = global_ladder * 128 + rung          for a chain's own generator
  *            = global_ladder * 128 + 127           for the ladder's generator (swap scheduling/tests)
- *   domain   = 0 stepping (step = PT iteration), 1 initialisation (step = index of the prior draw)
+ *   domain   = 0 stepping (step = PT iteration), 1 initialisation (step = index of the prior draw), 2 cross-GPU boundary swaps
  *
  * Like MotherOfAll::Next() = (seed+0.5)/2^32 (newran1.cxx:432) every uniform lies in the OPEN interval
  * (0,1): u32 = (w+0.5)*2^-32, u52 = ((w0<<20 | w1>>12)+0.5)*2^-52.
@@ -27,6 +27,8 @@
 #define PTG_STREAM_LADDER 127
 #define PTG_DOMAIN_STEP 0
 #define PTG_DOMAIN_INIT 1
+#define PTG_DOMAIN_BOUNDARY 2   /* rung-sharded ladders: swap trial across a GPU boundary; step = exchange index, block = boundary id,
+                                   (w0,w1) u_swap (u52), drawn from the ladder's stream under the SHARED key */
 
 /* blocks of a chain's stream within one MH step (domain 0): two blocks carry every draw of a common step */
 #define PTG_BLK_A 0           /* w0 u_sel | w1 u_snooker (DE) / u_1d (GAUSS) | w2 u_gamma (DE) / u_axis (GAUSS) | w3 DE index s1  (u32) */

@@ -1028,6 +1028,40 @@ int pto_get_swap_stats(pto_handle *h, int64_t *sc, int64_t *sa, int32_t *dir, in
   if (inst) memcpy(inst, h->instances, (size_t)h->nchains * sizeof(int32_t));
   return 0;
 }
+/* rung-sharded ladders: restatement of ptg_boundary_pack / ptg_boundary_swap (host memory) */
+int pto_boundary_pack(pto_handle *h, int32_t rung, void *out) {
+  double *o = (double *)out;
+  for (int l = 0; l < h->L; l++) {
+    chain_t *c = &h->chains[(size_t)l * h->R + rung];
+    double *rec = o + (size_t)l * (h->d + 3);
+    memcpy(rec, c->x, (size_t)h->d * sizeof(double));
+    rec[h->d] = c->llike; rec[h->d + 1] = prior_eval_log(h, c->x, 1); rec[h->d + 2] = c->beta;
+  }
+  return 0;
+}
+int pto_boundary_swap(pto_handle *h, int32_t my_rung, const void *nb, int32_t i_am_lower, uint64_t shared_seed, int64_t boundary_id, int64_t exchange_index) {
+  const double *pk = (const double *)nb;
+  for (int l = 0; l < h->L; l++) {
+    chain_t *c = &h->chains[(size_t)l * h->R + my_rung];
+    const double *rec = pk + (size_t)l * (h->d + 3);
+    const double nb_ll = rec[h->d], nb_lprior = rec[h->d + 1], nb_beta = rec[h->d + 2];
+    double lla = i_am_lower ? c->llike : nb_ll; if (!(lla > -1e200)) lla = -1e200;
+    double llb = i_am_lower ? nb_ll : c->llike; if (!(llb > -1e200)) llb = -1e200;
+    const double ba = i_am_lower ? c->beta : nb_beta, bb = i_am_lower ? nb_beta : c->beta;
+    const double lhr = -(bb - ba) * (llb - lla);
+    int accept = 1;
+    if (lhr < 0) {
+      uint32_t w[4];
+      ptg_philox_draw(shared_seed, (uint64_t)(h->cfg.ladder_offset + l) * PTG_STREAM_STRIDE + PTG_STREAM_LADDER, PTG_DOMAIN_BOUNDARY, (uint64_t)exchange_index,
+                      (uint32_t)boundary_id, w);
+      accept = (log(ptg_u52_to_unit(w[0], w[1])) < lhr);
+    }
+    if (accept) add_state(h, c, rec, nb_ll, nb_lprior + c->beta * nb_ll);
+    else add_state(h, c, c->x, c->llike, c->lpost);
+    if (i_am_lower) { h->swap_count[(size_t)l * (h->R > 1 ? h->R - 1 : 1) + (my_rung < h->R - 1 ? my_rung : 0)] += 0; }
+  }
+  return 0;
+}
 int pto_get_trace(pto_handle *h, int64_t first, int64_t count, double *lhr, int32_t *code) {
   if (first < 0 || first + count > h->cfg.trace_steps || first + count > h->istep) return fail(PTG_EINVAL, "trace range");
   if (lhr) memcpy(lhr, h->trace_lhr + (size_t)first * h->nchains, (size_t)count * h->nchains * sizeof(double));

@@ -49,6 +49,8 @@ int pto_get_history(pto_handle *h, int32_t ladder, int32_t rung, int64_t first, 
 int pto_get_swap_stats(pto_handle *h, int64_t *swap_count, int64_t *swap_accept, int32_t *directions, int32_t *ups, int32_t *downs, int32_t *instances);
 int pto_get_trace(pto_handle *h, int64_t first, int64_t count, double *lhr, int32_t *code);
 int pto_get_total_steps(pto_handle *h, int64_t *total);
+int pto_boundary_pack(pto_handle *h, int32_t rung, void *out);
+int pto_boundary_swap(pto_handle *h, int32_t my_rung, const void *nb, int32_t i_am_lower, uint64_t shared_seed, int64_t boundary_id, int64_t exchange_index);
 /* stand-alone evaluation helpers for unit tests (n states, row-major x[n][dim]) */
 int pto_eval_loglike(pto_handle *h, const double *x, int64_t n, double *out);
 int pto_eval_logprior(pto_handle *h, const double *x, int64_t n, double *out);

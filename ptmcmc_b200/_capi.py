@@ -197,5 +197,13 @@ class CApi:
         self._call("get_trace", self.h, C.c_int64(first), C.c_int64(count), _dp(lhr), _ip(code, C.c_int32))
         return lhr, code
 
+    # ---- rung-sharded ladders (buffers are raw addresses: device memory for the engine, host memory for the test oracle)
+    def boundary_pack(self, rung, out_ptr):
+        self._call("boundary_pack", self.h, C.c_int32(rung), C.c_void_p(out_ptr))
+
+    def boundary_swap(self, my_rung, neighbour_pack_ptr, i_am_lower, shared_seed, boundary_id, exchange_index):
+        self._call("boundary_swap", self.h, C.c_int32(my_rung), C.c_void_p(neighbour_pack_ptr), C.c_int32(1 if i_am_lower else 0),
+                   C.c_uint64(shared_seed), C.c_int64(boundary_id), C.c_int64(exchange_index))
+
     def get_total_steps(self):
         t = C.c_int64(); self._call("get_total_steps", self.h, C.byref(t)); return t.value

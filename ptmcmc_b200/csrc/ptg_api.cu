@@ -835,6 +835,84 @@ extern "C" int ptg_set_stream(ptg_handle *h, void *cuda_stream) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------- rung-sharded ladders
+__global__ void ptg_boundary_pack_kernel(PtgModel m, PtgState s, int rung, double *out) {
+  const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= m.n_ladders) return;
+  const long long c = l * m.n_rungs + rung;
+  const int D = m.dim;
+  double *rec = out + l * (D + 3);
+  for (int k = 0; k < D; k++) rec[k] = s.cur_x[(long long)k * m.n_chains + c];
+  rec[D] = s.llike[c]; rec[D + 1] = s.lprior[c]; rec[D + 2] = s.beta[c];
+}
+// one thread per ladder: swap trial between my rung and the neighbour's packed rung (chain.cc:1459-1490), then add_state
+__global__ void ptg_boundary_swap_kernel(PtgModel m, PtgState s, int rung, const double *__restrict__ nb, int i_am_lower, uint64_t shared_seed,
+                                         long long boundary_id, long long exchange_index) {
+  const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= m.n_ladders) return;
+  const long long c = l * m.n_rungs + rung;
+  const int D = m.dim;
+  const double *rec = nb + l * (D + 3);
+  const double my_ll = s.llike[c], my_beta = s.beta[c], nb_ll = rec[D], nb_lprior = rec[D + 1], nb_beta = rec[D + 2];
+  // pair (i, i+1): i = the colder chain
+  double lla = i_am_lower ? my_ll : nb_ll; if (!(lla > -1e200)) lla = -1e200;
+  double llb = i_am_lower ? nb_ll : my_ll; if (!(llb > -1e200)) llb = -1e200;
+  const double ba = i_am_lower ? my_beta : nb_beta, bb = i_am_lower ? nb_beta : my_beta;
+  const double lhr = -(bb - ba) * (llb - lla);
+  bool accept = true;
+  if (lhr < 0) {
+    uint32_t w[4];
+    ptg_philox_draw(shared_seed, (uint64_t)(m.ladder_offset + l) * PTG_STREAM_STRIDE + PTG_STREAM_LADDER, PTG_DOMAIN_BOUNDARY, (uint64_t)exchange_index,
+                    (uint32_t)boundary_id, w);
+    accept = (log(ptg_u52_to_unit(w[0], w[1])) < lhr);
+  }
+  double lpost = s.lpost[c], llike = my_ll;
+  if (accept) {
+    for (int k = 0; k < D; k++) s.cur_x[(long long)k * m.n_chains + c] = rec[k];
+    llike = nb_ll;
+    lpost = nb_lprior + my_beta * nb_ll; // lpost recomputed = lprior(x) + beta*llike (chain.cc:925-928)
+    s.llike[c] = llike; s.lprior[c] = nb_lprior; s.lpost[c] = lpost;
+  }
+  // MH_chain::add_state (chain.cc:916-949)
+  if (lpost > s.map_lpost[c]) {
+    s.map_lpost[c] = lpost;
+    for (int k = 0; k < D; k++) s.map_x[(long long)k * m.n_chains + c] = s.cur_x[(long long)k * m.n_chains + c];
+  }
+  const long long nhist = s.nhist[c];
+  if (nhist % m.save_every == 0) {
+    const long long nsize = s.nsize[c], slot = nsize % m.hist_cap, r = c * m.hist_cap + slot;
+    double *hrec = s.hist + r * (D + 2);
+    for (int k = 0; k < D; k++) hrec[k] = s.cur_x[(long long)k * m.n_chains + c];
+    hrec[D] = lpost; hrec[D + 1] = llike;
+    if (m.record_full) { s.hist_acc[r] = s.naccept[c] / (double)s.ntries[c]; s.hist_beta[r] = my_beta; s.hist_type[r] = s.last_type[c]; }
+    s.nsize[c] = nsize + 1;
+  }
+  s.nhist[c] = nhist + 1;
+  if (i_am_lower) { s.swap_count[c] += 1; if (accept) s.swap_accept[c] += 1; } // counted at the pair's lower rung (this rank's last rung)
+}
+
+extern "C" int ptg_boundary_pack(ptg_handle *h, int32_t rung, void *out_dev) {
+  if (!h || !out_dev) return fail(PTG_EINVAL, "null argument");
+  if (!h->inited) return fail(PTG_EINVAL, "not initialised");
+  if (rung < 0 || rung >= h->m.n_rungs) return fail(PTG_EINVAL, "rung %d out of range", rung);
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  ptg_boundary_pack_kernel<<<grid_for(h->m.n_ladders), 256, 0, h->stream>>>(h->m, h->s, rung, (double *)out_dev);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+extern "C" int ptg_boundary_swap(ptg_handle *h, int32_t my_rung, const void *neighbour_pack_dev, int32_t i_am_lower, uint64_t shared_seed,
+                                 int64_t boundary_id, int64_t exchange_index) {
+  if (!h || !neighbour_pack_dev) return fail(PTG_EINVAL, "null argument");
+  if (!h->inited) return fail(PTG_EINVAL, "not initialised");
+  if (my_rung < 0 || my_rung >= h->m.n_rungs) return fail(PTG_EINVAL, "rung %d out of range", my_rung);
+  if (h->cfg.rng_mode != PTG_RNG_PHILOX) return fail(PTG_EINVAL, "boundary swaps draw from the Philox layout");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  ptg_boundary_swap_kernel<<<grid_for(h->m.n_ladders), 256, 0, h->stream>>>(h->m, h->s, my_rung, (const double *)neighbour_pack_dev, i_am_lower ? 1 : 0,
+                                                                            shared_seed, (long long)boundary_id, (long long)exchange_index);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------- checkpoint
 // One binary file: magic, config, istep, then every device array of PtgState in declaration order.
 struct CkArr { void *p; size_t bytes; };

@@ -1,0 +1,87 @@
+"""Rung-sharded temperature ladders: the optional multi-GPU layout with an exchange step (BASELINE config 5, "cross-GPU rung
+swaps over NVLink").  It mirrors the reference's MPI scheme (chain.cc:1290-1311: rungs dealt to ranks, every rank replays the same
+swap decisions from the shared seed, only data is communicated, chain.cc:1433-1435) with BLOCK rung assignment, so that only
+world-1 rung boundaries cross NVLink:
+
+    rank g owns rungs [g*R, (g+1)*R) of EVERY ladder of a (world*R)-rung geometric ladder (ptg_set_betas);
+    swaps inside a block run in the step kernels (reference schedule over the local rungs);
+    every `exchange_every` PT iterations the ranks exchange their edge rungs -- (x, llike, lprior, beta) per ladder, one NCCL
+    all_gather of [n_ladders, dim+3] doubles per edge -- and both sides of a boundary evaluate the same swap trial
+    (ptg_boundary_swap: acceptance draw from the ladder's Philox stream under the shared key), so decisions never travel.
+
+The ladder-sharded layout (sharding.py) needs no exchange step and is the default; this one exists for ladders too long for
+one GPU's warp/CTA (more than 32 rungs per ladder at full speed) and to measure the collective's cost.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def global_betas(n_rungs_total, Tmax):
+    """inverse temperatures of the geometric ladder (chain.cc:1181-1183,1339): temps[i] = temps[i-1] * Tmax^(1/(N-1))"""
+    tratio = np.exp(np.log(Tmax) / (n_rungs_total - 1)) if n_rungs_total > 1 else 1.0
+    temps = np.empty(n_rungs_total)
+    t = 1.0
+    for i in range(n_rungs_total):
+        if i > 0:
+            t = t * tratio
+        temps[i] = t
+    return 1.0 / temps
+
+
+def rank_betas(n_ladders, rungs_per_rank, rank, world, Tmax):
+    """[n_ladders * rungs_per_rank] betas of this rank's block of every ladder"""
+    b = global_betas(rungs_per_rank * world, Tmax)[rank * rungs_per_rank:(rank + 1) * rungs_per_rank]
+    return np.tile(b, n_ladders)
+
+
+class RungShardedLadders:
+    """Drives one rank's engine (anything with the C-ABI methods step / boundary_pack / boundary_swap) in the rung-sharded layout."""
+
+    def __init__(self, api, rank, world, shared_seed, exchange_every=10, device="cpu"):
+        self.api, self.rank, self.world, self.shared_seed, self.exchange_every = api, rank, world, int(shared_seed), exchange_every
+        self.device = torch.device(device)
+        L, d = api.cfg.n_ladders, api.cfg.dim
+        self.R = api.cfg.n_rungs
+        self.bottom = torch.zeros((L, d + 3), dtype=torch.float64, device=self.device)
+        self.top = torch.zeros((L, d + 3), dtype=torch.float64, device=self.device)
+        self.all_bottom = torch.zeros((world, L, d + 3), dtype=torch.float64, device=self.device)
+        self.all_top = torch.zeros((world, L, d + 3), dtype=torch.float64, device=self.device)
+        self.n_exchanges = 0
+
+    def _gather(self, out, inp):
+        if self.world == 1:
+            out[0].copy_(inp)
+        elif dist.get_backend() == "nccl":
+            dist.all_gather_into_tensor(out, inp)
+        else:
+            parts = [torch.empty_like(inp) for _ in range(self.world)]
+            dist.all_gather(parts, inp)
+            for r in range(self.world):
+                out[r].copy_(parts[r])
+
+    def exchange(self):
+        """one cross-boundary swap trial per ladder and per rung boundary"""
+        api, R, g = self.api, self.R, self.rank
+        api.boundary_pack(0, self.bottom.data_ptr())
+        api.boundary_pack(R - 1, self.top.data_ptr())
+        if self.device.type == "cuda":
+            api.synchronize()  # packs were written on the engine's stream
+        self._gather(self.all_bottom, self.bottom)
+        self._gather(self.all_top, self.top)
+        if self.device.type == "cuda":
+            torch.cuda.current_stream().synchronize()
+        if g + 1 < self.world:   # my hottest rung with the neighbour's coldest: I hold the lower index of the pair
+            api.boundary_swap(R - 1, self.all_bottom[g + 1].data_ptr(), True, self.shared_seed, g, self.n_exchanges)
+        if g > 0:
+            api.boundary_swap(0, self.all_top[g - 1].data_ptr(), False, self.shared_seed, g - 1, self.n_exchanges)
+        self.n_exchanges += 1
+
+    def run(self, n_steps):
+        """n_steps PT iterations with an exchange after every `exchange_every`"""
+        done = 0
+        while done < n_steps:
+            k = min(self.exchange_every, n_steps - done)
+            self.api.step(k)
+            self.exchange()
+            done += k
