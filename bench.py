@@ -33,7 +33,9 @@ sys.path.insert(0, ROOT)
 # ---------------------------------------------------------------------------------------------------- workloads
 WORKLOADS = {
     # BASELINE.json configs[2] / SURVEY 8d C1: sines.hh as written, d=3, ks=(2,2,2), default select_proposal mix
-    "c1_sines": dict(model="sines", dim=3, rungs=32, ladders=4096, pt_steps=1000, hist=1024, f_de=0.8, f_sn=0.1,
+    # hist = 8192 slots per chain (43 GB): a short ring makes DE adapt to the chain's own recent past and biases the sampler
+    # (measured: variance -6 % at 1024 slots); the reference's unbounded history is the limit of a long ring
+    "c1_sines": dict(model="sines", dim=3, rungs=32, ladders=4096, pt_steps=1000, hist=8192, save_every=1, f_de=0.8, f_sn=0.1,
                      desc="sines.hh sin^4 surface d=3, 4096 ladders x 32 rungs, default proposal mix (80% DE / 20% 6-scale Gaussian), swap_rate 0.1"),
     # configs[1] / B: polynomial chi^2, d=5, N=1000, DE only
     "b_poly": dict(model="poly", dim=5, rungs=16, ladders=1024, pt_steps=20, hist=1024, f_de=1.0, f_sn=0.1,
@@ -44,7 +46,9 @@ WORKLOADS = {
     # configs[3] / D: correlated Gaussian d=100, full covariance; "65536 chains x 24 rungs" read as 65 544 chains in total
     # (2731 ladders x 24 rungs; the 1.57 M-chain reading leaves < 100 history slots per chain in 180 GB, SURVEY.md 8d, and the
     # reference's DE member needs >= 10 d = 1000 stored samples to be ready).  Ninit = 11 d prior draws per chain (de_ni = 11).
-    "d_fullcov": dict(model="fullcov", dim=100, rungs=24, ladders=2731, pt_steps=50, hist=1280, f_de=0.5, f_sn=0.1,
+    # save_every = 8: the 1280-slot ring then spans 10 240 PT iterations, which removes the short-window bias at d = 100 without
+    # 8x the memory ("D must run with a short ring and/or save_every >> 1")
+    "d_fullcov": dict(model="fullcov", dim=100, rungs=24, ladders=2731, pt_steps=50, hist=1280, save_every=8, f_de=0.5, f_sn=0.1,
                       desc="correlated Gaussian d=100 full covariance (DMMA batched quadratic form + proposal rotation), 2731 ladders x 24 rungs, "
                            "50% eigen-rotated Gaussian proposal (2.38^2/d C) + 50% DE"),
     # configs[0] / A as a throughput batch
@@ -54,6 +58,12 @@ WORKLOADS = {
 
 
 def make_spec(w):
+    spec = _make_spec(w)
+    spec.save_every = w.get("save_every", 1)
+    return spec
+
+
+def _make_spec(w):
     from tests.models import Spec, poly_data, sinusoid_spec
     if w["model"] == "sines":
         return Spec("sines", w["dim"], w["rungs"])
@@ -69,9 +79,9 @@ def make_spec(w):
     raise ValueError(w["model"])
 
 
-def algorithmic_bytes_per_chain_step(w, save_every=1):
+def algorithmic_bytes_per_chain_step(w):
     """history append 8(d+2)/s [x, lpost, llike] + DE gathers f_DE (2 + f_sn) 8 d"""
-    d = w["dim"]
+    d, save_every = w["dim"], w.get("save_every", 1)
     return 8.0 * (d + 2) / save_every + w["f_de"] * (2 + w["f_sn"]) * 8.0 * d
 
 
@@ -181,6 +191,8 @@ def main():
     ap.add_argument("--workload", default="c1_sines", choices=sorted(WORKLOADS))
     ap.add_argument("--pt-steps", type=int, default=0, help="PT iterations per bench step (default: per workload)")
     ap.add_argument("--ladders", type=int, default=0, help="ladders per GPU (default: per workload)")
+    ap.add_argument("--hist", type=int, default=0, help="history ring slots per chain (default: per workload)")
+    ap.add_argument("--save-every", type=int, default=0, help="add_every_N: store every N-th sample (default: per workload)")
     ap.add_argument("--swap-mode", default="reference", choices=["reference", "even_odd"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rung-sharded", type=int, default=0, metavar="K",
@@ -201,9 +213,12 @@ def main():
     w = dict(WORKLOADS[args.workload])
     if args.pt_steps: w["pt_steps"] = args.pt_steps
     if args.ladders: w["ladders"] = args.ladders
+    if args.hist: w["hist"] = args.hist
+    if args.save_every: w["save_every"] = args.save_every
+    w.setdefault("save_every", 1)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     config = dict(workload="%s: %s" % (args.workload, w["desc"]), ladders_per_gpu=w["ladders"], rungs=w["rungs"], dim=w["dim"],
-                  chains_per_gpu=w["ladders"] * w["rungs"], pt_iterations_per_step=w["pt_steps"], save_every=1, hist_capacity=w["hist"],
+                  chains_per_gpu=w["ladders"] * w["rungs"], pt_iterations_per_step=w["pt_steps"], save_every=w["save_every"], hist_capacity=w["hist"],
                   swap_mode=args.swap_mode, rng="philox4x32-10", parallelism="ladders sharded, %d per GPU, no data-path collective" % w["ladders"],
                   l2="history ring (%.1f GB per GPU) is larger than L2" % (w["ladders"] * w["rungs"] * w["hist"] * 8.0 * (w["dim"] + 2) / 1e9))
     metric, unit = "tempered chain-steps/s", "chain-steps/s"
@@ -247,7 +262,7 @@ def main():
     if args.rung_sharded:
         # ---- optional rung-sharded layout (ptmcmc_b200/rung_sharding.py): the same ladders on every rank, a different rung block
         from ptmcmc_b200.rung_sharding import RungShardedLadders, rank_betas
-        eng = Engine(spec.config(n_ladders=L, rng_mode=K.RNG_PHILOX, record_level=K.RECORD_BASIC, hist_capacity=w["hist"], device=local,
+        eng = Engine(spec.config(n_ladders=L, rng_mode=K.RNG_PHILOX, record_level=K.RECORD_BASIC, hist_capacity=w["hist"], save_every=w["save_every"], device=local,
                                  seed=0xB2000003 + 977 * rank))
         spec.setup(eng)
         eng.set_betas(rank_betas(L, R, rank, world, spec.Tmax))
@@ -284,7 +299,7 @@ def main():
             dist.destroy_process_group()
         return 0
     swap_mode = K.SWAP_REFERENCE if args.swap_mode == "reference" else K.SWAP_EVEN_ODD
-    eng = Engine(spec.config(n_ladders=L, rng_mode=K.RNG_PHILOX, record_level=K.RECORD_BASIC, hist_capacity=w["hist"], swap_mode=swap_mode,
+    eng = Engine(spec.config(n_ladders=L, rng_mode=K.RNG_PHILOX, record_level=K.RECORD_BASIC, hist_capacity=w["hist"], save_every=w["save_every"], swap_mode=swap_mode,
                              device=local, ladder_offset=rank * L, seed=0xB2000003))
     spec.setup(eng)
     stream = torch.cuda.Stream()
@@ -348,7 +363,8 @@ def main():
         cold = np.stack([eng.get_history(l, 0, int(cnt["nsize"][l * R]) - nh, nh, full=False)["x"] for l in range(nl)])
         eps, taus = ess_per_sample(cold)
         pt_iter_per_s = args.steps * S / (ms_max * 1e-3)
-        ess = dict(value=eps * pt_iter_per_s * L * world, unit="ESS/s", tau_pt_iterations=float(taus.max()), window=nh, ladders_sampled=nl,
+        ess = dict(value=eps / w["save_every"] * pt_iter_per_s * L * world, unit="ESS/s", tau_pt_iterations=float(taus.max()) * w["save_every"], window=nh,
+                   ladders_sampled=nl,
                    estimator="min over parameters of N/tau, Sokal-windowed integrated autocorrelation time (ptmcmc_b200/analysis.py)")
     except Exception as exc:  # analysis is not part of the timed path
         ess = dict(value=None, error=repr(exc))
