@@ -204,6 +204,14 @@ int ptg_set_stream(ptg_handle *h, void *cuda_stream);
  * authoritative does before each block of steps).  Asynchronous on the handle's stream. */
 int ptg_set_current(ptg_handle *h, const double *x, const double *lpost, const double *llike, const double *lprior);
 
+/* Thermodynamic-integration evidence, computed on the device from the history ring:
+ *   ptg_get_mean_loglike: mean log-likelihood of every chain over its newest `n_last` stored samples -> mean_ll[n_chains];
+ *   ptg_get_log_evidence: per ladder, the reference's trapezoid over the rungs plus its tail term below the hottest rung
+ *                         (parallel_tempering_chains::log_evidence_ratio and "Total log-evidence", chain.cc:1582-1600,1984-2012)
+ *                         -> log_evidence[n_ladders]. */
+int ptg_get_mean_loglike(ptg_handle *h, int32_t n_last, double *mean_ll);
+int ptg_get_log_evidence(ptg_handle *h, int32_t n_last, double *log_evidence);
+
 /* Rung-sharded ladders (the reference's MPI layout, chain.cc:1290-1311,1433-1435, with block rung assignment): every GPU holds
  * a contiguous block of rungs of EVERY ladder (explicit betas via ptg_set_betas); replica swaps inside a block run in the step
  * kernels, swaps ACROSS a block boundary are a separate exchange step between launches:

@@ -835,6 +835,63 @@ extern "C" int ptg_set_stream(ptg_handle *h, void *cuda_stream) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------- evidence
+// mean log-likelihood of every chain over its newest `n_last` stored samples (one warp per chain, lanes stride the ring)
+__global__ void ptg_mean_llike_kernel(PtgModel m, PtgState s, int n_last, double *out) {
+  const long long c = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (c >= m.n_chains) return;
+  const long long nsize = s.nsize[c];
+  long long n = n_last;
+  if (n > nsize) n = nsize;
+  if (n > m.hist_cap) n = m.hist_cap;
+  const double *base = s.hist + c * m.hist_cap * (m.dim + 2);
+  double sum = 0;
+  for (long long k = lane; k < n; k += 32) sum += base[((nsize - n + k) % m.hist_cap) * (m.dim + 2) + m.dim + 1];
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) out[c] = n > 0 ? sum / (double)n : CUDART_NAN;
+}
+// thermodynamic-integration evidence of every ladder from the per-rung means, the reference's trapezoid
+// (parallel_tempering_chains::log_evidence_ratio and its use, chain.cc:1582-1600,1984-2012)
+__global__ void ptg_log_evidence_kernel(PtgModel m, PtgState s, const double *mean_ll, double *out) {
+  const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= m.n_ladders) return;
+  const int R = m.n_rungs;
+  const double *ml = mean_ll + l * R, *b = s.beta + l * R;
+  double evidence = 0, up = 0, down = 0;
+  for (int i = 0; i < R - 1; i++) {
+    up = ml[i + 1] * (b[i] - b[i + 1]);        // log_evidence_ratio(i, i+1): mean over rung i+1's samples of llike * (beta_i - beta_{i+1})
+    down = -(ml[i] * (b[i + 1] - b[i]));       // -log_evidence_ratio(i+1, i)
+    evidence += (up + down) / 2.0;
+  }
+  if (R > 1) evidence += (up + down) / 2.0 / (b[R - 2] / b[R - 1] - 1); // the tail below the hottest rung (chain.cc:1597)
+  out[l] = evidence;
+}
+
+extern "C" int ptg_get_mean_loglike(ptg_handle *h, int32_t n_last, double *mean_ll) {
+  if (!h || !mean_ll || n_last < 1) return fail(PTG_EINVAL, "bad argument");
+  if (!h->inited) return fail(PTG_EINVAL, "not initialised");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const size_t n = (size_t)h->m.n_chains;
+  int rc = ensure_scratch(h, (n + h->m.n_ladders) * sizeof(double)); if (rc) return rc;
+  ptg_mean_llike_kernel<<<grid_for((long long)n * 32), 256, 0, h->stream>>>(h->m, h->s, n_last, h->d_scratch);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(mean_ll, h->d_scratch, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  return ptg_synchronize(h);
+}
+extern "C" int ptg_get_log_evidence(ptg_handle *h, int32_t n_last, double *log_evidence) {
+  if (!h || !log_evidence || n_last < 1) return fail(PTG_EINVAL, "bad argument");
+  if (!h->inited) return fail(PTG_EINVAL, "not initialised");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const size_t n = (size_t)h->m.n_chains, L = (size_t)h->m.n_ladders;
+  int rc = ensure_scratch(h, (n + L) * sizeof(double)); if (rc) return rc;
+  ptg_mean_llike_kernel<<<grid_for((long long)n * 32), 256, 0, h->stream>>>(h->m, h->s, n_last, h->d_scratch);
+  ptg_log_evidence_kernel<<<grid_for((long long)L), 256, 0, h->stream>>>(h->m, h->s, h->d_scratch, h->d_scratch + n);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(log_evidence, h->d_scratch + n, L * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  return ptg_synchronize(h);
+}
+
 // ------------------------------------------------------------------------------------------------- rung-sharded ladders
 __global__ void ptg_boundary_pack_kernel(PtgModel m, PtgState s, int rung, double *out) {
   const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;

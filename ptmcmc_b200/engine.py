@@ -39,6 +39,16 @@ class Engine(K.CApi):
         self._call("eval", self.h, K._dp(x), C.c_int64(len(x)), None, K._dp(out))
         return out
 
+    def get_mean_loglike(self, n_last):
+        out = np.empty(self.n_chains)
+        self._call("get_mean_loglike", self.h, C.c_int32(n_last), K._dp(out))
+        return out
+
+    def get_log_evidence(self, n_last):
+        out = np.empty(self.cfg.n_ladders)
+        self._call("get_log_evidence", self.h, C.c_int32(n_last), K._dp(out))
+        return out
+
     def get_lprior(self):
         out = np.empty(self.n_chains)
         self._call("get_lprior", self.h, K._dp(out))

@@ -189,3 +189,28 @@ def test_set_current_roundtrip(engine_cls):
     e.synchronize()
     got = e.get_current()
     assert got["x"].tobytes() == x2.tobytes() and got["llike"].tobytes() == cur["llike"][::-1].tobytes()
+
+
+def test_device_evidence_matches_reference_formula_and_analytic_value(engine_cls):
+    """thermodynamic-integration evidence from the device history ring: equals the reference's formula (chain.cc:1582-1600,
+    1984-2012) applied on the host to the same histories, and approaches the analytic ln Z = -ln(prior volume) of a normalised
+    Gaussian likelihood inside a uniform box (example.cc:102-105: -ln(8*2*3*5) in 3-D; here 2-D, volume 4 x 6)"""
+    spec = Spec("gauss", 2, 24, centers=[2, -3], halfwidths=[2, 3], Tmax=1e6)
+    L, steps, n_last = 128, 5000, 3000
+    e = engine_cls(spec.config(n_ladders=L, rng_mode=K.RNG_PHILOX, hist_capacity=8192, record_level=K.RECORD_BASIC))
+    spec.setup(e); e.init_from_prior(); e.step(steps); e.synchronize()
+    ev = e.get_log_evidence(n_last)
+    ml = e.get_mean_loglike(n_last).reshape(L, 24)
+    beta = e.get_current()["beta"].reshape(L, 24)
+    cnt = e.get_counters()
+    # host restatement on ladder 0 from its histories
+    host_ml = []
+    for r in range(24):
+        n = int(cnt["nsize"][r]); host_ml.append(e.get_history(0, r, n - n_last, n_last, full=False)["llike"].mean())
+    host_ml = np.array(host_ml)
+    assert np.allclose(ml[0], host_ml, rtol=1e-12)
+    b = beta[0]
+    up = host_ml[1:] * (b[:-1] - b[1:]); down = -(host_ml[:-1] * (b[1:] - b[:-1]))
+    want = ((up + down) / 2).sum() + (up[-1] + down[-1]) / 2 / (b[-2] / b[-1] - 1)
+    assert ev[0] == pytest.approx(want, rel=1e-12)
+    assert abs(ev.mean() - (-np.log(24.0))) < 0.15, ev.mean()
