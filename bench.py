@@ -64,7 +64,7 @@ def make_spec(w):
 
 
 def _make_spec(w):
-    from tests.models import Spec, poly_data, sinusoid_spec
+    from ptmcmc_b200.workloads import Spec, poly_data, sinusoid_spec
     if w["model"] == "sines":
         return Spec("sines", w["dim"], w["rungs"])
     if w["model"] == "poly":
@@ -74,7 +74,7 @@ def _make_spec(w):
     if w["model"] == "gauss":
         return Spec("gauss", 2, w["rungs"], centers=[2, -3], halfwidths=[2, 3])
     if w["model"] == "fullcov":
-        from tests.models import fullcov_spec
+        from ptmcmc_b200.workloads import fullcov_spec
         return fullcov_spec(w["dim"], w["rungs"], de_ni=11)
     raise ValueError(w["model"])
 
