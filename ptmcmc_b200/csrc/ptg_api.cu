@@ -36,6 +36,7 @@ struct ptg_handle {
   cudaStream_t stream;
   bool own_stream;
   bool have_space, have_prior, have_like, have_props, inited, model_uploaded;
+  bool model_dirty;                // a set_* call changed the model since the last upload
   std::vector<HostProp> props;
   double Tpow;
   std::vector<double> lparams, ldata, betas;
@@ -155,7 +156,7 @@ extern "C" int ptg_create(const ptg_config *cfg, ptg_handle **out) {
   h->wide = cfg->dim > PTG_TPC_MAX_DIM; h->wide_trans_off = -1;
   h->lower.assign(cfg->dim, PTG_BOUND_OPEN); h->upper.assign(cfg->dim, PTG_BOUND_OPEN);
   h->xmin.assign(cfg->dim, -INFINITY); h->xmax.assign(cfg->dim, INFINITY); h->prior.resize(cfg->dim);
-  h->have_space = h->have_prior = h->have_like = h->have_props = h->inited = h->model_uploaded = false;
+  h->have_space = h->have_prior = h->have_like = h->have_props = h->inited = h->model_uploaded = false; h->model_dirty = true;
   h->d_lparams = h->d_ldata = h->d_prop_data = h->d_bins = nullptr;
   h->d_tape_u = h->d_tape_z = nullptr; h->d_u_end = h->d_z_end = nullptr;
   h->kernel_choice = PTG_KERNEL_AUTO; h->launches = 0; h->istep = 0; h->Tpow = 0; h->d_scratch = nullptr; h->scratch_bytes = 0; h->h_pinned = nullptr; h->pinned_bytes = 0;
@@ -250,6 +251,7 @@ extern "C" int ptg_set_space(ptg_handle *h, const int32_t *lt, const int32_t *ut
   m.any_bound = 0;
   for (int i = 0; i < m.dim; i++) if (lt[i] != PTG_BOUND_OPEN || ut[i] != PTG_BOUND_OPEN) m.any_bound = 1;
   h->have_space = true;
+  h->model_dirty = true;
   return 0;
 }
 
@@ -279,6 +281,7 @@ extern "C" int ptg_set_prior(ptg_handle *h, const int32_t *type, const double *a
   for (int i = 0; i < m.dim && i < PTG_TPC_MAX_DIM; i++) m.prior[i] = h->prior[i];
   m.all_uniform_prior = all_uniform ? 1 : 0;
   h->have_prior = true;
+  h->model_dirty = true;
   return 0;
 }
 
@@ -311,6 +314,7 @@ extern "C" int ptg_set_likelihood(ptg_handle *h, int32_t kind, const double *par
     m.like_nsum = nsum;
   }
   h->have_like = true;
+  h->model_dirty = true;
   return 0;
 }
 
@@ -332,12 +336,14 @@ extern "C" int ptg_set_proposals(ptg_handle *h, int32_t n, const ptg_proposal *p
   }
   h->Tpow = Tpow; h->m.wrap_in_set = wrap_in_set ? 1 : 0; h->m.n_props = n;
   h->have_props = true;
+  h->model_dirty = true;
   return 0;
 }
 
 extern "C" int ptg_set_betas(ptg_handle *h, const double *betas) {
   if (!h) return fail(PTG_EINVAL, "null handle");
   if (betas) h->betas.assign(betas, betas + h->m.n_chains);
+  h->model_dirty = true;
   return 0;
 }
 
@@ -475,7 +481,7 @@ static int upload_model(ptg_handle *h) {
     CUDA_TRY(cudaMemcpyAsync(&m.uniform_lprior, d_out, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   }
   CUDA_TRY(cudaStreamSynchronize(h->stream));
-  h->model_uploaded = true;
+  h->model_uploaded = true; h->model_dirty = false;
   return 0;
 }
 
@@ -497,7 +503,7 @@ static int do_init(ptg_handle *h, const double *x_host) {
   if (h->inited) return fail(PTG_EINVAL, "already initialised (chain.cc:847-850)");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   if (h->cfg.rng_mode == PTG_RNG_TAPE && !h->s.tape_u && !x_host) return fail(PTG_EINVAL, "PTG_RNG_TAPE: inject tapes before init");
-  int rc = upload_model(h); if (rc) return rc;
+  int rc = (h->model_uploaded && !h->model_dirty) ? 0 : upload_model(h); if (rc) return rc; // uploaded already by ptg_eval and unchanged since
   PtgModel &m = h->m; PtgState &s = h->s;
   const long long n = m.n_chains;
   CUDA_TRY(cudaMemcpyAsync(s.beta, h->betas.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -537,11 +543,6 @@ static int ladders_per_block(const PtgModel &m) {
   if (lpb > m.n_ladders) lpb = m.n_ladders;
   return lpb;
 }
-static size_t ladder_shared_bytes(int D, int R) {
-  size_t b = sizeof(double) * ((size_t)R * D * 2 + (size_t)R * 10 + PTG_SWAP_SLOTS * 3) + sizeof(int) * ((size_t)R * 5 + PTG_SWAP_SLOTS) +
-             sizeof(long long) * (size_t)R * 2;
-  return (b + 15) & ~(size_t)15;
-}
 
 // lanes per ladder of the warp kernels: the smallest power of two that holds n_rungs; 0 = the ladder does not fit one
 // warp (or has more swap trials per step than lanes) and the shared-memory kernel runs instead
@@ -573,7 +574,7 @@ extern "C" int ptg_step(ptg_handle *h, int64_t n_steps) {
   int W = 0;
   const int kern = pick_kernel(h, &W);
   const int lpb = ladders_per_block(m);
-  const size_t smem = (size_t)lpb * ladder_shared_bytes(m.dim, m.n_rungs) + (size_t)m.n_rungs * m.n_props * sizeof(double);
+  const size_t smem = (size_t)lpb * ptg_ladder_shared_bytes(m.dim, m.n_rungs) + (size_t)m.n_rungs * m.n_props * sizeof(double);
   const int max_chunk = (kern == PTG_KERNEL_FAST) ? 16384 : (1 << 20); // the fast kernel keeps 16-bit launch-local statistics
   int64_t left = n_steps;
   while (left > 0) {
@@ -656,7 +657,7 @@ extern "C" int ptg_eval(ptg_handle *h, const double *x, int64_t n, double *logli
   if (!h || !x || n < 0) return fail(PTG_EINVAL, "bad argument");
   if (n == 0) return 0;
   CUDA_TRY(cudaSetDevice(h->cfg.device));
-  if (!h->model_uploaded) { int rc = upload_model(h); if (rc) return rc; }
+  if (!h->model_uploaded || h->model_dirty) { int rc = upload_model(h); if (rc) return rc; }
   PtgModel &m = h->m;
   const size_t d = (size_t)m.dim;
   int rc = ensure_scratch(h, (size_t)n * (d + 2) * sizeof(double)); if (rc) return rc;

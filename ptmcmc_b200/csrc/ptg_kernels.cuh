@@ -398,11 +398,6 @@ struct LadderShared {
     napp = i; i += R; iswap = i; i += PTG_SWAP_SLOTS; dir = i; i += R; ups = i; i += R; downs = i; i += R; inst = i; i += R;
   }
 };
-static inline size_t ptg_ladder_shared_bytes(int D, int R) {
-  size_t b = sizeof(double) * ((size_t)R * D * 2 + (size_t)R * 10 + PTG_SWAP_SLOTS * 3) + sizeof(int) * ((size_t)R * 5 + PTG_SWAP_SLOTS) +
-             sizeof(long long) * (size_t)R * 2;
-  return (b + 15) & ~(size_t)15;
-}
 
 // record one history append of rung r with the ladder's shared copies as they are now
 template <int D>
@@ -492,7 +487,7 @@ __global__ void __launch_bounds__(256) ptg_step_kernel(const __grid_constant__ P
   const bool active = (ll_ < lpb) && (ladder < m.n_ladders);
   const long long chain = ladder * R + rung;
   const size_t lbytes = (sizeof(double) * ((size_t)R * D * 2 + (size_t)R * 10 + PTG_SWAP_SLOTS * 3) + sizeof(int) * ((size_t)R * 5 + PTG_SWAP_SLOTS) +
-                         sizeof(long long) * (size_t)R * 2 + 15) & ~(size_t)15;
+                         sizeof(long long) * (size_t)R * 2 + 15) & ~(size_t)15; // = ptg_ladder_shared_bytes(D, R) of ptg_launch.h
   LadderShared<D> L;
   L.carve(smem_raw + (size_t)(ll_ < lpb ? ll_ : 0) * lbytes, R);
   double *sbins = reinterpret_cast<double *>(smem_raw + (size_t)lpb * lbytes); // [R][n_props]

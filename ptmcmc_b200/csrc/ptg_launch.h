@@ -2,6 +2,12 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "ptg_types.h"
+// dynamic shared memory of one ladder in the shared-memory step kernel (must match LadderShared::carve in ptg_kernels.cuh)
+static inline size_t ptg_ladder_shared_bytes(int D, int R) {
+  size_t b = sizeof(double) * ((size_t)R * D * 2 + (size_t)R * 10 + PTG_SWAP_SLOTS * 3) + sizeof(int) * ((size_t)R * 5 + PTG_SWAP_SLOTS) +
+             sizeof(long long) * (size_t)R * 2;
+  return (b + 15) & ~(size_t)15;
+}
 #ifdef PTG_DEV_DIM3  // developer build: `make DEV=1` compiles only dim = 3, 5, 9 (seconds instead of minutes)
 #define PTG_DIM_LIST(X) X(3) X(5) X(9)
 #else
