@@ -12,19 +12,31 @@
 // Out[r][n] = sum_k In[r][k] * Cm[n*D + k]  for r < RP, n < D ; In / Out are [RP][DP] shared-memory matrices whose
 // columns >= D are zero.  Called by every warp of the CTA.
 __device__ __forceinline__ void xcta_dmma(const double *In, const double *__restrict__ Cm, double *Out, int RP, int D, int DP, int warp, int nwarps, int lane) {
-  const int mt_n = RP >> 3, nt_n = (D + 7) >> 3, KP = (D + 3) & ~3;
+  const int mt_n = RP >> 3, nt_n = (D + 7) >> 3;
   const int g = lane >> 2, t = lane & 3;
+  // Columns n >= D of the last tile are computed from a clamped matrix row and never read (consumers stop at D), which keeps
+  // the inner loop free of predicates.  When D is a multiple of 4 the k index is consumed in a permuted order -- within each
+  // group of 8, lane t takes elements (2t, 2t+1) for two consecutive MMAs instead of (t, 4+t) -- so that both operands come
+  // from one 16-byte load each; A and B use the same permutation, so the contraction is unchanged.
+  const bool vec = (D & 3) == 0;
+  const int K8 = vec ? (D & ~7) : 0;
   for (int tile = warp; tile < mt_n * nt_n; tile += nwarps) {
     const int mt = tile / nt_n, nt = tile - mt * nt_n;
     const double *arow = In + (size_t)(mt * 8 + g) * DP;
-    const int n = nt * 8 + g;
+    int n = nt * 8 + g;
+    if (n >= D) n = D - 1;
     const double *__restrict__ brow = Cm + (size_t)n * D;
-    const bool nok = n < D;
     double c0 = 0, c1 = 0;
-    for (int k0 = 0; k0 < KP; k0 += 4) {
+    for (int k0 = 0; k0 < K8; k0 += 8) {
+      const double2 a2 = *reinterpret_cast<const double2 *>(arow + k0 + 2 * t);
+      const double2 b2 = __ldg(reinterpret_cast<const double2 *>(brow + k0 + 2 * t));
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a2.x), "d"(b2.x));
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a2.y), "d"(b2.y));
+    }
+    for (int k0 = K8; k0 < D; k0 += 4) { // tail (and the whole contraction when D is not a multiple of 4): scalar operands, guarded
       const int k = k0 + t;
-      const double a = arow[k];
-      const double b = (nok && k < D) ? __ldg(brow + k) : 0.0;
+      const double a = arow[k];                       // shared-memory columns >= D are zero
+      const double b = (k < D) ? __ldg(brow + k) : 0.0;
       asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
     }
     double *orow = Out + (size_t)(mt * 8 + g) * DP + nt * 8 + 2 * t;
