@@ -35,7 +35,7 @@ struct XShared {
   __device__ void carve(unsigned char *base, int R, int DP, int NP) {
     double *d = reinterpret_cast<double *>(base);
     const int RP = (R + 7) & ~7; // the DMMA kernel treats rowA / rowB as [RP][DP] matrices (8-row tiles)
-    sx = d; d += (size_t)RP * DP; rowA = d; d += (size_t)RP * DP; rowB = d; d += (size_t)RP * DP;
+    sx = d; d += (size_t)RP * DP; rowA = d; d += (size_t)RP * DP; rowB = d; d += (size_t)(RP + 2) * DP; // +2 rows: prior box edges (DMMA kernel)
     sll = d; d += R; slpost = d; d += R; slprior = d; d += R; sbeta = d; d += R;
     n_lpost = d; d += R; n_beta = d; d += R; app_lpost = d; d += 2 * R; app_beta = d; d += 2 * R; split = d; d += R;
     udraw = d; d += 3 * PTG_SWAP_SLOTS; sbins = d; d += (size_t)R * NP;
@@ -47,7 +47,7 @@ struct XShared {
   }
 };
 static inline size_t ptg_xshared_bytes(int R, int DP, int NP) {
-  size_t b = sizeof(double) * ((size_t)3 * ((R + 7) & ~7) * DP + (size_t)R * 11 + 3 * PTG_SWAP_SLOTS + (size_t)R * NP) + sizeof(long long) * 2 * (size_t)R +
+  size_t b = sizeof(double) * ((size_t)(3 * ((R + 7) & ~7) + 2) * DP + (size_t)R * 11 + 3 * PTG_SWAP_SLOTS + (size_t)R * NP) + sizeof(long long) * 2 * (size_t)R +
              sizeof(int) * ((size_t)R * 8 + PTG_SWAP_SLOTS);
   return (b + 15) & ~(size_t)15;
 }

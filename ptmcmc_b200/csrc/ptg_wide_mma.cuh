@@ -265,6 +265,13 @@ __global__ void __launch_bounds__(MAXT) ptg_xmstep_kernel(const __grid_constant_
   double ptry = 2 * m.swap_rate; if (ptry > 1) ptry = 1;
   const double *bins = L.sbins + (size_t)rung * NP;
   const bool fullcov = m.like_kind == PTG_LIKE_GAUSS_FULLCOV;
+  // all-uniform prior: this lane's box edges are loop-invariant (the PtgPrior1D structs sit 56 bytes apart in global memory)
+  // staged once per CTA in the (otherwise unused) padding rows' neighbour: two rows of DP doubles behind rowB
+  double *plo = L.rowB + (size_t)RP * DP, *phi = plo + DP;
+  for (int c = threadIdx.x; c < DP; c += blockDim.x) {
+    plo[c] = (c < D && m.all_uniform_prior) ? m.prior_w[c].a : -CUDART_INF;
+    phi[c] = (c < D && m.all_uniform_prior) ? m.prior_w[c].b : CUDART_INF;
+  }
   __syncthreads();
 
   for (int it = 0; it < n_steps; it++) {
@@ -395,7 +402,12 @@ __global__ void __launch_bounds__(MAXT) ptg_xmstep_kernel(const __grid_constant_
         for (int k = 0; k < CPL; k++) newx[k] = ch.x[k] + off[k];
       }
       if (valid) valid = xenforce<CPL>(m, newx, lane);
-      newlprior = xprior<CPL>(m, newx, valid, rowA, lane);
+      if (m.all_uniform_prior) {
+        bool in = valid;
+#pragma unroll
+        for (int k = 0; k < CPL; k++) in = in && !(newx[k] < plo[CPL * lane + k]) && !(newx[k] > phi[CPL * lane + k]);
+        newlprior = __all_sync(0xffffffffu, in) ? m.uniform_lprior : -CUDART_INF;
+      } else newlprior = xprior<CPL>(m, newx, valid, rowA, lane);
       gate = valid && ((newlprior > -1e200) || (newlprior - oldlprior > m.dprior_min));
     }
     // ---------------------------------------------------------------- batched quadratic form Y = X' Cinv^T on the tensor cores
