@@ -358,14 +358,18 @@ def main():
     ess = None
     try:
         from ptmcmc_b200.analysis import ess_per_sample
-        nl, nh = min(L, 256), min(w["hist"] - 8, 1000)
+        nh = min(w["hist"] - 8, 2000)
+        tau_dev = eng.get_act(0, nh, min(nh // 2, 1000))                 # device: every ladder's cold chain, per parameter
+        eps_dev = float(np.mean(1.0 / tau_dev.max(axis=1)))              # ESS per stored sample, mean over ladders
+        nl = min(L, 256)                                                 # host cross-check on a sample of ladders (ACFs averaged, then windowed)
         cnt = eng.get_counters()
         cold = np.stack([eng.get_history(l, 0, int(cnt["nsize"][l * R]) - nh, nh, full=False)["x"] for l in range(nl)])
-        eps, taus = ess_per_sample(cold)
+        eps_host, taus = ess_per_sample(cold)
         pt_iter_per_s = args.steps * S / (ms_max * 1e-3)
-        ess = dict(value=eps / w["save_every"] * pt_iter_per_s * L * world, unit="ESS/s", tau_pt_iterations=float(taus.max()) * w["save_every"], window=nh,
-                   ladders_sampled=nl,
-                   estimator="min over parameters of N/tau, Sokal-windowed integrated autocorrelation time (ptmcmc_b200/analysis.py)")
+        ess = dict(value=eps_dev / w["save_every"] * pt_iter_per_s * L * world, unit="ESS/s", tau_pt_iterations=float(np.median(tau_dev.max(axis=1))) * w["save_every"],
+                   window=nh, ladders=L, estimator="device (ptg_get_act): per cold chain N/tau, tau = Sokal-windowed integrated autocorrelation time, "
+                   "min over parameters, mean over ladders", host_check=dict(value=eps_host / w["save_every"] * pt_iter_per_s * L * world,
+                   tau_pt_iterations=float(taus.max()) * w["save_every"], ladders_sampled=nl))
     except Exception as exc:  # analysis is not part of the timed path
         ess = dict(value=None, error=repr(exc))
 

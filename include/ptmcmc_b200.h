@@ -210,6 +210,9 @@ int ptg_set_current(ptg_handle *h, const double *x, const double *lpost, const d
  *                         (parallel_tempering_chains::log_evidence_ratio and "Total log-evidence", chain.cc:1582-1600,1984-2012)
  *                         -> log_evidence[n_ladders]. */
 int ptg_get_mean_loglike(ptg_handle *h, int32_t n_last, double *mean_ll);
+/* Device-side ESS input: integrated autocorrelation time (Sokal window, c = 5) of every parameter of rung `rung` of every ladder over
+ * its newest n_last stored samples, lags < max_lag -> tau[n_ladders][dim]; ESS of a chain = n_last / max_j tau_j (in stored samples). */
+int ptg_get_act(ptg_handle *h, int32_t rung, int32_t n_last, int32_t max_lag, double *tau);
 int ptg_get_log_evidence(ptg_handle *h, int32_t n_last, double *log_evidence);
 
 /* Rung-sharded ladders (the reference's MPI layout, chain.cc:1290-1311,1433-1435, with block rung assignment): every GPU holds

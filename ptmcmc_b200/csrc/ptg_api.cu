@@ -869,6 +869,68 @@ __global__ void ptg_log_evidence_kernel(PtgModel m, PtgState s, const double *me
   out[l] = evidence;
 }
 
+// integrated autocorrelation time of every parameter of rung `rung` of every ladder over its newest n_last stored samples:
+// one CTA per ladder; the series is staged in shared memory, one thread per lag computes the (biased) autocovariance, thread 0
+// applies Sokal's self-consistent window M >= c*tau(M) to tau(M) = 1 + 2 sum_{t<=M} rho_t  (the estimator of
+// ptmcmc_b200/analysis.py:integrated_act, per chain).  Not the reference's own recipe (chain.cc:126-643), which is a different
+// finite-sample estimator of the same quantity.
+__global__ void __launch_bounds__(256) ptg_act_kernel(PtgModel m, PtgState s, int rung, int n_last, int max_lag, double cwin, double *tau_out) {
+  extern __shared__ double sh[];
+  double *y = sh, *rho = sh + n_last, *red = rho + max_lag;
+  const long long l = blockIdx.x, c = l * m.n_rungs + rung;
+  const long long nsize = s.nsize[c];
+  int n = n_last;
+  if (n > nsize) n = (int)nsize;
+  if (n > m.hist_cap) n = m.hist_cap;
+  const double *base = s.hist + c * m.hist_cap * (m.dim + 2);
+  for (int j = 0; j < m.dim; j++) {
+    double part = 0;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) { const double v = base[((nsize - n + k) % m.hist_cap) * (m.dim + 2) + j]; y[k] = v; part += v; }
+    red[threadIdx.x] = part;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
+    const double mean = red[0] / n;
+    __syncthreads();
+    for (int k = threadIdx.x; k < n; k += blockDim.x) y[k] -= mean;
+    __syncthreads();
+    for (int lag = threadIdx.x; lag < max_lag; lag += blockDim.x) {
+      double acc = 0;
+      for (int k = 0; k + lag < n; k++) acc += y[k] * y[k + lag];
+      rho[lag] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const double c0 = rho[0];
+      double tau = 1.0, cum = 0;
+      const int lim = max_lag < n ? max_lag : n;
+      for (int M = 0; M < lim; M++) {
+        cum += (c0 > 0 ? rho[M] / c0 : 1.0);
+        tau = 2.0 * cum - 1.0;
+        if (M >= cwin * tau) break;
+      }
+      tau_out[l * m.dim + j] = tau > 1.0 ? tau : 1.0;
+    }
+    __syncthreads();
+  }
+}
+
+extern "C" int ptg_get_act(ptg_handle *h, int32_t rung, int32_t n_last, int32_t max_lag, double *tau) {
+  if (!h || !tau || n_last < 8 || max_lag < 2) return fail(PTG_EINVAL, "bad argument");
+  if (!h->inited) return fail(PTG_EINVAL, "not initialised");
+  if (rung < 0 || rung >= h->m.n_rungs) return fail(PTG_EINVAL, "rung %d out of range", rung);
+  if (max_lag > n_last) max_lag = n_last;
+  const size_t smem = ((size_t)n_last + max_lag + 256) * sizeof(double);
+  if (smem > 200 * 1024) return fail(PTG_EINVAL, "n_last + max_lag too large for shared memory (%zu bytes)", smem);
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const size_t cnt = (size_t)h->m.n_ladders * h->m.dim;
+  int rc = ensure_scratch(h, cnt * sizeof(double)); if (rc) return rc;
+  if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(ptg_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ptg_act_kernel<<<h->m.n_ladders, 256, smem, h->stream>>>(h->m, h->s, rung, n_last, max_lag, 5.0, h->d_scratch);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(tau, h->d_scratch, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  return ptg_synchronize(h);
+}
+
 extern "C" int ptg_get_mean_loglike(ptg_handle *h, int32_t n_last, double *mean_ll) {
   if (!h || !mean_ll || n_last < 1) return fail(PTG_EINVAL, "bad argument");
   if (!h->inited) return fail(PTG_EINVAL, "not initialised");

@@ -39,6 +39,12 @@ class Engine(K.CApi):
         self._call("eval", self.h, K._dp(x), C.c_int64(len(x)), None, K._dp(out))
         return out
 
+    def get_act(self, rung, n_last, max_lag):
+        """integrated autocorrelation times [n_ladders, dim] of rung `rung`, computed on the device"""
+        out = np.empty((self.cfg.n_ladders, self.dim))
+        self._call("get_act", self.h, C.c_int32(rung), C.c_int32(n_last), C.c_int32(max_lag), K._dp(out))
+        return out
+
     def get_mean_loglike(self, n_last):
         out = np.empty(self.n_chains)
         self._call("get_mean_loglike", self.h, C.c_int32(n_last), K._dp(out))

@@ -214,3 +214,20 @@ def test_device_evidence_matches_reference_formula_and_analytic_value(engine_cls
     want = ((up + down) / 2).sum() + (up[-1] + down[-1]) / 2 / (b[-2] / b[-1] - 1)
     assert ev[0] == pytest.approx(want, rel=1e-12)
     assert abs(ev.mean() - (-np.log(24.0))) < 0.15, ev.mean()
+
+
+def test_device_act_matches_host_estimator(engine_cls):
+    """ptg_get_act (one CTA per ladder on the device) == the same Sokal-windowed estimator applied on the host to the same history"""
+    from ptmcmc_b200.analysis import integrated_act
+    spec = Spec("gauss", 2, 8, centers=[2, -3], halfwidths=[2, 3])
+    L, n_last, max_lag = 64, 3000, 600
+    e = engine_cls(spec.config(n_ladders=L, rng_mode=K.RNG_PHILOX, hist_capacity=4096, record_level=K.RECORD_BASIC))
+    spec.setup(e); e.init_from_prior(); e.step(5000); e.synchronize()
+    tau = e.get_act(0, n_last, max_lag)
+    cnt = e.get_counters()
+    for l in (0, 17, 63):
+        n = int(cnt["nsize"][l * 8])
+        x = e.get_history(l, 0, n - n_last, n_last, full=False)["x"]
+        for j in range(2):
+            assert tau[l, j] == pytest.approx(integrated_act(x[:, j]), rel=1e-9)
+    assert 8 < np.median(tau) < 30   # tau ~ 16 for this configuration (tests/test_gpu_statistical.py)
