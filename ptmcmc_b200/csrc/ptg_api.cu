@@ -537,8 +537,11 @@ extern "C" int ptg_init_states(ptg_handle *h, const double *x) {
 }
 
 // ------------------------------------------------------------------------------------------------- stepping
+// ladders per CTA of the shared-memory kernel: ~128 threads, bounded by the shared memory a ladder needs
 static int ladders_per_block(const PtgModel &m) {
   int lpb = 128 / m.n_rungs;
+  const size_t per_ladder = ptg_ladder_shared_bytes(m.dim, m.n_rungs), budget = 96 * 1024;
+  if ((size_t)lpb * per_ladder > budget) lpb = (int)(budget / per_ladder);
   if (lpb < 1) lpb = 1;
   if (lpb > m.n_ladders) lpb = m.n_ladders;
   return lpb;
@@ -640,6 +643,7 @@ extern "C" int ptg_step_host(ptg_handle *h, int64_t n_steps, int32_t n_out, doub
   int rc = ptg_step(h, n_steps); if (rc) return rc;
   if (n_out <= 0) return ptg_synchronize(h);
   if (!x_out || !lpost_out || !llike_out) return fail(PTG_EINVAL, "null output");
+  if (n_out > h->m.hist_cap) return fail(PTG_EINVAL, "n_out = %d exceeds the history ring (%d slots)", n_out, h->m.hist_cap);
   PtgModel &m = h->m;
   const long long total = (long long)m.n_ladders * n_out;
   rc = ensure_scratch(h, (size_t)total * (m.dim + 2) * sizeof(double)); if (rc) return rc;

@@ -5,7 +5,7 @@
 #include "../../include/ptmcmc_b200.h"
 
 #define PTG_TPC_MAX_DIM 16   // thread-per-chain kernels
-#define PTG_SWAP_SLOTS 32    // swap trials per PT step: maxswapsperstep = 1+2*swap_rate*Ntemps (chain.cc:1192), capped
+#define PTG_SWAP_SLOTS 64    // swap trials per PT step: maxswapsperstep = 1+2*swap_rate*Ntemps (chain.cc:1192), capped (the oracle caps at 64 too)
 
 // 1-D prior factor (ProbabilityDist.h:76-257)
 struct PtgPrior1D {

@@ -76,6 +76,7 @@ def max_size_cases():
         ("max_dim16_R8", fullcov_spec(16, 8, Tmax=1e3, de_ni=12), 150, 2),
         ("max_dim128_R32", fullcov_spec(128, 32, Tmax=1e4, de_ni=11, swap_rate=0.05), 40, 1),
         ("max_R64", Spec("gauss", 2, 64, centers=[2, -3], halfwidths=[2, 3], seed=0.55, swap_rate=0.05), 200, 1),
+        ("max_swaps_R40", Spec("gauss", 2, 40, centers=[2, -3], halfwidths=[2, 3], seed=0.58, swap_rate=0.5), 150, 1),   # 41 trials per step
         ("min_dim1_R1", Spec("gauss", 1, 1, centers=[0.5], halfwidths=[2.0], prop="gauss", seed=0.66), 500, 3),
     ]
 
