@@ -55,7 +55,8 @@ enum {
   PTG_LIKE_SINES = 2,         /* sin^4 multimodal surface                    (sines.hh:22-54)              */
   PTG_LIKE_POLY_CHI2 = 3,     /* chi^2 of polynomial model over data         (bayesian.hh:595-622, poly_example.cc:85-106) */
   PTG_LIKE_SINUSOID_CHI2 = 4, /* chi^2 of sum of sinusoids over data         (same chi^2) */
-  PTG_LIKE_GAUSS_FULLCOV = 5  /* like0 - x^T Cinv x / 2                      (cython/exampleGaussian.py:103-109) */
+  PTG_LIKE_GAUSS_FULLCOV = 5, /* like0 - x^T Cinv x / 2                      (cython/exampleGaussian.py:103-109) */
+  PTG_LIKE_HOST_CALLBACK = 6  /* the caller's own likelihood, evaluated on the host for all chains at once (ptg_register_evaluate_log) */
 };
 /* proposal kinds (members of a proposal_distribution_set, proposal_distribution.cc:99-129) */
 enum { PTG_PROP_DE = 1, PTG_PROP_GAUSS = 2, PTG_PROP_PRIOR_DRAW = 3 };
@@ -127,6 +128,14 @@ int ptg_set_prior(ptg_handle *h, const int32_t *type, const double *a, const dou
  *   GAUSS_FULLCOV  params = [like0]; data = Cinv[dim*dim] row-major (n_data = dim*dim) */
 int ptg_set_likelihood(ptg_handle *h, int32_t kind, const double *params, int32_t n_params,
                        const double *data, int64_t n_data);
+/* Host-callback likelihood: the batched form of bayes_likelihood::register_evaluate_log / register_reference_object
+ * (bayesian.hh:544-552) for likelihoods that exist only as host code (C++ classes, Python through Cython).  `fn(user, x, n, out)`
+ * receives n states x[n][dim] (row-major) and writes their log-likelihoods; non-finite values count as -inf (bayesian.hh:569-575).
+ * Everything else of the step stays on the GPU: per PT iteration one kernel runs the swap phase and generates every chain's
+ * proposal, the proposals that pass the prior gate (chain.cc:980) are handed to `fn` in ONE call, a second kernel does the
+ * Metropolis test and the history append.  Replaces ptg_set_likelihood.  Philox draws, dim <= 16. */
+typedef void (*ptg_batch_loglike_fn)(void *user, const double *x, int64_t n, double *loglike);
+int ptg_register_evaluate_log(ptg_handle *h, ptg_batch_loglike_fn fn, void *user);
 /* proposal_distribution_set constructor (proposal_distribution.cc:61-93).  wrap_in_set=0 (n must be 1) uses the
  * single proposal bare, as ptmcmc drivers do when they pass e.g. a differential_evolution directly to
  * set_proposal (testMH.cpp:91-160): no selection draw, type() not multiplied by 10. */

@@ -132,9 +132,28 @@ protected:
 public:
   probability_function(const stateSpace *space, int32_t kind) : space(space), kind(kind) {}
   virtual ~probability_function() {}
-  void push(ptg_handle *h) const {
+  virtual void push(ptg_handle *h) {
     check(ptg_set_likelihood(h, kind, params.data(), (int32_t)params.size(), data.empty() ? nullptr : data.data(), (int64_t)data.size()), "ptg_set_likelihood");
   }
+};
+// A likelihood that exists only as host code: derive and override evaluate_log(state&) exactly as with the reference's
+// probability_function / bayes_likelihood (probability_function.hh:31-45, bayesian.hh:553-581).  The engine calls it for all
+// chains' proposals of a PT iteration in one batch (ptg_register_evaluate_log); everything else of the step stays on the GPU.
+class host_probability_function : public probability_function {
+  static void trampoline(void *user, const double *x, int64_t n, double *out) {
+    host_probability_function *self = static_cast<host_probability_function *>(user);
+    const int d = self->space->size();
+    std::valarray<double> p(d);
+    for (int64_t i = 0; i < n; i++) {
+      for (int j = 0; j < d; j++) p[j] = x[i * d + j];
+      state s(self->space, p);
+      out[i] = self->evaluate_log(s);
+    }
+  }
+public:
+  explicit host_probability_function(const stateSpace *space) : probability_function(space, PTG_LIKE_HOST_CALLBACK) {}
+  virtual double evaluate_log(state &s) = 0;
+  void push(ptg_handle *h) { check(ptg_register_evaluate_log(h, trampoline, this), "ptg_register_evaluate_log"); }
 };
 // sines.hh:12-61
 class sines : public probability_function {

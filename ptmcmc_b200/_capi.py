@@ -16,7 +16,7 @@ MAX_RUNGS = 64
 # enums (include/ptmcmc_b200.h)
 BOUND_OPEN, BOUND_LIMIT, BOUND_REFLECT, BOUND_WRAP = 0, 1, 2, 3
 PRIOR_UNIFORM, PRIOR_GAUSSIAN, PRIOR_POLAR, PRIOR_COPOLAR, PRIOR_LOG = 1, 2, 3, 4, 5
-LIKE_FLAT, LIKE_GAUSS_ISO, LIKE_SINES, LIKE_POLY_CHI2, LIKE_SINUSOID_CHI2, LIKE_GAUSS_FULLCOV = 0, 1, 2, 3, 4, 5
+LIKE_FLAT, LIKE_GAUSS_ISO, LIKE_SINES, LIKE_POLY_CHI2, LIKE_SINUSOID_CHI2, LIKE_GAUSS_FULLCOV, LIKE_HOST_CALLBACK = 0, 1, 2, 3, 4, 5, 6
 PROP_DE, PROP_GAUSS, PROP_PRIOR_DRAW = 1, 2, 3
 SWAP_REFERENCE, SWAP_EVEN_ODD = 0, 1
 RNG_PHILOX, RNG_TAPE = 0, 1

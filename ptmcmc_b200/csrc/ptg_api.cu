@@ -50,6 +50,9 @@ struct ptg_handle {
   double *d_scratch; size_t scratch_bytes;
   double *h_pinned; size_t pinned_bytes;
   int kernel_choice; long long launches;
+  ptg_batch_loglike_fn cb_fn; void *cb_user;   // host-callback likelihood
+  int32_t *d_attempt, *d_nopen;
+  std::vector<double> cb_x, cb_like, cb_xc, cb_lc; std::vector<int32_t> cb_flags; std::vector<int64_t> cb_idx;
 };
 
 template <typename T>
@@ -159,7 +162,7 @@ extern "C" int ptg_create(const ptg_config *cfg, ptg_handle **out) {
   h->have_space = h->have_prior = h->have_like = h->have_props = h->inited = h->model_uploaded = false; h->model_dirty = true;
   h->d_lparams = h->d_ldata = h->d_prop_data = h->d_bins = nullptr;
   h->d_tape_u = h->d_tape_z = nullptr; h->d_u_end = h->d_z_end = nullptr;
-  h->kernel_choice = PTG_KERNEL_AUTO; h->launches = 0; h->istep = 0; h->Tpow = 0; h->d_scratch = nullptr; h->scratch_bytes = 0; h->h_pinned = nullptr; h->pinned_bytes = 0;
+  h->kernel_choice = PTG_KERNEL_AUTO; h->launches = 0; h->cb_fn = nullptr; h->cb_user = nullptr; h->d_attempt = h->d_nopen = nullptr; h->istep = 0; h->Tpow = 0; h->d_scratch = nullptr; h->scratch_bytes = 0; h->h_pinned = nullptr; h->pinned_bytes = 0;
   cudaError_t es = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (es != cudaSuccess) { delete h; return fail(PTG_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(es)); }
   h->own_stream = true;
@@ -295,6 +298,7 @@ extern "C" int ptg_set_likelihood(ptg_handle *h, int32_t kind, const double *par
   case PTG_LIKE_GAUSS_ISO: need = 2 + d; break;
   case PTG_LIKE_SINES: need = 2 + 3 * d; break;
   case PTG_LIKE_POLY_CHI2: case PTG_LIKE_SINUSOID_CHI2: case PTG_LIKE_GAUSS_FULLCOV: need = 1; break;
+  case PTG_LIKE_HOST_CALLBACK: return fail(PTG_EINVAL, "use ptg_register_evaluate_log for a host-callback likelihood");
   default: return fail(PTG_EINVAL, "unknown likelihood kind %d", kind);
   }
   if (n_params < need || (need && !params)) return fail(PTG_EINVAL, "likelihood kind %d needs %d params", kind, need);
@@ -315,6 +319,46 @@ extern "C" int ptg_set_likelihood(ptg_handle *h, int32_t kind, const double *par
   }
   h->have_like = true;
   h->model_dirty = true;
+  return 0;
+}
+
+extern "C" int ptg_register_evaluate_log(ptg_handle *h, ptg_batch_loglike_fn fn, void *user) {
+  if (!h || !fn) return fail(PTG_EINVAL, "null argument");
+  if (h->inited) return fail(PTG_EINVAL, "register the likelihood before initialising");
+  if (h->wide) return fail(PTG_EINVAL, "host-callback likelihoods need dim <= 16");
+  if (h->cfg.rng_mode != PTG_RNG_PHILOX) return fail(PTG_EINVAL, "host-callback likelihoods run with Philox draws");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  PtgModel &m = h->m; PtgState &s = h->s;
+  const size_t n = (size_t)m.n_chains, d = (size_t)m.dim;
+  if (!s.pend_x) {
+    int rc = 0;
+    rc |= dev_alloc(h, &s.pend_x, n * d); rc |= dev_alloc(h, &s.pend_lprior, n); rc |= dev_alloc(h, &s.pend_lh, n); rc |= dev_alloc(h, &s.pend_like, n);
+    rc |= dev_alloc(h, &s.pend_type, n); rc |= dev_alloc(h, &s.pend_flags, n); rc |= dev_alloc(h, &s.pend_w, 2 * n);
+    rc |= dev_alloc(h, &h->d_attempt, n); rc |= dev_alloc(h, &h->d_nopen, 1);
+    if (rc) return PTG_ENOMEM;
+  }
+  h->cb_fn = fn; h->cb_user = user;
+  h->cb_x.resize(n * d); h->cb_like.resize(n); h->cb_xc.resize(n * d); h->cb_lc.resize(n); h->cb_flags.resize(n); h->cb_idx.resize(n);
+  h->lparams.assign(1, 0.0); h->ldata.clear();
+  m.like_kind = PTG_LIKE_HOST_CALLBACK; m.n_lparams = 0; m.n_ldata = 0; m.like_nsum = 0;
+  h->have_like = true; h->model_dirty = true;
+  return 0;
+}
+
+// host-callback mode: fetch the parked proposals, evaluate the caller's likelihood for the gated ones in one call, send the values back
+static int callback_round(ptg_handle *h) {
+  PtgModel &m = h->m; PtgState &s = h->s;
+  const size_t n = (size_t)m.n_chains, d = (size_t)m.dim;
+  CUDA_TRY(cudaMemcpyAsync(h->cb_x.data(), s.pend_x, n * d * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->cb_flags.data(), s.pend_flags, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  int64_t cnt = 0;
+  for (size_t c = 0; c < n; c++)
+    if ((h->cb_flags[c] & 2) && h->cb_flags[c] != 8) { memcpy(&h->cb_xc[(size_t)cnt * d], &h->cb_x[c * d], d * sizeof(double)); h->cb_idx[cnt++] = (int64_t)c; }
+  if (cnt) h->cb_fn(h->cb_user, h->cb_xc.data(), cnt, h->cb_lc.data());
+  for (size_t c = 0; c < n; c++) h->cb_like[c] = -INFINITY;
+  for (int64_t k = 0; k < cnt; k++) h->cb_like[(size_t)h->cb_idx[k]] = h->cb_lc[k];
+  CUDA_TRY(cudaMemcpyAsync(s.pend_like, h->cb_like.data(), n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   return 0;
 }
 
@@ -518,6 +562,40 @@ static int do_init(ptg_handle *h, const double *x_host) {
     rc = dev_alloc(h, &d_x, cnt, false); if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(d_x, x_host, cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   }
+  if (m.like_kind == PTG_LIKE_HOST_CALLBACK) {
+    // MH_chain::initialize (chain.cc:846-876) with the caller's likelihood: one prior draw per chain and round, redrawn while invalid
+    // or log L < -1e100, the same Philox addresses as the fused init kernel
+    if (x_host) return fail(PTG_EINVAL, "ptg_init_states is not available with a host-callback likelihood");
+    const int lpb0 = 1; (void)lpb0;
+    for (int k = 0; k < m.n_init; k++) {
+      CUDA_TRY(cudaMemsetAsync(s.pend_flags, 0, (size_t)n * sizeof(int32_t), h->stream));
+      CUDA_TRY(cudaMemsetAsync(h->d_attempt, 0, (size_t)n * sizeof(int32_t), h->stream));
+      for (int round = 0;; round++) {
+        cudaError_t ec = cudaErrorInvalidValue;
+        switch (m.dim) {
+#define X(D) case D: ec = ptg_launch_cb_d##D(2, m, s, 0, 1, 0, k, h->d_attempt, h->d_nopen, h->stream); break;
+          PTG_DIM_LIST(X)
+#undef X
+        }
+        CUDA_TRY(ec);
+        rc = callback_round(h); if (rc) return rc;
+        CUDA_TRY(cudaMemsetAsync(h->d_nopen, 0, sizeof(int32_t), h->stream));
+        switch (m.dim) {
+#define X(D) case D: ec = ptg_launch_cb_d##D(3, m, s, 0, 1, 0, k, h->d_attempt, h->d_nopen, h->stream); break;
+          PTG_DIM_LIST(X)
+#undef X
+        }
+        CUDA_TRY(ec);
+        int32_t open = 0;
+        CUDA_TRY(cudaMemcpyAsync(&open, h->d_nopen, sizeof(open), cudaMemcpyDeviceToHost, h->stream));
+        rc = check_device_error(h); if (rc) return rc;
+        if (open == 0) break;
+      }
+    }
+    CUDA_TRY(cudaMemsetAsync(s.pend_flags, 0, (size_t)n * sizeof(int32_t), h->stream));
+    h->inited = true; h->istep = 0;
+    return 0;
+  }
   cudaError_t e = cudaErrorInvalidValue;
   if (h->wide) e = ptg_launch_xinit(h->cfg.rng_mode, m, s, d_x, h->stream);
   else switch (m.dim) {
@@ -574,6 +652,29 @@ extern "C" int ptg_step(ptg_handle *h, int64_t n_steps) {
   if (n_steps < 0) return fail(PTG_EINVAL, "negative step count");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   PtgModel &m = h->m;
+  if (m.like_kind == PTG_LIKE_HOST_CALLBACK) {
+    // per PT iteration: swap phase + proposals on the device, the caller's likelihood on the host, Metropolis test + append on the device
+    const int lpb = ladders_per_block(m);
+    const size_t smem = (size_t)lpb * ptg_ladder_shared_bytes(m.dim, m.n_rungs) + (size_t)m.n_rungs * m.n_props * sizeof(double);
+    for (int64_t it = 0; it < n_steps; it++) {
+      cudaError_t ec = cudaErrorInvalidValue;
+      switch (m.dim) {
+#define X(D) case D: ec = ptg_launch_cb_d##D(0, m, h->s, h->istep, lpb, smem, 0, nullptr, nullptr, h->stream); break;
+        PTG_DIM_LIST(X)
+#undef X
+      }
+      CUDA_TRY(ec);
+      int rc = callback_round(h); if (rc) return rc;
+      switch (m.dim) {
+#define X(D) case D: ec = ptg_launch_cb_d##D(1, m, h->s, h->istep, lpb, smem, 0, nullptr, nullptr, h->stream); break;
+        PTG_DIM_LIST(X)
+#undef X
+      }
+      CUDA_TRY(ec);
+      h->istep++; h->launches += 2;
+    }
+    return 0;
+  }
   int W = 0;
   const int kern = pick_kernel(h, &W);
   const int lpb = ladders_per_block(m);
@@ -663,6 +764,12 @@ extern "C" int ptg_eval(ptg_handle *h, const double *x, int64_t n, double *logli
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   if (!h->model_uploaded || h->model_dirty) { int rc = upload_model(h); if (rc) return rc; }
   PtgModel &m = h->m;
+  if (m.like_kind == PTG_LIKE_HOST_CALLBACK && loglike) { // the caller's own function: evaluated where it lives
+    h->cb_fn(h->cb_user, x, n, loglike);
+    for (int64_t i = 0; i < n; i++) if (!std::isfinite(loglike[i])) loglike[i] = -INFINITY;
+    if (!logprior) return 0;
+    loglike = nullptr;
+  }
   const size_t d = (size_t)m.dim;
   int rc = ensure_scratch(h, (size_t)n * (d + 2) * sizeof(double)); if (rc) return rc;
   double *dx = h->d_scratch, *dll = dx + (size_t)n * d, *dlp = dll + n;

@@ -7,14 +7,14 @@
 #include "ptg_launch.h"
 
 template <int D, int MODE>
-static cudaError_t launch_step_t(const PtgModel &m, const PtgState &s, long long step0, int n_steps, int lpb, size_t smem, cudaStream_t st) {
+static cudaError_t launch_step_t(const PtgModel &m, const PtgState &s, long long step0, int n_steps, int lpb, size_t smem, cudaStream_t st, int phase = 0) {
   auto k = ptg_step_kernel<D, MODE>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
   int blocks = (int)((m.n_ladders + lpb - 1) / lpb);
-  k<<<blocks, lpb * m.n_rungs, smem, st>>>(m, s, step0, n_steps, lpb);
+  k<<<blocks, lpb * m.n_rungs, smem, st>>>(m, s, step0, n_steps, lpb, phase);
   return cudaGetLastError();
 }
 // second-generation kernel: ladder-in-a-warp (n_rungs <= W <= 32), 4 warps per CTA
@@ -47,6 +47,15 @@ static cudaError_t launch_init_t(const PtgModel &m, const PtgState &s, const dou
                                    size_t smem, cudaStream_t st) {                                                           \
     return mode == PTG_RNG_TAPE ? launch_step_t<D, PTG_RNG_TAPE>(m, s, step0, n_steps, lpb, smem, st)                        \
                                 : launch_step_t<D, PTG_RNG_PHILOX>(m, s, step0, n_steps, lpb, smem, st);                     \
+  }                                                                                                                          \
+  cudaError_t ptg_launch_cb_d##D(int what, const PtgModel &m, const PtgState &s, long long step, int lpb, size_t smem, int k, int32_t *attempt,   \
+                                 int32_t *n_open, cudaStream_t st) {                                                        \
+    const unsigned nb = (unsigned)((m.n_chains + 127) / 128);                                                                \
+    if (what == 0) return launch_step_t<D, PTG_RNG_PHILOX>(m, s, step, 1, lpb, smem, st, 1);                                 \
+    if (what == 1) ptg_cb_finish_kernel<D><<<nb, 128, 0, st>>>(m, s, step);                                                  \
+    else if (what == 2) ptg_cb_init_draw_kernel<D><<<nb, 128, 0, st>>>(m, s, k, attempt);                                    \
+    else ptg_cb_init_accept_kernel<D><<<nb, 128, 0, st>>>(m, s, attempt, n_open);                                            \
+    return cudaGetLastError();                                                                                               \
   }                                                                                                                          \
   cudaError_t ptg_launch_wstep_d##D(int mode, const PtgModel &m, const PtgState &s, long long step0, int n_steps, int W,     \
                                     cudaStream_t st) {                                                                       \

@@ -125,11 +125,24 @@ __device__ __forceinline__ int de_draw_index(const PtgModel &m, const PtgState &
 
 struct MhOut { double lhr; int code; };
 
-// MH_chain::step(prop) (chain.cc:966-1022) with proposal_distribution_set::draw (proposal_distribution.cc:99-129)
-template <int D, int MODE>
-__device__ __forceinline__ MhOut mh_step(const PtgModel &m, const PtgState &s, Chain<D> &ch, Stream<MODE> &rs,
-                                         const double *__restrict__ bins) {
+// A proposal between its generation and the Metropolis test: what MH_chain::step holds when it calls the likelihood
+// (chain.cc:975-981).  The fused kernels evaluate a device functor in between; the host-callback mode (ptg_callback.cuh)
+// parks this in global memory while the caller's likelihood runs.
+template <int D>
+struct MhPending {
   double newx[D];
+  double newlprior, prop_lh;
+  int type;
+  bool valid, gate;    // gate: the likelihood is evaluated (chain.cc:980)
+  uint32_t wacc[2];    // the acceptance draw's Philox words
+};
+
+// first half of MH_chain::step(prop) (chain.cc:966-980) with proposal_distribution_set::draw (proposal_distribution.cc:99-129):
+// draw, enforce, prior, likelihood gate
+template <int D, int MODE>
+__device__ __forceinline__ void mh_propose(const PtgModel &m, const PtgState &s, Chain<D> &ch, Stream<MODE> &rs,
+                                           const double *__restrict__ bins, MhPending<D> &pend) {
+  double (&newx)[D] = pend.newx;
   double prop_lh = 0;
   int type = 0;
   bool valid = m.zero_valid != 0;
@@ -258,26 +271,35 @@ __device__ __forceinline__ MhOut mh_step(const PtgModel &m, const PtgState &s, C
   }
   if (m.wrap_in_set) type = member + 10 * type;
 
-  // ---- enforce, prior, gated likelihood (chain.cc:976-987)
+  // ---- enforce, prior, likelihood gate (chain.cc:976-980)
   if (valid) valid = space_enforce<D>(m, newx);
   const double newlprior = prior_eval_log<D>(m, newx, valid);
-  double newlike, newlpost;
+  pend.newlprior = newlprior; pend.prop_lh = prop_lh; pend.type = type; pend.valid = valid;
+  pend.gate = valid && ((newlprior > -1e200) || (newlprior - oldlprior > m.dprior_min));
+  pend.wacc[0] = widx[2]; pend.wacc[1] = widx[3];
+}
+
+// second half of MH_chain::step (chain.cc:981-1019): posterior, Metropolis test, add_state.  newlike is ignored unless pend.gate.
+template <int D, int MODE>
+__device__ __forceinline__ MhOut mh_finish(const PtgModel &m, const PtgState &s, Chain<D> &ch, Stream<MODE> &rs, const MhPending<D> &pend,
+                                           double newlike) {
+  const double (&newx)[D] = pend.newx;
+  const double newlprior = pend.newlprior;
+  const int type = pend.type;
+  const bool valid = pend.valid;
+  double newlpost;
   int code = 0;
   bool accept = true;
-  if (valid && ((newlprior > -1e200) || (newlprior - oldlprior > m.dprior_min))) {
-    newlike = like_eval<D>(m, newx);
-    newlpost = newlike * ch.beta + newlprior;
-  } else {
-    newlike = newlpost = -CUDART_INF;
-    code |= PTG_TRACE_NOLIKE;
-  }
+  if (pend.gate) newlpost = newlike * ch.beta + newlprior;
+  else { newlike = newlpost = -CUDART_INF; code |= PTG_TRACE_NOLIKE; }
   // ---- Metropolis test (chain.cc:989-1001)
-  double lhr = prop_lh;
+  double lhr = pend.prop_lh;
   if (isnan(lhr)) accept = false;
   lhr += newlpost - ch.lpost;
   if (!valid) { accept = false; code |= PTG_TRACE_INVALID; }
   if (accept && lhr < 0) {
-    double u = rs.u52(widx, 1);
+    double u;
+    if constexpr (MODE == PTG_RNG_PHILOX) u = ptg_u52_to_unit(pend.wacc[0], pend.wacc[1]); else u = rs.next_u();
     accept = (log(u) < lhr);
   }
   ch.ntries++;
@@ -293,6 +315,17 @@ __device__ __forceinline__ MhOut mh_step(const PtgModel &m, const PtgState &s, C
   code |= (type & PTG_TRACE_TYPE_MASK);
   MhOut o; o.lhr = lhr; o.code = code;
   return o;
+}
+
+// MH_chain::step(prop) (chain.cc:966-1022), fused with a device likelihood functor
+template <int D, int MODE>
+__device__ __forceinline__ MhOut mh_step(const PtgModel &m, const PtgState &s, Chain<D> &ch, Stream<MODE> &rs,
+                                         const double *__restrict__ bins) {
+  MhPending<D> pend;
+  mh_propose<D, MODE>(m, s, ch, rs, bins, pend);
+  double newlike = -CUDART_INF;
+  if (pend.gate) newlike = like_eval<D>(m, pend.newx);
+  return mh_finish<D, MODE>(m, s, ch, rs, pend, newlike);
 }
 
 template <int MODE>
@@ -376,6 +409,73 @@ __global__ void __launch_bounds__(128) ptg_eval_kernel(const __grid_constant__ P
     bool valid = space_enforce<D>(m, v);
     out_lp[i] = prior_eval_log<D>(m, v, valid);
   }
+}
+
+// ------------------------------------------------------------------------------------------------- host-callback likelihood
+// completes the MH step of every chain that parked a proposal (ptg_step_kernel phase 1), with the caller's log-likelihoods
+template <int D>
+__global__ void __launch_bounds__(128) ptg_cb_finish_kernel(const __grid_constant__ PtgModel m, PtgState s, long long step) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= m.n_chains) return;
+  const int flags = s.pend_flags[c];
+  if (!(flags & 4)) return;
+  Chain<D> ch;
+  chain_load<D>(m, s, c, ch);
+  MhPending<D> pend;
+#pragma unroll
+  for (int k = 0; k < D; k++) pend.newx[k] = s.pend_x[c * D + k];
+  pend.newlprior = s.pend_lprior[c]; pend.prop_lh = s.pend_lh[c]; pend.type = s.pend_type[c];
+  pend.valid = (flags & 1) != 0; pend.gate = (flags & 2) != 0;
+  pend.wacc[0] = s.pend_w[2 * c]; pend.wacc[1] = s.pend_w[2 * c + 1];
+  double newlike = s.pend_like[c];
+  if (!isfinite(newlike)) newlike = -CUDART_INF; // bayesian.hh:569-575
+  Stream<PTG_RNG_PHILOX> rs;
+  stream_blank<PTG_RNG_PHILOX>(m, rs);
+  const MhOut o = mh_finish<D, PTG_RNG_PHILOX>(m, s, ch, rs, pend, newlike);
+  chain_store<D>(m, s, ch);
+  if (step < m.trace_steps) { s.trace_lhr[step * m.n_chains + c] = o.lhr; s.trace_code[step * m.n_chains + c] = o.code; }
+}
+// MH_chain::initialize with a host likelihood, one prior draw per chain and round: chains whose flag is still 0 draw sample `k`
+// (attempt[c]) into pend_x; after the caller evaluated pend_like, ptg_cb_init_accept_kernel appends the accepted ones
+template <int D>
+__global__ void __launch_bounds__(128) ptg_cb_init_draw_kernel(const __grid_constant__ PtgModel m, PtgState s, int k, const int32_t *__restrict__ attempt) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= m.n_chains || s.pend_flags[c] == 8) return; // 8 = sample k already accepted
+  const int R = m.n_rungs;
+  const long long ladder = c / R; const int rung = (int)(c - ladder * R);
+  Stream<PTG_RNG_PHILOX> rs;
+  stream_blank<PTG_RNG_PHILOX>(m, rs);
+  rs.id = (uint64_t)(m.ladder_offset + ladder) * PTG_STREAM_STRIDE + (uint64_t)rung; rs.domain = PTG_DOMAIN_INIT; rs.step = (uint64_t)k;
+  double x[D];
+  const bool valid = prior_draw<D, PTG_RNG_PHILOX>(m, rs, (uint32_t)attempt[c] * PTG_INIT_ATTEMPT_STRIDE, x);
+#pragma unroll
+  for (int i = 0; i < D; i++) s.pend_x[c * D + i] = x[i];
+  s.pend_flags[c] = valid ? 3 : 0; // valid + likelihood wanted
+}
+template <int D>
+__global__ void __launch_bounds__(128) ptg_cb_init_accept_kernel(const __grid_constant__ PtgModel m, PtgState s, int32_t *attempt, int32_t *n_open) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= m.n_chains || s.pend_flags[c] == 8) return;
+  double ll = s.pend_like[c];
+  if (!isfinite(ll)) ll = -CUDART_INF;
+  if (!(s.pend_flags[c] & 1) || ll < -1e100) { // chain.cc:854-866: redraw
+    attempt[c]++;
+    if (attempt[c] >= 100000) atomicMax(s.err, 4); else atomicAdd(n_open, 1);
+    return;
+  }
+  Chain<D> ch;
+  chain_load<D>(m, s, c, ch);
+  double x[D];
+#pragma unroll
+  for (int i = 0; i < D; i++) { x[i] = s.pend_x[c * D + i]; ch.x[i] = x[i]; }
+  const double lp = prior_eval_log<D>(m, x, true);
+  ch.llike = ll; ch.lprior = lp; ch.lpost = lp + ch.beta * ll;
+  ch.nhist = 0; ch.since_save = 0;
+  chain_append<D>(m, s, ch, ch.x, ch.llike, ch.lpost, ch.beta);
+  ch.nhist = 0;
+  chain_store<D>(m, s, ch);
+  s.pend_flags[c] = 8;
+  attempt[c] = 0;
 }
 
 // ------------------------------------------------------------------------------------------------- PT step
@@ -478,7 +578,9 @@ __device__ __forceinline__ void swap_phase_leader(const PtgModel &m, LadderShare
 
 // The fused PT-step kernel.  blockDim.x = lpb * n_rungs; dynamic shared memory = lpb * ptg_ladder_shared_bytes + bins.
 template <int D, int MODE>
-__global__ void __launch_bounds__(256) ptg_step_kernel(const __grid_constant__ PtgModel m, PtgState s, long long step0, int n_steps, int lpb) {
+// phase 0: fused step.  phase 1 (host-callback likelihood, n_steps = 1): swap phase + proposal, the MH lanes park their proposal in
+// s.pend_* and ptg_cb_finish_kernel completes the step once the caller's likelihood values are in s.pend_like.
+__global__ void __launch_bounds__(256) ptg_step_kernel(const __grid_constant__ PtgModel m, PtgState s, long long step0, int n_steps, int lpb, int phase) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int R = m.n_rungs;
   const int ll_ = threadIdx.x / R;              // local ladder
@@ -594,10 +696,21 @@ __global__ void __launch_bounds__(256) ptg_step_kernel(const __grid_constant__ P
       } else {
         if (m.evolve_rate > 0) ch.lpost = L.slpost[rung]; // resetTemp may have touched any interior rung
         rs.step = step;
-        MhOut o = mh_step<D, MODE>(m, s, ch, rs, sbins + rung * m.n_props);
-        lhr = o.lhr; code = o.code;
+        if (phase == 0) {
+          MhOut o = mh_step<D, MODE>(m, s, ch, rs, sbins + rung * m.n_props);
+          lhr = o.lhr; code = o.code;
+        } else {
+          MhPending<D> pend;
+          mh_propose<D, MODE>(m, s, ch, rs, sbins + rung * m.n_props, pend);
+#pragma unroll
+          for (int k = 0; k < D; k++) s.pend_x[chain * D + k] = pend.newx[k];
+          s.pend_lprior[chain] = pend.newlprior; s.pend_lh[chain] = pend.prop_lh; s.pend_type[chain] = pend.type;
+          s.pend_w[2 * chain] = pend.wacc[0]; s.pend_w[2 * chain + 1] = pend.wacc[1];
+          s.pend_flags[chain] = (pend.valid ? 1 : 0) | (pend.gate ? 2 : 0) | 4;
+        }
       }
-      if ((long long)step < m.trace_steps) {
+      if (phase == 1 && na > 0) s.pend_flags[chain] = 0;
+      if ((long long)step < m.trace_steps && !(phase == 1 && na == 0)) {
         s.trace_lhr[step * m.n_chains + chain] = lhr;
         s.trace_code[step * m.n_chains + chain] = code;
       }

@@ -73,6 +73,11 @@ struct PtgState {
   // trace
   double *trace_lhr;  // [trace_steps][n_chains]
   int32_t *trace_code;
+  // host-callback likelihood mode (ptg_register_evaluate_log): the parked proposal of every chain
+  double *pend_x;                       // [n_chains][dim]  (row-major: handed to the caller's batched likelihood as is)
+  double *pend_lprior, *pend_lh, *pend_like; // [n_chains]
+  int32_t *pend_type, *pend_flags;      // flags: bit0 valid, bit1 gate (likelihood wanted), bit2 MH step pending
+  uint32_t *pend_w;                     // [n_chains][2] acceptance-draw words
   int32_t *err;       // device error flag (PTG_ETAPE, PTG_ESTUCK)
 };
 #endif

@@ -11,6 +11,20 @@ class Engine(K.CApi):
     def __init__(self, cfg):
         super().__init__(load(), "ptg_", cfg)
 
+    def register_evaluate_log(self, fn):
+        """host-callback likelihood: fn(x[n, dim]) -> loglike[n], called once per PT iteration with every gated proposal
+        (the batched form of bayes_likelihood::register_evaluate_log, bayesian.hh:544-552)"""
+        CB = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_double), C.c_int64, C.POINTER(C.c_double))
+        d = self.dim
+
+        def trampoline(_user, xp, n, outp):
+            x = np.ctypeslib.as_array(xp, shape=(n, d))
+            out = np.ctypeslib.as_array(outp, shape=(n,))
+            out[:] = fn(x)
+
+        self._cb = CB(trampoline)  # keep alive
+        self._call("register_evaluate_log", self.h, self._cb, None)
+
     def synchronize(self):
         self._call("synchronize", self.h)
 

@@ -1,6 +1,6 @@
 // facade_driver.cc -- a driver written against include/ptmcmc_b200.hh the way testMH.cpp / example.cc are written against
 // the reference: state space, prior, likelihood, proposal mix, parallel_tempering_chains, step loop, dumpChain.
-//   facade_driver <model: sines|gauss> <dim> <Ntemps> <nsteps> <n_ladders> <outfile> [evolve_rate]
+//   facade_driver <model: sines|gauss|hostgauss> <dim> <Ntemps> <nsteps> <n_ladders> <outfile> [evolve_rate]
 // Writes the cold chain of ladder 0 (and of the last ladder, to <outfile>.last) in the reference's chain-file format.
 #include <cstdio>
 #include <cstdlib>
@@ -9,6 +9,22 @@
 #include "ptmcmc_b200.hh"
 using namespace ptg;
 using namespace std;
+
+// a likelihood written the reference's way: a class with evaluate_log(state&) on the host (example.cc:74-143)
+class host_gaussian : public host_probability_function {
+  valarray<double> x0; double lnnormfac, twosigmasq;
+public:
+  host_gaussian(const stateSpace *sp, const valarray<double> &x0, double sigma) : host_probability_function(sp), x0(x0) {
+    twosigmasq = 2 * sigma * sigma;
+    lnnormfac = -0.5 * (double)x0.size() * std::log(M_PI * twosigmasq);
+  }
+  double evaluate_log(state &s) {
+    valarray<double> p = s.get_params();
+    double r2 = 0;
+    for (size_t i = 0; i < x0.size(); i++) { double dx = p[i] - x0[i]; r2 += dx * dx; }
+    return lnnormfac - r2 / twosigmasq;
+  }
+};
 
 int main(int argc, char **argv) {
   if (argc < 7) { fprintf(stderr, "usage: %s model dim Ntemps nsteps n_ladders outfile [evolve_rate]\n", argv[0]); return 2; }
@@ -29,7 +45,8 @@ int main(int argc, char **argv) {
     like = new sines(&space, 64.0, ks, lo, hi, log(2.0));
   } else { // example.cc:88-104: uniform prior box, isotropic Gaussian likelihood, bounds left open
     for (int i = 0; i < dim; i++) { centers[i] = 2.0 - 5.0 * (i % 2); lo[i] = centers[i] - 2 - i; hi[i] = centers[i] + 2 + i; }
-    like = new gaussian_likelihood(&space, centers, 0.5);
+    if (model == "hostgauss") like = new host_gaussian(&space, centers, 0.5);   // same arithmetic, evaluated by the caller on the host
+    else like = new gaussian_likelihood(&space, centers, 0.5);
   }
   uniform_dist_product prior(&space, lo, hi);
   default_proposal_mix mix(prior);

@@ -41,7 +41,7 @@ def read_chain_file(path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("model,dim,R,steps,L,evolve", [("sines", 3, 8, 400, 5, 0.0), ("gauss", 2, 6, 300, 3, 0.01)])
+@pytest.mark.parametrize("model,dim,R,steps,L,evolve", [("sines", 3, 8, 400, 5, 0.0), ("gauss", 2, 6, 300, 3, 0.01), ("hostgauss", 2, 6, 120, 3, 0.01)])
 def test_facade_driver_matches_engine(model, dim, R, steps, L, evolve, tmp_path, engine_cls):
     exe = build_driver(tmp_path)
     out = os.path.join(str(tmp_path), "chain.dat")
@@ -56,7 +56,10 @@ def test_facade_driver_matches_engine(model, dim, R, steps, L, evolve, tmp_path,
         c = np.array([2.0 - 5.0 * (i % 2) for i in range(dim)]); hw = np.array([2.0 + i for i in range(dim)])
         spec = Spec("gauss", dim, R, centers=c, halfwidths=hw, evolve_rate=evolve)
     e = engine_cls(spec.config(n_ladders=L, rng_mode=K.RNG_PHILOX, hist_capacity=50 * dim + 2 * steps + 8, seed=0xB2000003))
-    spec.setup(e); e.init_from_prior(); e.step(steps); e.synchronize()
+    spec.setup(e)
+    if model == "hostgauss":
+        e.select_kernel(K.KERNEL_SHARED)   # the C++ driver's host likelihood (evaluate_log(state&)) against the fused device functor
+    e.init_from_prior(); e.step(steps); e.synchronize()
     cnt = e.get_counters(); cur = e.get_current()
     for path, ladder, with_init in ((out, 0, True), (out + ".last", L - 1, False)):
         f = read_chain_file(path)
