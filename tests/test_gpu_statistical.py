@@ -111,3 +111,29 @@ def test_ring_window_bias_and_its_remedy(oracle_cls, engine_cls):
     # samples after 6000 iterations and sits 2 % low; the thinned ring forgets them and is closest to the target
     assert abs(v_thinned / 0.25 - 1) < 0.02 and abs(v_long / 0.25 - 1) < 0.04
     assert v_short < v_thinned - 0.004   # the bias a thinned (or much longer) ring removes
+
+
+def test_gaussian_proposal_covariance(engine_cls):
+    """the reference's testGaussian.cc (:24-75): draws from gaussian_prop(cov) for a random 5x5 covariance reproduce that covariance.
+    Here through the engine: flat likelihood inside a huge uniform box accepts every proposal, so the increments of a plain MH chain
+    ARE the proposal draws (Philox Box-Muller, sigma scaling, eigen-rotation in Eigen's summation order)."""
+    rng = np.random.default_rng(224)
+    d = 5
+    A = rng.normal(size=(d, d)); cov = A @ A.T + 0.1 * np.eye(d)
+    w, V = np.linalg.eigh(cov)
+    spec = Spec("flat", d, 1, centers=np.zeros(d), halfwidths=np.full(d, 1e6), prop="cov")
+    spec.eig = (np.sqrt(w), V)
+    L, steps = 512, 2000
+    e = engine_cls(spec.config(n_ladders=L, rng_mode=K.RNG_PHILOX, hist_capacity=spec.de_ni * d + steps + 8, record_level=K.RECORD_BASIC))
+    spec.setup(e); e.init_from_prior(); e.step(steps); e.synchronize()
+    inc = []
+    for l in range(0, L, 8):
+        n = int(e.get_counters()["nsize"][l])
+        x = e.get_history(l, 0, n - steps, steps, full=False)["x"]
+        inc.append(np.diff(x, axis=0))
+    inc = np.concatenate(inc)
+    assert (np.abs(inc).sum(axis=1) > 0).all()              # every proposal was accepted
+    sample = np.cov(inc.T)
+    err = np.linalg.norm(sample - cov) / np.linalg.norm(cov)
+    assert err < 0.02, err                                   # ~1.3e5 draws: testGaussian.cc prints this norm at powers of two
+    assert abs(inc.mean()) < 0.02
