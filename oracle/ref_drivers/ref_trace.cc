@@ -285,6 +285,14 @@ int main(int argc, char **argv) {
   for (int r = 0; r < nrungs - 1; r++) { wi(f, ptc->swap_count[r]); wi(f, ptc->swap_accept_count[r]); }
   for (int r = 0; r < nrungs; r++) { wi(f, ptc->directions[r]); wi(f, ptc->ups[r]); wi(f, ptc->downs[r]); wi(f, ptc->instances[r]); }
   fclose(f);
+  if (I("ess", 0)) {
+    // the run loop's effective-sample report (ptmcmc.cc:645): report_effective_samples(-1, save_every*1000, save_every, esslimit)
+    cout.rdbuf(sink.rdbuf());
+    ptc->reporting = false;
+    pair<double, int> el = ptc->report_effective_samples(-1, I("ess_width", save_every * 1000), I("ess_every", save_every), D("esslimit", -1));
+    cout.rdbuf(old);
+    printf("ref_ess: ess=%.17g length=%d\n", el.first, el.second);
+  }
   long long total = 0;
   for (int r = 0; r < nrungs; r++) total += ptc->chains[r].Nhist;
   printf("ref_trace: model=%s d=%d rungs=%d steps=%d Ninit=%d total_Nhist=%lld cold_Nsize=%d\n",

@@ -22,6 +22,9 @@ struct FChain {
 };
 // Launch-local counters that are touched once per step live in shared memory, one word per thread and counter
 // ([counter][thread]: conflict-free), to keep the register-resident state within the one-wave budget.
+// largest CTA the production kernel is launched with (28 warps = one CTA per SM at 72 registers); smaller batches use smaller CTAs
+#define PTG_FSTEP_MAX_THREADS 896
+#define PTG_FC_STRIDE 7 // per-thread counter row in shared memory, odd stride: conflict-free
 enum { FC_NHIST = 0, FC_NTRIES, FC_NACCEPT, FC_LAST_TYPE, FC_UD, FC_SC, FC_COUNT };
 
 // proposal member parameters staged in shared memory
@@ -45,15 +48,15 @@ __device__ __forceinline__ void fappend(const PtgModel &m, const PtgState &s, FC
     h[D] = ch.lpost; h[D + 1] = ch.llike;
     if (m.record_full) {
       const long long rec = chain * m.hist_cap + ch.slot;
-      s.hist_acc[rec] = (s.naccept[chain] + cnt[FC_NACCEPT * 128]) / (double)(s.ntries[chain] + cnt[FC_NTRIES * 128]);
+      s.hist_acc[rec] = (s.naccept[chain] + cnt[FC_NACCEPT]) / (double)(s.ntries[chain] + cnt[FC_NTRIES]);
       s.hist_beta[rec] = ch.beta;
-      s.hist_type[rec] = cnt[FC_LAST_TYPE * 128];
+      s.hist_type[rec] = cnt[FC_LAST_TYPE];
     }
     if (ch.hfill < m.hist_cap) ch.hfill++;
     ch.slot = (ch.slot + 1 == m.hist_cap) ? 0 : ch.slot + 1;
   }
   ch.since_save = (ch.since_save + 1 == m.save_every) ? 0 : ch.since_save + 1;
-  cnt[FC_NHIST * 128]++;
+  cnt[FC_NHIST]++;
 }
 
 // element `index` of the eligible window (newest min(nsize,cap) samples): once the ring is full the oldest sits at `slot`
@@ -153,21 +156,18 @@ __device__ __noinline__ FVec<D> ftransform(const double *__restrict__ M, FVec<D>
   return t;
 }
 
-#ifndef PTG_FSTEP_MINB
-#define PTG_FSTEP_MINB 7
-#endif
 
 // packed ladder statistics: st_di = dir (low 2 bits, biased by 1) | inst << 2 ; st_ud = ups delta | downs delta << 16 ;
 // st_sc = swap_count delta | swap_accept delta << 16   (deltas per launch; the host keeps launches <= 32767 steps)
 #define PTG_FAST_MAX_STEPS 16384
 
 template <int D>
-__global__ void __launch_bounds__(128, PTG_FSTEP_MINB) ptg_fstep_kernel(const __grid_constant__ PtgModel m, PtgState s, long long step0, int n_steps, int W) {
+__global__ void __launch_bounds__(PTG_FSTEP_MAX_THREADS, 1) ptg_fstep_kernel(const __grid_constant__ PtgModel m, PtgState s, long long step0, int n_steps, int W) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int R = m.n_rungs, NP = m.n_props;
   double *sbins = reinterpret_cast<double *>(smem_raw);                   // [R][NP]
   FProp *sprop = reinterpret_cast<FProp *>(sbins + R * NP);               // [NP]
-  int *cnt = reinterpret_cast<int *>(sprop + NP) + threadIdx.x;            // [FC_COUNT][128], this thread's column
+  int *cnt = reinterpret_cast<int *>(sprop + NP) + threadIdx.x * PTG_FC_STRIDE; // [blockDim][PTG_FC_STRIDE], this thread's row
   for (int i = threadIdx.x; i < R * NP; i += blockDim.x) sbins[i] = m.bins[i];
   for (int i = threadIdx.x; i < NP; i += blockDim.x) {
     const PtgProp &p = m.props[i];
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(128, PTG_FSTEP_MINB) ptg_fstep_kernel(const __
   FChain<D> ch;
   int st_di = 1;
 #pragma unroll
-  for (int k = 0; k < FC_COUNT; k++) cnt[k * 128] = 0;
+  for (int k = 0; k < FC_COUNT; k++) cnt[k] = 0;
   if (active) {
 #pragma unroll
     for (int k = 0; k < D; k++) ch.x[k] = s.cur_x[(long long)k * m.n_chains + chain];
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(128, PTG_FSTEP_MINB) ptg_fstep_kernel(const __
     ch.slot = (int)(nsize % m.hist_cap);
     ch.hfill = (int)(nsize > m.hist_cap ? (long long)m.hist_cap : nsize);
     ch.since_save = (int)(s.nhist[chain] % m.save_every);
-    cnt[FC_LAST_TYPE * 128] = s.last_type[chain];
+    cnt[FC_LAST_TYPE] = s.last_type[chain];
     st_di = (s.directions[chain] + 1) | (s.instances[chain] << 2);
   } else {
 #pragma unroll
@@ -274,8 +274,8 @@ __global__ void __launch_bounds__(128, PTG_FSTEP_MINB) ptg_fstep_kernel(const __
           const bool is_lo = (rung == c), is_hi = (rung == c + 1), involved = is_lo || is_hi;
           if (is_lo && c > 0) { // ups / downs of the lower rung before the exchange (chain.cc:1440-1443)
             const int dir = (st_di & 3) - 1;
-            if (dir > 0) cnt[FC_UD * 128] += 1;
-            if (dir < 0) cnt[FC_UD * 128] += 1 << 16;
+            if (dir > 0) cnt[FC_UD] += 1;
+            if (dir < 0) cnt[FC_UD] += 1 << 16;
           }
           if (accept) {
             const int partner = is_lo ? c + 1 : (is_hi ? c : rung);
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(128, PTG_FSTEP_MINB) ptg_fstep_kernel(const __
             { const int v = __shfl_sync(gm, st_di, partner, W); st_di = v; }
             if (c == 0 && is_lo) st_di = (st_di & ~3) | 2;          // directions[0] = +1
             if (c + 1 == R - 1 && is_hi) st_di = (st_di & ~3) | 0;  // directions[R-1] = -1
-            if (is_lo) cnt[FC_SC * 128] += 1 << 16;
+            if (is_lo) cnt[FC_SC] += 1 << 16;
             if (m.evolve_rate > 0) {
               // pry_temps, one pried gap (chain.cc:1809-1846) + resetTemp (chain.cc:1088-1091), reference summation order
               const double rate = m.evolve_rate;
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(128, PTG_FSTEP_MINB) ptg_fstep_kernel(const __
               if (rung >= 1 && rung < R - 1) { ch.beta = mine; ch.lpost = ch.lprior + mine * ch.llike; }
             }
           }
-          if (is_lo) cnt[FC_SC * 128] += 1;
+          if (is_lo) cnt[FC_SC] += 1;
         }
       } else {
         // even/odd performance mode: all pairs (i,i+1), i = parity, parity+2, ... are disjoint -> one shuffle round
@@ -334,8 +334,8 @@ __global__ void __launch_bounds__(128, PTG_FSTEP_MINB) ptg_fstep_kernel(const __
             bool accept = true;
             if (lhr < 0) accept = (log(ptg_u52_to_unit(q[2], q[3])) < lhr);
             flags = 1 | (accept ? 2 : 0);
-            if (rung > 0) { const int dir = (st_di & 3) - 1; if (dir > 0) cnt[FC_UD * 128] += 1; if (dir < 0) cnt[FC_UD * 128] += 1 << 16; }
-            cnt[FC_SC * 128] += 1 + (accept ? (1 << 16) : 0);
+            if (rung > 0) { const int dir = (st_di & 3) - 1; if (dir > 0) cnt[FC_UD] += 1; if (dir < 0) cnt[FC_UD] += 1 << 16; }
+            cnt[FC_SC] += 1 + (accept ? (1 << 16) : 0);
           }
         }
         const int pflags = __shfl_sync(gm, flags, partner, W);
@@ -537,10 +537,10 @@ __global__ void __launch_bounds__(128, PTG_FSTEP_MINB) ptg_fstep_kernel(const __
     if (!valid) { accept = false; code |= PTG_TRACE_INVALID; }
     if (accept && lhr < 0) accept = (log(ptg_u52_to_unit(wB[2], wB[3])) < lhr);
     if (do_mh) {
-      cnt[FC_NTRIES * 128]++;
+      cnt[FC_NTRIES]++;
       if (accept) {
-        cnt[FC_NACCEPT * 128]++;
-        cnt[FC_LAST_TYPE * 128] = type;
+        cnt[FC_NACCEPT]++;
+        cnt[FC_LAST_TYPE] = type;
 #pragma unroll
         for (int i = 0; i < D; i++) ch.x[i] = newx[i];
         ch.llike = newlike; ch.lpost = newlpost; ch.lprior = newlprior;
@@ -559,12 +559,12 @@ __global__ void __launch_bounds__(128, PTG_FSTEP_MINB) ptg_fstep_kernel(const __
     for (int k = 0; k < D; k++) s.cur_x[(long long)k * m.n_chains + chain] = ch.x[k];
     s.lpost[chain] = ch.lpost; s.llike[chain] = ch.llike; s.lprior[chain] = ch.lprior; s.beta[chain] = ch.beta;
     // saves = appends k in [0, dnhist) with (since_save0 + k) % save_every == 0
-    const int dnhist = cnt[FC_NHIST * 128], se = m.save_every;
+    const int dnhist = cnt[FC_NHIST], se = m.save_every;
     const int dnsize = (since_save0 + dnhist + se - 1) / se - (since_save0 + se - 1) / se;
-    s.nhist[chain] += dnhist; s.nsize[chain] += dnsize; s.ntries[chain] += cnt[FC_NTRIES * 128]; s.naccept[chain] += cnt[FC_NACCEPT * 128];
-    s.last_type[chain] = cnt[FC_LAST_TYPE * 128];
+    s.nhist[chain] += dnhist; s.nsize[chain] += dnsize; s.ntries[chain] += cnt[FC_NTRIES]; s.naccept[chain] += cnt[FC_NACCEPT];
+    s.last_type[chain] = cnt[FC_LAST_TYPE];
     s.directions[chain] = (st_di & 3) - 1; s.instances[chain] = st_di >> 2;
-    const int st_ud = cnt[FC_UD * 128], st_sc = cnt[FC_SC * 128];
+    const int st_ud = cnt[FC_UD], st_sc = cnt[FC_SC];
     s.ups[chain] += st_ud & 0xffff; s.downs[chain] += st_ud >> 16;
     s.swap_count[chain] += st_sc & 0xffff; s.swap_accept[chain] += st_sc >> 16;
     if (err) atomicMax(s.err, err);

@@ -59,6 +59,22 @@ class Engine(K.CApi):
         self._call("get_act", self.h, C.c_int32(rung), C.c_int32(n_last), C.c_int32(max_lag), K._dp(out))
         return out
 
+    def report_effective_samples(self, ladder=0, rung=0, esslimit=-1, imax=-1):
+        """(ess, useful length) of one chain by the reference's own recipe, called the way the run loop calls it
+        (chain::report_effective_samples(-1, save_every*1000, save_every, esslimit), ptmcmc.cc:645; restated in
+        analysis.report_effective_samples and pinned to the reference build's outputs).  Host-side analysis of the history the
+        ring still holds: the whole run must be resident (hist_capacity >= n_init + steps / save_every)."""
+        from .analysis import report_effective_samples
+        c = self.get_counters()
+        i = ladder * self.cfg.n_rungs + rung
+        nsize, nhist = int(c["nsize"][i]), int(c["nhist"][i])
+        if nsize > self.cfg.hist_capacity:
+            raise RuntimeError("report_effective_samples: the ring has wrapped (%d records > capacity %d)" % (nsize, self.cfg.hist_capacity))
+        x = self.get_history(ladder, rung, 0, nsize, full=False)["x"]
+        se = self.cfg.save_every
+        return report_effective_samples(x, nhist, n_init=self.cfg.n_init, add_every=se,
+                                        width=se * 1000, every=se, esslimit=esslimit, imax=imax)
+
     def get_mean_loglike(self, n_last):
         out = np.empty(self.n_chains)
         self._call("get_mean_loglike", self.h, C.c_int32(n_last), K._dp(out))

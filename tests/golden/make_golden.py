@@ -9,6 +9,8 @@ and stores, per case, in ref_<case>.npz:
     * for every rung the final counters and the SHA-256 of its full history record block (bit-exact pin),
     * the swap statistics, and for eigen-rotated Gaussian proposals the eigen-decomposition the reference used.
 newran.txt holds raw draws of the reference's RNG layer (oracle/_ref/ref_rng) for the seeds the tests use.
+ref_ess.npz (`python tests/golden/make_golden.py ess`) holds, for a few longer runs, the cold chain's parameter history and the
+(ess, length) pair the reference's own chain::report_effective_samples returned for it (called as ptmcmc.cc:645 does).
 """
 import hashlib
 import os
@@ -55,5 +57,38 @@ def main():
             f.write("# seed %s\n%s" % (seed, out))
 
 
+ESS_CASES = [  # (parity case, steps, esslimit)
+    ("A_gauss2d_default", 12000, -1),
+    ("C1_sines_d3_R32", 12000, -1),
+    ("gauss3_de_save3", 40000, -1),
+    ("A_gauss2d_default", 30000, 1000),
+]
+
+
+def run_ref_ess(spec, steps, esslimit, td):
+    """-> (ref trace dict, ess, length) from oracle/_ref/ref_trace ... ess=1"""
+    import re
+    out = os.path.join(td, "ref.bin")
+    args = [os.path.join(REF_DIR, "ref_trace")] + spec.ref_args(td, steps, out) + ["ess=1", "esslimit=%d" % esslimit]
+    m = re.search(r"ref_ess: ess=(\S+) length=(\d+)", subprocess.check_output(args).decode())
+    return read_ref_trace(out), float(m.group(1)), int(m.group(2))
+
+
+def main_ess():
+    cases = {c[0]: c[1] for c in parity_cases()}
+    blob = {}
+    for i, (name, steps, esslimit) in enumerate(ESS_CASES):
+        with tempfile.TemporaryDirectory() as td:
+            ref, ess, length = run_ref_ess(cases[name], steps, esslimit, td)
+        cold = ref["rungs"][0]
+        blob["x%d" % i] = cold["x"]
+        blob["meta%d" % i] = np.array([cold["nhist"], ref["ninit"], ref["save_every"], esslimit, ess, length], dtype=np.float64)
+        print("golden ess:", name, steps, esslimit, "->", ess, length)
+    np.savez_compressed(os.path.join(HERE, "ref_ess.npz"), **blob)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "ess":
+        main_ess()
+    else:
+        main()

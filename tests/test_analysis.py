@@ -23,3 +23,33 @@ def test_integrated_act_of_ar1():
     assert abs(tau - (1 + phi) / (1 - phi)) / 19.0 < 0.1
     eps, taus = ess_per_sample(np.stack([x, x], axis=2))
     assert abs(eps - 1 / tau) < 1e-12 and len(taus) == 2
+
+
+def test_reference_ess_recipe_matches_golden():
+    """analysis.report_effective_samples restates chain::report_effective_samples (chain.cc:457-643); the fixtures are the
+    (ess, length) pairs the reference build itself returned for these cold-chain histories (tests/golden/make_golden.py ess)."""
+    import os
+    from ptmcmc_b200.analysis import report_effective_samples
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_ess.npz"))
+    n = len([k for k in g.files if k.startswith("x")])
+    assert n >= 4
+    for i in range(n):
+        nhist, ninit, se, esslimit, ess_ref, len_ref = g["meta%d" % i]
+        ess, length = report_effective_samples(g["x%d" % i], int(nhist), n_init=int(ninit), add_every=int(se), width=int(se) * 1000,
+                                               every=int(se), esslimit=esslimit)
+        assert length == int(len_ref)
+        assert abs(ess - ess_ref) <= 1e-10 * ess_ref, (i, ess, ess_ref)
+
+
+def test_reference_ess_recipe_on_ar1():
+    """AR(1) with coefficient a has autocorrelation time (1+a)/(1-a): the recipe's ESS/length lands on it."""
+    from ptmcmc_b200.analysis import report_effective_samples
+    rng = np.random.default_rng(5)
+    a, n = 0.9, 400000
+    e = rng.normal(size=n)
+    x = np.empty(n); x[0] = e[0]
+    for i in range(1, n):
+        x[i] = a * x[i - 1] + e[i]
+    ess, length = report_effective_samples(x, n, width=1000, every=1)
+    assert length > n // 2
+    assert abs(length / ess / ((1 + a) / (1 - a)) - 1) < 0.15

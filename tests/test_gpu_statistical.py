@@ -5,7 +5,7 @@ own RNG (the oracle, which reproduces the unmodified reference bit for bit, test
 import numpy as np
 import pytest
 from ptmcmc_b200 import _capi as K
-from ptmcmc_b200.analysis import knn_kl, ess_per_sample
+from ptmcmc_b200.analysis import knn_kl, ess_per_sample, report_effective_samples
 from tests.models import Spec
 
 pytestmark = pytest.mark.gpu
@@ -61,6 +61,14 @@ def test_posterior_kl_and_ess_match_reference(name, spec, oracle_cls, engine_cls
     eps_eng, tau_eng = ess_per_sample(eng)
     print("%s: ESS/sample reference %.4f (tau %s) engine %.4f (tau %s)" % (name, eps_ref, np.round(tau_ref, 1), eps_eng, np.round(tau_eng, 1)))
     assert abs(eps_eng / eps_ref - 1) < 0.10
+    # the same bar with the reference's own estimator (chain::report_effective_samples, restated in analysis.py and pinned to the
+    # reference build by tests/test_analysis.py), per ladder, averaged over the ladders
+    def recipe(c):
+        e = np.array([report_effective_samples(c[l], STEPS, width=1000, every=1) for l in range(0, L, 2)])
+        return float(np.mean(e[:, 0] / np.maximum(e[:, 1], 1)))
+    r_ref, r_eng = recipe(ref), recipe(eng)
+    print("%s: ESS/sample by the reference's recipe: reference %.4f engine %.4f" % (name, r_ref, r_eng))
+    assert abs(r_eng / r_ref - 1) < 0.10
     # first two moments as a plain cross-check
     assert np.allclose(p_eng.mean(axis=0), p_ref.mean(axis=0), atol=4 * p_ref.std(axis=0).max() / np.sqrt(len(p_ref) / 4))
 
