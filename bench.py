@@ -39,9 +39,11 @@ WORKLOADS = {
                      desc="sines.hh sin^4 surface d=3, 4096 ladders x 32 rungs, default proposal mix (80% DE / 20% 6-scale Gaussian), swap_rate 0.1"),
     # configs[1] / B: polynomial chi^2, d=5, N=1000, DE only
     "b_poly": dict(model="poly", dim=5, rungs=16, ladders=1024, pt_steps=20, hist=1024, f_de=1.0, f_sn=0.1,
+                   flops=dict(per_chain_step=1000 * 26.0, peak_key="fp64_dmul_dadd_tflops", what="1000 points x (Horner 2(d-1) + residual 3 + division 15)"),
                    desc="5-coefficient polynomial chi^2 over 1000 points, 1024 ladders x 16 rungs, DE proposals"),
     # C2: 3-sinusoid chi^2 over 1e4 samples, d=9
     "c2_sinusoid": dict(model="sinusoid", dim=9, rungs=32, ladders=4096, pt_steps=1, hist=512, f_de=0.8, f_sn=0.1,
+                        flops=dict(per_chain_step=1e4 * 89.0, peak_key="fp64_dmul_dadd_tflops", what="1e4 samples x (3 sin at 24 flop + 17), SURVEY.md 8(d) convention"),
                         desc="3-sinusoid chi^2 fit to 1e4 samples d=9, 4096 ladders x 32 rungs, default proposal mix"),
     # configs[3] / D: correlated Gaussian d=100, full covariance; "65536 chains x 24 rungs" read as 65 544 chains in total
     # (2731 ladders x 24 rungs; the 1.57 M-chain reading leaves < 100 history slots per chain in 180 GB, SURVEY.md 8d, and the
@@ -49,6 +51,7 @@ WORKLOADS = {
     # save_every = 8: the 1280-slot ring then spans 10 240 PT iterations, which removes the short-window bias at d = 100 without
     # 8x the memory ("D must run with a short ring and/or save_every >> 1")
     "d_fullcov": dict(model="fullcov", dim=100, rungs=24, ladders=2731, pt_steps=50, hist=1280, save_every=8, f_de=0.5, f_sn=0.1,
+                      flops=dict(per_chain_step=2 * 100 * 100 * 1.5, peak_key="fp64_dmma_tflops", what="quadratic form 2 d^2 + eigen-rotation 2 d^2 on the 50 % Gaussian proposals"),
                       desc="correlated Gaussian d=100 full covariance (DMMA batched quadratic form + proposal rotation), 2731 ladders x 24 rungs, "
                            "50% eigen-rotated Gaussian proposal (2.38^2/d C) + 50% DE"),
     # configs[0] / A as a throughput batch
@@ -366,10 +369,25 @@ def main():
         cold = np.stack([eng.get_history(l, 0, int(cnt["nsize"][l * R]) - nh, nh, full=False)["x"] for l in range(nl)])
         eps_host, taus = ess_per_sample(cold)
         pt_iter_per_s = args.steps * S / (ms_max * 1e-3)
+        # the reference's own estimator (chain::report_effective_samples as the run loop calls it, ptmcmc.cc:645; analysis.py restates
+        # it and tests pin it to the reference build) on the newest ring window of each sampled cold chain
+        from ptmcmc_b200.analysis import report_effective_samples
+        nr = min(w["hist"] - 8, 8000)
+        se = w["save_every"]
+        rec = []
+        for l in range(min(L, 32)):
+            xs = eng.get_history(l, 0, int(cnt["nsize"][l * R]) - nr, nr, full=False)["x"][:, :20]
+            e_l, len_l = report_effective_samples(xs, nr * se, n_init=0, add_every=se, width=se * 1000, every=se)
+            if len_l > 0:
+                rec.append(e_l / len_l)
+        eps_recipe = float(np.mean(rec)) if rec else None              # ESS per PT iteration
         ess = dict(value=eps_dev / w["save_every"] * pt_iter_per_s * L * world, unit="ESS/s", tau_pt_iterations=float(np.median(tau_dev.max(axis=1))) * w["save_every"],
                    window=nh, ladders=L, estimator="device (ptg_get_act): per cold chain N/tau, tau = Sokal-windowed integrated autocorrelation time, "
                    "min over parameters, mean over ladders", host_check=dict(value=eps_host / w["save_every"] * pt_iter_per_s * L * world,
-                   tau_pt_iterations=float(taus.max()) * w["save_every"], ladders_sampled=nl))
+                   tau_pt_iterations=float(taus.max()) * w["save_every"], ladders_sampled=nl),
+                   reference_recipe=dict(value=(eps_recipe * pt_iter_per_s * L * world) if eps_recipe else None, ess_per_pt_iteration=eps_recipe,
+                                         window_records=nr, ladders_sampled=len(rec),
+                                         estimator="chain::report_effective_samples(-1, 1000 save_every, save_every) (chain.cc:457-643) per cold chain"))
     except Exception as exc:  # analysis is not part of the timed path
         ess = dict(value=None, error=repr(exc))
 
@@ -392,10 +410,23 @@ def main():
                     algorithmic_bytes_per_chain_step=bpcs, chain_steps_per_launch=(n1 - n0) / args.steps, launch_ms=launch_s * 1e3, peak_source=peak_src,
                     note="latency/ALU-bound fp64+Philox kernel: HBM is the stated roofline, see DESIGN.md section 5")
 
+    # compute-side view for the workloads with a dense fp64 flop count: algorithmic flops against the FP64 peaks measured by
+    # `bench.py --peaks` on this pool (profiles/r01_fp64_peaks.json; MEASURED_PEAKS.json carries HBM and bf16 only)
+    roofline_fp64 = None
+    fl = w.get("flops")
+    ppath = os.path.join(ROOT, "profiles", "r01_fp64_peaks.json")
+    if fl and os.path.exists(ppath):
+        pk = float(json.load(open(ppath))[fl["peak_key"]])
+        ach = fl["per_chain_step"] * ((n1 - n0) / args.steps) / launch_s / 1e12
+        roofline_fp64 = dict(bound="fp64", achieved=ach, peak=pk, unit="TFLOP/s", frac=ach / pk, flops_per_chain_step=fl["per_chain_step"],
+                             counted=fl["what"], peak_source="measured: profiles/r01_fp64_peaks.json " + fl["peak_key"])
+
     out = dict(metric=metric, value=value, unit=unit, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_max / args.steps,
                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", config=config, clocks=clk,
                e2e=dict(value=e2e_val, unit=unit, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=e2e_steps),
                gpu_launches=args.steps, roofline=roofline, ess=ess)
+    if roofline_fp64:
+        out["roofline_fp64"] = roofline_fp64
     # ---- N > 1: the one collective of the ladder-sharded layout, the gather of cold-chain samples to rank 0 (off the hot path)
     if world > 1:
         from ptmcmc_b200.sharding import gather_cold_samples
