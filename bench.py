@@ -273,7 +273,7 @@ def main():
         eng.set_stream(stream.cuda_stream)
         with torch.cuda.stream(stream):
             eng.init_from_prior(); eng.synchronize()
-            drv = RungShardedLadders(eng, rank, world, 0xB2005EED, exchange_every=args.rung_sharded, device="cuda:%d" % local)
+            drv = RungShardedLadders(eng, rank, world, 0xB2005EED, exchange_every=args.rung_sharded, device="cuda:%d" % local, stream_ordered=True)
             for _ in range(args.warmup):
                 drv.run(S)
             eng.synchronize(); n0 = eng.get_total_steps()
@@ -295,7 +295,7 @@ def main():
         if rank == 0:
             print(json.dumps(dict(metric=metric, value=val, unit=unit, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_step,
                                   higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", config=config,
-                                  exchange=dict(ms=ex_ms, bytes_per_rank=int(2 * L * (d + 3) * 8), collective="2 x all_gather_into_tensor (NCCL)"),
+                                  exchange=dict(ms=ex_ms, bytes_per_rank=int((2 if 0 < rank < world - 1 else 1) * L * (d + 3) * 8), collective="neighbour send/recv pairs (NCCL batch_isend_irecv), stream-ordered with the pack / swap kernels"),
                                   gpu_launches=args.steps * ((S + args.rung_sharded - 1) // args.rung_sharded) * 5)))
         eng.close()
         if world > 1:

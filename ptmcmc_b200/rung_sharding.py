@@ -5,8 +5,8 @@ world-1 rung boundaries cross NVLink:
 
     rank g owns rungs [g*R, (g+1)*R) of EVERY ladder of a (world*R)-rung geometric ladder (ptg_set_betas);
     swaps inside a block run in the step kernels (reference schedule over the local rungs);
-    every `exchange_every` PT iterations the ranks exchange their edge rungs -- (x, llike, lprior, beta) per ladder, one NCCL
-    all_gather of [n_ladders, dim+3] doubles per edge -- and both sides of a boundary evaluate the same swap trial
+    every `exchange_every` PT iterations neighbouring ranks exchange their edge rungs -- (x, llike, lprior, beta) per ladder,
+    [n_ladders, dim+3] doubles each way over NCCL send/recv -- and both sides of a boundary evaluate the same swap trial
     (ptg_boundary_swap: acceptance draw from the ladder's Philox stream under the shared key), so decisions never travel.
 
 The ladder-sharded layout (sharding.py) needs no exchange step and is the default; this one exists for ladders too long for
@@ -38,43 +38,45 @@ def rank_betas(n_ladders, rungs_per_rank, rank, world, Tmax):
 class RungShardedLadders:
     """Drives one rank's engine (anything with the C-ABI methods step / boundary_pack / boundary_swap) in the rung-sharded layout."""
 
-    def __init__(self, api, rank, world, shared_seed, exchange_every=10, device="cpu"):
+    def __init__(self, api, rank, world, shared_seed, exchange_every=10, device="cpu", stream_ordered=False):
+        """stream_ordered: the engine launches on torch's CURRENT CUDA stream (Engine.set_stream(torch stream) inside
+        `with torch.cuda.stream(...)`), so packs, the NCCL all_gather and the swap kernels are ordered on the device and the host
+        never waits inside the loop.  Otherwise the host synchronises around the collective."""
         self.api, self.rank, self.world, self.shared_seed, self.exchange_every = api, rank, world, int(shared_seed), exchange_every
         self.device = torch.device(device)
+        self.stream_ordered = bool(stream_ordered) and self.device.type == "cuda"
         L, d = api.cfg.n_ladders, api.cfg.dim
         self.R = api.cfg.n_rungs
-        self.bottom = torch.zeros((L, d + 3), dtype=torch.float64, device=self.device)
-        self.top = torch.zeros((L, d + 3), dtype=torch.float64, device=self.device)
-        self.all_bottom = torch.zeros((world, L, d + 3), dtype=torch.float64, device=self.device)
-        self.all_top = torch.zeros((world, L, d + 3), dtype=torch.float64, device=self.device)
+        # edges[0] = my coldest rung (bottom), edges[1] = my hottest rung (top); nbr[0] = the hotter neighbour's bottom, nbr[1] = the
+        # colder neighbour's top.  Only neighbours talk: two send/recv pairs per rank per exchange, whatever the world size.
+        self.edges = torch.zeros((2, L, d + 3), dtype=torch.float64, device=self.device)
+        self.nbr = torch.zeros((2, L, d + 3), dtype=torch.float64, device=self.device)
         self.n_exchanges = 0
 
-    def _gather(self, out, inp):
-        if self.world == 1:
-            out[0].copy_(inp)
-        elif dist.get_backend() == "nccl":
-            dist.all_gather_into_tensor(out, inp)
-        else:
-            parts = [torch.empty_like(inp) for _ in range(self.world)]
-            dist.all_gather(parts, inp)
-            for r in range(self.world):
-                out[r].copy_(parts[r])
+    def _neighbour_exchange(self):
+        g, ops = self.rank, []
+        if g + 1 < self.world:
+            ops += [dist.P2POp(dist.isend, self.edges[1], g + 1), dist.P2POp(dist.irecv, self.nbr[0], g + 1)]
+        if g > 0:
+            ops += [dist.P2POp(dist.isend, self.edges[0], g - 1), dist.P2POp(dist.irecv, self.nbr[1], g - 1)]
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()  # NCCL: orders the current stream after the transfer, the host does not block
 
     def exchange(self):
         """one cross-boundary swap trial per ladder and per rung boundary"""
         api, R, g = self.api, self.R, self.rank
-        api.boundary_pack(0, self.bottom.data_ptr())
-        api.boundary_pack(R - 1, self.top.data_ptr())
-        if self.device.type == "cuda":
+        api.boundary_pack(0, self.edges[0].data_ptr())
+        api.boundary_pack(R - 1, self.edges[1].data_ptr())
+        if self.device.type == "cuda" and not self.stream_ordered:
             api.synchronize()  # packs were written on the engine's stream
-        self._gather(self.all_bottom, self.bottom)
-        self._gather(self.all_top, self.top)
-        if self.device.type == "cuda":
+        self._neighbour_exchange()
+        if self.device.type == "cuda" and not self.stream_ordered:
             torch.cuda.current_stream().synchronize()
         if g + 1 < self.world:   # my hottest rung with the neighbour's coldest: I hold the lower index of the pair
-            api.boundary_swap(R - 1, self.all_bottom[g + 1].data_ptr(), True, self.shared_seed, g, self.n_exchanges)
+            api.boundary_swap(R - 1, self.nbr[0].data_ptr(), True, self.shared_seed, g, self.n_exchanges)
         if g > 0:
-            api.boundary_swap(0, self.all_top[g - 1].data_ptr(), False, self.shared_seed, g - 1, self.n_exchanges)
+            api.boundary_swap(0, self.nbr[1].data_ptr(), False, self.shared_seed, g - 1, self.n_exchanges)
         self.n_exchanges += 1
 
     def run(self, n_steps):
