@@ -198,6 +198,7 @@ def main():
     ap.add_argument("--save-every", type=int, default=0, help="add_every_N: store every N-th sample (default: per workload)")
     ap.add_argument("--swap-mode", default="reference", choices=["reference", "even_odd"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fused-exchange", action="store_true", help="with --rung-sharded: exchange fused into the step kernel over NVLink peer memory (no collective)")
     ap.add_argument("--rung-sharded", type=int, default=0, metavar="K",
                     help="optional layout: ONE (n_gpus x rungs)-rung ladder family sharded by rung blocks, cross-GPU boundary swaps over NCCL every K PT iterations")
     ap.add_argument("--peaks", action="store_true", help="measure the FP64 peaks (DFMA, DMUL+DADD, DMMA) of cuda:0, print them as JSON and exit")
@@ -264,7 +265,7 @@ def main():
     L, R, d, S = w["ladders"], w["rungs"], w["dim"], w["pt_steps"]
     if args.rung_sharded:
         # ---- optional rung-sharded layout (ptmcmc_b200/rung_sharding.py): the same ladders on every rank, a different rung block
-        from ptmcmc_b200.rung_sharding import RungShardedLadders, rank_betas
+        from ptmcmc_b200.rung_sharding import RungShardedLadders, FusedRungShardedLadders, rank_betas
         eng = Engine(spec.config(n_ladders=L, rng_mode=K.RNG_PHILOX, record_level=K.RECORD_BASIC, hist_capacity=w["hist"], save_every=w["save_every"], device=local,
                                  seed=0xB2000003 + 977 * rank))
         spec.setup(eng)
@@ -273,7 +274,10 @@ def main():
         eng.set_stream(stream.cuda_stream)
         with torch.cuda.stream(stream):
             eng.init_from_prior(); eng.synchronize()
-            drv = RungShardedLadders(eng, rank, world, 0xB2005EED, exchange_every=args.rung_sharded, device="cuda:%d" % local, stream_ordered=True)
+            if args.fused_exchange:
+                drv = FusedRungShardedLadders(eng, rank, world, 0xB2005EED, exchange_every=args.rung_sharded)
+            else:
+                drv = RungShardedLadders(eng, rank, world, 0xB2005EED, exchange_every=args.rung_sharded, device="cuda:%d" % local, stream_ordered=True)
             for _ in range(args.warmup):
                 drv.run(S)
             eng.synchronize(); n0 = eng.get_total_steps()
@@ -281,22 +285,33 @@ def main():
             t0 = time.perf_counter()
             for _ in range(args.steps):
                 drv.run(S)
+            drv.finish()
             eng.synchronize(); torch.cuda.synchronize(); barrier()
             dt = time.perf_counter() - t0
             n1 = eng.get_total_steps()
-            # cost of the exchange step alone
+            # the same launches without any exchange (what a cycle costs on its own), and the exchange step alone
             torch.cuda.synchronize(); t1 = time.perf_counter()
-            for _ in range(20):
-                drv.exchange()
-            eng.synchronize(); torch.cuda.synchronize(); ex_ms = 1e3 * (time.perf_counter() - t1) / 20
+            for _ in range(100):
+                eng.step(args.rung_sharded)
+            eng.synchronize(); torch.cuda.synchronize(); bare_ms = 1e3 * (time.perf_counter() - t1) / 100
+            ex_ms = None
+            if not args.fused_exchange:
+                torch.cuda.synchronize(); t1 = time.perf_counter()
+                for _ in range(20):
+                    drv.exchange()
+                eng.synchronize(); torch.cuda.synchronize(); ex_ms = 1e3 * (time.perf_counter() - t1) / 20
         val = sum_over_ranks(n1 - n0) / max_over_ranks(dt)
-        config["parallelism"] = "rung-sharded: %d ladders x (%d GPUs x %d rungs), boundary swaps over NCCL every %d PT iterations" % (L, world, R, args.rung_sharded)
+        config["parallelism"] = "rung-sharded: %d ladders x (%d GPUs x %d rungs), boundary swaps %s every %d PT iterations" % (
+            L, world, R, "fused into the step kernel over NVLink peer memory" if args.fused_exchange else "over NCCL", args.rung_sharded)
         ms_step = 1e3 * max_over_ranks(dt) / args.steps
         if rank == 0:
             print(json.dumps(dict(metric=metric, value=val, unit=unit, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_step,
                                   higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", config=config,
-                                  exchange=dict(ms=ex_ms, bytes_per_rank=int((2 if 0 < rank < world - 1 else 1) * L * (d + 3) * 8), collective="neighbour send/recv pairs (NCCL batch_isend_irecv), stream-ordered with the pack / swap kernels"),
-                                  gpu_launches=args.steps * ((S + args.rung_sharded - 1) // args.rung_sharded) * 5)))
+                                  exchange=dict(ms=ex_ms, ms_per_cycle=ms_step / ((S + args.rung_sharded - 1) // args.rung_sharded), ms_per_cycle_without_exchange=bare_ms,
+                                                bytes_per_rank=int((2 if 0 < rank < world - 1 else 1) * L * (d + 3) * 8),
+                                                collective="none: peer-memory loads in the step kernel's prologue, per-ladder flags" if args.fused_exchange else
+                                                "neighbour send/recv pairs (NCCL batch_isend_irecv), stream-ordered with the pack / swap kernels"),
+                                  gpu_launches=args.steps * ((S + args.rung_sharded - 1) // args.rung_sharded) * (1 if args.fused_exchange else 5))))
         eng.close()
         if world > 1:
             dist.destroy_process_group()

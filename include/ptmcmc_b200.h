@@ -240,6 +240,23 @@ int ptg_boundary_pack(ptg_handle *h, int32_t rung, void *out_dev);
 int ptg_boundary_swap(ptg_handle *h, int32_t my_rung, const void *neighbour_pack_dev, int32_t i_am_lower, uint64_t shared_seed,
                       int64_t boundary_id, int64_t exchange_index);
 
+/* The same exchange FUSED into the production step kernel over peer memory (NVLink loads, no collective and no extra launch):
+ * every engine owns an exchange area in its own HBM; the epilogue of a ptg_step_exchange launch publishes the block's two edge
+ * rungs there and raises a per-ladder flag, and the prologue of the NEXT launch waits (per ladder, bounded) for the neighbour's
+ * flag, reads the neighbour's record through a peer pointer and runs the trial of ptg_boundary_swap with the same Philox address
+ * (exchange_index = number of publishes so far, boundary ids as given), so fused and unfused runs produce identical chains.
+ *   ptg_xchg_export   allocates the area; returns its CUDA IPC handle (64 bytes, for other processes) and/or its device pointer
+ *                     (for engines of the same process);
+ *   ptg_xchg_connect  takes the colder / hotter neighbour's handle or pointer (NULL at the ends of the ladder) and the two
+ *                     boundary ids (= rank of the pair's lower block);
+ *   ptg_step_exchange n_steps (<= 16384, may be 0) PT iterations in one launch; apply_pending runs the pending boundary trials
+ *                     first, publish publishes the edges at the end.
+ * Engines that wait on each other must run on DIFFERENT GPUs (or be launched strictly one after the other): the prologue spins. */
+int ptg_xchg_export(ptg_handle *h, void *ipc_handle_64_bytes, void **local_ptr);
+int ptg_xchg_connect(ptg_handle *h, const void *colder, const void *hotter, int32_t handles_are_ipc, uint64_t shared_seed,
+                     int64_t colder_boundary_id, int64_t hotter_boundary_id);
+int ptg_step_exchange(ptg_handle *h, int64_t n_steps, int32_t apply_pending, int32_t publish);
+
 /* FP64 peak microbenchmarks on `device` (the FP64 roofline denominators): out[0] = DFMA TFLOP/s,
  * out[1] = DMUL+DADD pairs (the engine's unfused arithmetic) TFLOP/s, out[2] = DMMA (mma.sync.m8n8k4.f64) TFLOP/s, out[3] = SM count */
 int ptg_measure_fp64_peaks(int32_t device, double *out);

@@ -205,5 +205,26 @@ class CApi:
         self._call("boundary_swap", self.h, C.c_int32(my_rung), C.c_void_p(neighbour_pack_ptr), C.c_int32(1 if i_am_lower else 0),
                    C.c_uint64(shared_seed), C.c_int64(boundary_id), C.c_int64(exchange_index))
 
+    # ---- the same exchange fused into the production step kernel over peer memory (engine only)
+    def xchg_export(self):
+        """-> (64-byte CUDA IPC handle, device pointer) of this engine's exchange area"""
+        hd = C.create_string_buffer(64); ptr = C.c_void_p()
+        self._call("xchg_export", self.h, hd, C.byref(ptr))
+        return hd.raw, ptr.value
+
+    def xchg_connect(self, colder, hotter, shared_seed, colder_boundary_id, hotter_boundary_id):
+        """colder / hotter: the neighbour's IPC handle (bytes, another process), its device pointer (int, same process) or None"""
+        ipc = isinstance(colder, (bytes, bytearray)) or isinstance(hotter, (bytes, bytearray))
+        def arg(v):
+            if v is None:
+                return None
+            return C.c_char_p(bytes(v)) if ipc else C.c_void_p(v)
+        self._keep_xchg = (arg(colder), arg(hotter))
+        self._call("xchg_connect", self.h, self._keep_xchg[0], self._keep_xchg[1], C.c_int32(1 if ipc else 0), C.c_uint64(shared_seed),
+                   C.c_int64(colder_boundary_id), C.c_int64(hotter_boundary_id))
+
+    def step_exchange(self, n_steps, apply_pending, publish):
+        self._call("step_exchange", self.h, C.c_int64(n_steps), C.c_int32(1 if apply_pending else 0), C.c_int32(1 if publish else 0))
+
     def get_total_steps(self):
         t = C.c_int64(); self._call("get_total_steps", self.h, C.byref(t)); return t.value

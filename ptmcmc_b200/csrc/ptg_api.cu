@@ -53,6 +53,9 @@ struct ptg_handle {
   ptg_batch_loglike_fn cb_fn; void *cb_user;   // host-callback likelihood
   int32_t *d_attempt, *d_nopen;
   std::vector<double> cb_x, cb_like, cb_xc, cb_lc; std::vector<int32_t> cb_flags; std::vector<int64_t> cb_idx;
+  // rung-sharded ladders with the exchange fused into the step kernel (ptg_xchg_*)
+  void *d_xchg; size_t xchg_bytes; void *peer_lo, *peer_hi; bool peer_lo_ipc, peer_hi_ipc;
+  PtgXchg xchg; const PtgXchg *xchg_launch; // xchg_launch: parameters of the launch in flight through ptg_step (null = plain step)
 };
 
 template <typename T>
@@ -219,6 +222,8 @@ extern "C" int ptg_destroy(ptg_handle *h) {
   if (!h) return 0;
   cudaSetDevice(h->cfg.device);
   cudaStreamSynchronize(h->stream);
+  if (h->peer_lo && h->peer_lo_ipc) cudaIpcCloseMemHandle(h->peer_lo);
+  if (h->peer_hi && h->peer_hi_ipc) cudaIpcCloseMemHandle(h->peer_hi);
   for (void *p : h->allocs) cudaFree(p);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -637,6 +642,7 @@ static int warp_kernel_width(const ptg_handle *h) {
 }
 // which step kernel runs: PTG_KERNEL_FAST (Philox draws, <= 32 rungs), PTG_KERNEL_WARP (tape replay, <= 32 rungs),
 // PTG_KERNEL_SHARED otherwise; ptg_select_kernel can pin WARP or SHARED where they apply
+static const PtgXchg xchg_off = {};
 static int pick_kernel(const ptg_handle *h, int *W) {
   *W = warp_kernel_width(h);
   int k = PTG_KERNEL_SHARED;
@@ -699,7 +705,7 @@ extern "C" int ptg_step(ptg_handle *h, int64_t n_steps) {
     }
     else switch (m.dim) {
 #define X(D) case D:                                                                                                       \
-      if (kern == PTG_KERNEL_FAST) e = ptg_launch_fstep_d##D(m, h->s, h->istep, chunk, W, h->stream);                       \
+      if (kern == PTG_KERNEL_FAST) e = ptg_launch_fstep_d##D(m, h->s, h->istep, chunk, W, h->xchg_launch ? *h->xchg_launch : xchg_off, h->stream); \
       else if (kern == PTG_KERNEL_WARP) e = ptg_launch_wstep_d##D(h->cfg.rng_mode, m, h->s, h->istep, chunk, W, h->stream); \
       else e = ptg_launch_step_d##D(h->cfg.rng_mode, m, h->s, h->istep, chunk, lpb, smem, h->stream);                       \
       break;
@@ -1141,6 +1147,97 @@ extern "C" int ptg_boundary_swap(ptg_handle *h, int32_t my_rung, const void *nei
   ptg_boundary_swap_kernel<<<grid_for(h->m.n_ladders), 256, 0, h->stream>>>(h->m, h->s, my_rung, (const double *)neighbour_pack_dev, i_am_lower ? 1 : 0,
                                                                             shared_seed, (long long)boundary_id, (long long)exchange_index);
   CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// ---- exchange fused into the production step kernel over peer memory (NVLink): see PtgXchg in ptg_types.h
+static size_t xchg_edge_doubles(const ptg_handle *h) { return (size_t)4 * h->m.n_ladders * (h->m.dim + 3); }
+static int xchg_alloc(ptg_handle *h) {
+  if (h->d_xchg) return 0;
+  h->xchg_bytes = xchg_edge_doubles(h) * sizeof(double) + (size_t)2 * h->m.n_ladders * sizeof(int);
+  // a dedicated cudaMalloc (IPC handles cover whole allocations); freed in ptg_destroy with every other allocation
+  CUDA_TRY(cudaMalloc(&h->d_xchg, h->xchg_bytes));
+  h->allocs.push_back(h->d_xchg);
+  CUDA_TRY(cudaMemsetAsync(h->d_xchg, 0, h->xchg_bytes, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+static int xchg_check(ptg_handle *h) {
+  if (!h) return fail(PTG_EINVAL, "null handle");
+  if (!h->inited) return fail(PTG_EINVAL, "not initialised");
+  int W = 0;
+  if (h->wide || h->m.like_kind == PTG_LIKE_HOST_CALLBACK || pick_kernel(h, &W) != PTG_KERNEL_FAST)
+    return fail(PTG_EINVAL, "the fused exchange runs in the production kernel only (Philox draws, n_rungs <= 32, dim <= 16)");
+  return 0;
+}
+extern "C" int ptg_xchg_export(ptg_handle *h, void *ipc_handle_64_bytes, void **local_ptr) {
+  int rc = xchg_check(h); if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  rc = xchg_alloc(h); if (rc) return rc;
+  if (ipc_handle_64_bytes) {
+    cudaIpcMemHandle_t hd;
+    CUDA_TRY(cudaIpcGetMemHandle(&hd, h->d_xchg));
+    static_assert(sizeof(hd) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(ipc_handle_64_bytes, &hd, sizeof(hd));
+  }
+  if (local_ptr) *local_ptr = h->d_xchg;
+  return 0;
+}
+static int xchg_open(ptg_handle *h, const void *handle_or_ptr, int is_ipc, void **out, bool *out_ipc) {
+  *out = nullptr; *out_ipc = false;
+  if (!handle_or_ptr) return 0;
+  if (!is_ipc) { *out = const_cast<void *>(handle_or_ptr); return 0; }
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, handle_or_ptr, sizeof(hd));
+  CUDA_TRY(cudaIpcOpenMemHandle(out, hd, cudaIpcMemLazyEnablePeerAccess));
+  *out_ipc = true;
+  return 0;
+}
+extern "C" int ptg_xchg_connect(ptg_handle *h, const void *colder, const void *hotter, int32_t handles_are_ipc, uint64_t shared_seed,
+                                int64_t colder_boundary_id, int64_t hotter_boundary_id) {
+  int rc = xchg_check(h); if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  rc = xchg_alloc(h); if (rc) return rc;
+  rc = xchg_open(h, colder, handles_are_ipc, &h->peer_lo, &h->peer_lo_ipc); if (rc) return rc;
+  rc = xchg_open(h, hotter, handles_are_ipc, &h->peer_hi, &h->peer_hi_ipc); if (rc) return rc;
+  const size_t ed = xchg_edge_doubles(h);
+  PtgXchg &x = h->xchg;
+  x = PtgXchg{};
+  x.on = 1; x.has_lo = h->peer_lo != nullptr; x.has_hi = h->peer_hi != nullptr; x.index = 0;
+  x.my_edges = (double *)h->d_xchg; x.my_flags = (int *)((double *)h->d_xchg + ed);
+  x.lo_edges = (const double *)h->peer_lo; x.lo_flags = h->peer_lo ? (const int *)((const double *)h->peer_lo + ed) : nullptr;
+  x.hi_edges = (const double *)h->peer_hi; x.hi_flags = h->peer_hi ? (const int *)((const double *)h->peer_hi + ed) : nullptr;
+  x.shared_seed = shared_seed; x.lo_boundary = colder_boundary_id; x.hi_boundary = hotter_boundary_id;
+  return 0;
+}
+// n_steps PT iterations in ONE launch; apply_pending: first run the boundary swap trials against what the neighbours published at
+// the end of their previous exchange launch; publish: publish this block's edge rungs at the end (exchange index = launches so far)
+extern "C" int ptg_step_exchange(ptg_handle *h, int64_t n_steps, int32_t apply_pending, int32_t publish) {
+  int rc = xchg_check(h); if (rc) return rc;
+  if (!h->xchg.on) return fail(PTG_EINVAL, "ptg_xchg_connect first");
+  if (n_steps < 0 || n_steps > 16384) return fail(PTG_EINVAL, "n_steps must be within one launch (0..16384)");
+  if (apply_pending && h->xchg.index == 0) return fail(PTG_EINVAL, "nothing has been published yet");
+  PtgXchg x = h->xchg;
+  x.swap_in = apply_pending ? 1 : 0; x.publish_out = publish ? 1 : 0;
+  h->xchg_launch = &x;
+  if (n_steps == 0) { // prologue / epilogue only
+    int W = 0; pick_kernel(h, &W);
+    cudaError_t e = cudaErrorInvalidValue;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    switch (h->m.dim) {
+#define X(D) case D: e = ptg_launch_fstep_d##D(h->m, h->s, h->istep, 0, W, x, h->stream); break;
+      PTG_DIM_LIST(X)
+#undef X
+    }
+    h->xchg_launch = nullptr;
+    CUDA_TRY(e);
+    h->launches++;
+  } else {
+    rc = ptg_step(h, n_steps);
+    h->xchg_launch = nullptr;
+    if (rc) return rc;
+  }
+  if (publish) h->xchg.index++;
   return 0;
 }
 

@@ -39,7 +39,7 @@ static inline int ptg_fstep_threads(long long warps) {
   return 128;
 }
 template <int D>
-static cudaError_t launch_fstep_t(const PtgModel &m, const PtgState &s, long long step0, int n_steps, int W, cudaStream_t st) {
+static cudaError_t launch_fstep_t(const PtgModel &m, const PtgState &s, long long step0, int n_steps, int W, const PtgXchg &xc, cudaStream_t st) {
   const long long warps = (m.n_ladders + (32 / W) - 1) / (32 / W);
   // CTA size: the largest of 28 / 14 / 4 warps that still puts a CTA on (nearly) every SM.  The kernel is compiled for 72
   // registers (launch bound 896 x 1), so 896 resident threads per SM in every geometry; one 28-warp CTA per SM measured
@@ -48,7 +48,8 @@ static cudaError_t launch_fstep_t(const PtgModel &m, const PtgState &s, long lon
   const int wpb = threads / 32;
   const int blocks = (int)((warps + wpb - 1) / wpb);
   const size_t smem = (size_t)m.n_rungs * m.n_props * sizeof(double) + (size_t)m.n_props * sizeof(FProp) + (size_t)PTG_FC_STRIDE * threads * sizeof(int);
-  ptg_fstep_kernel<D><<<blocks, threads, smem, st>>>(m, s, step0, n_steps, W);
+  if (xc.on) ptg_fstep_kernel<D, true><<<blocks, threads, smem, st>>>(m, s, step0, n_steps, W, xc);
+  else ptg_fstep_kernel<D, false><<<blocks, threads, smem, st>>>(m, s, step0, n_steps, W, xc);
   return cudaGetLastError();
 }
 template <int D, int MODE>
@@ -78,8 +79,8 @@ static cudaError_t launch_init_t(const PtgModel &m, const PtgState &s, const dou
     return mode == PTG_RNG_TAPE ? launch_wstep_t<D, PTG_RNG_TAPE>(m, s, step0, n_steps, W, st)                               \
                                 : launch_wstep_t<D, PTG_RNG_PHILOX>(m, s, step0, n_steps, W, st);                            \
   }                                                                                                                          \
-  cudaError_t ptg_launch_fstep_d##D(const PtgModel &m, const PtgState &s, long long step0, int n_steps, int W, cudaStream_t st) { \
-    return launch_fstep_t<D>(m, s, step0, n_steps, W, st);                                                                   \
+  cudaError_t ptg_launch_fstep_d##D(const PtgModel &m, const PtgState &s, long long step0, int n_steps, int W, const PtgXchg &xc, cudaStream_t st) { \
+    return launch_fstep_t<D>(m, s, step0, n_steps, W, xc, st);                                                                   \
   }                                                                                                                          \
   cudaError_t ptg_launch_init_d##D(int mode, const PtgModel &m, const PtgState &s, const double *init_x, cudaStream_t st) {  \
     return mode == PTG_RNG_TAPE ? launch_init_t<D, PTG_RNG_TAPE>(m, s, init_x, st)                                           \

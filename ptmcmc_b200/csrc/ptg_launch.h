@@ -21,7 +21,7 @@ static inline size_t ptg_ladder_shared_bytes(int D, int R) {
   /* host-callback likelihood mode: what = 0 propose (shared-memory kernel, phase 1), 1 finish, 2 init draw, 3 init accept */                 \
   cudaError_t ptg_launch_cb_d##D(int what, const PtgModel &m, const PtgState &s, long long step, int lpb, size_t smem, int k, int32_t *attempt,   \
                                  int32_t *n_open, cudaStream_t st);                                                          \
-  cudaError_t ptg_launch_fstep_d##D(const PtgModel &m, const PtgState &s, long long step0, int n_steps, int W, cudaStream_t st); \
+  cudaError_t ptg_launch_fstep_d##D(const PtgModel &m, const PtgState &s, long long step0, int n_steps, int W, const PtgXchg &xc, cudaStream_t st); \
   cudaError_t ptg_launch_init_d##D(int mode, const PtgModel &m, const PtgState &s, const double *init_x, cudaStream_t st);       \
   cudaError_t ptg_launch_eval_d##D(const PtgModel &m, const double *x, long long n, double *ll, double *lp, cudaStream_t st);
 PTG_DIM_LIST(PTG_DECLARE)

@@ -80,4 +80,19 @@ struct PtgState {
   uint32_t *pend_w;                     // [n_chains][2] acceptance-draw words
   int32_t *err;       // device error flag (PTG_ETAPE, PTG_ESTUCK)
 };
+// Rung-sharded ladders, exchange fused into the production step kernel over NVLink peer memory (ptg_fast.cuh).
+// Every rank owns one exchange area:  edges [2 parity][2 edge: 0 = coldest rung, 1 = hottest rung][n_ladders][dim + 3] doubles
+// (x, llike, lprior, beta) followed by flags [2 edge][n_ladders] int32 = number of publishes completed for that ladder's edge.
+// The epilogue of launch p publishes into parity p & 1 and raises the flags to p + 1; the prologue of the NEXT launch waits for the
+// neighbour's flag to reach p + 1, reads the neighbour's record through its peer pointer and runs the boundary swap trial.
+struct PtgXchg {
+  int on, swap_in, publish_out, has_lo, has_hi;
+  long long index;                   // publish index of this launch's epilogue; its prologue consumes index - 1
+  double *my_edges; int *my_flags;
+  const double *lo_edges; const int *lo_flags; // colder neighbour (its hottest rung pairs with my coldest)
+  const double *hi_edges; const int *hi_flags; // hotter neighbour (its coldest rung pairs with my hottest)
+  unsigned long long shared_seed;
+  long long lo_boundary, hi_boundary; // boundary ids for the Philox address (= rank of the pair's lower block)
+};
+
 #endif

@@ -87,3 +87,46 @@ class RungShardedLadders:
             self.api.step(k)
             self.exchange()
             done += k
+
+    def finish(self):
+        pass
+
+
+class FusedRungShardedLadders:
+    """The same layout and the same chains (same Philox addresses, so bit-identical states) with the exchange step fused into the
+    production step kernel over NVLink peer memory (ptg_xchg_* / ptg_step_exchange): the epilogue of each launch publishes the edge
+    rungs in this rank's own HBM, the prologue of the next launch reads the neighbours' records through CUDA-IPC peer pointers once
+    their per-ladder flags are up.  No collective, no extra launch and no host synchronisation inside the loop; one rank per GPU."""
+
+    def __init__(self, api, rank, world, shared_seed, exchange_every=10, peers=None):
+        """peers: {rank: device pointer} for engines of the SAME process (tests); otherwise handles travel over torch.distributed"""
+        self.api, self.rank, self.world, self.exchange_every = api, rank, world, exchange_every
+        handle, ptr = api.xchg_export()
+        if peers is None:
+            handles = [None] * world
+            if world > 1:
+                dist.all_gather_object(handles, handle)
+            lo = handles[rank - 1] if rank > 0 else None
+            hi = handles[rank + 1] if rank + 1 < world else None
+        else:
+            lo = peers.get(rank - 1) if rank > 0 else None
+            hi = peers.get(rank + 1) if rank + 1 < world else None
+        api.xchg_connect(lo, hi, int(shared_seed), rank - 1, rank)
+        self.pending = False
+        self.n_exchanges = 0
+
+    def run(self, n_steps):
+        """n_steps PT iterations, edges published after every `exchange_every`; each launch first applies the exchange that the
+        previous launch left pending (finish() applies the last one)"""
+        done = 0
+        while done < n_steps:
+            k = min(self.exchange_every, n_steps - done)
+            self.api.step_exchange(k, self.pending, True)
+            self.pending = True
+            self.n_exchanges += 1
+            done += k
+
+    def finish(self):
+        if self.pending:
+            self.api.step_exchange(0, True, False)
+            self.pending = False

@@ -110,3 +110,67 @@ def test_boundary_exchange_engine_matches_oracle(engine_cls):
         ne, no = eng[r].get_counters(), ora[r].get_counters()
         assert (ne["nhist"] == no["nhist"]).all() and (ne["nsize"] == no["nsize"]).all() and (ne["naccept"] == no["naccept"]).all()
     assert eng[0].get_total_steps() == ora[0].get_total_steps()
+
+
+def _final(api):
+    api.synchronize()
+    c, n = api.get_current(), api.get_counters()
+    k = int(n["nsize"][0])
+    return c["x"].copy(), c["lpost"].copy(), c["llike"].copy(), n["nhist"].copy(), n["nsize"].copy(), n["naccept"].copy(), api.get_history(0, 0, 0, k)["x"].copy(), \
+        api.get_swap_stats()["swap_count"].copy(), api.get_swap_stats()["swap_accept"].copy()
+
+
+@pytest.mark.gpu
+def test_fused_exchange_reproduces_the_unfused_exchange(engine_cls):
+    """three engines on one GPU stand for three ranks (the middle one has two boundaries).  The exchange fused into the step kernel
+    (peer pointers, per-ladder flags) uses the Philox addresses of ptg_boundary_swap, so the chains are bit-identical to the run
+    with separate pack / swap launches.  Launches are strictly sequential here: engines that spin on each other share this GPU."""
+    from ptmcmc_b200.rung_sharding import FusedRungShardedLadders
+    W, K_EVERY, CYCLES = 3, 7, 9
+    dev = torch.device("cuda", 0)
+    # --- unfused
+    ref = [make_rank(engine_cls, r, W) for r in range(W)]
+    packs = [[torch.zeros((L, DIM + 3), dtype=torch.float64, device=dev) for _ in range(2)] for _ in range(W)]
+    for c in range(CYCLES):
+        for e in ref:
+            e.step(K_EVERY); e.synchronize()
+        for r, e in enumerate(ref):
+            e.boundary_pack(0, packs[r][0].data_ptr()); e.boundary_pack(RPR - 1, packs[r][1].data_ptr()); e.synchronize()
+        for r, e in enumerate(ref):
+            if r + 1 < W:
+                e.boundary_swap(RPR - 1, packs[r + 1][0].data_ptr(), True, SHARED, r, c)
+            if r > 0:
+                e.boundary_swap(0, packs[r - 1][1].data_ptr(), False, SHARED, r - 1, c)
+            e.synchronize()
+    # --- fused
+    eng = [make_rank(engine_cls, r, W) for r in range(W)]
+    ptrs = {r: e.xchg_export()[1] for r, e in enumerate(eng)}
+    drv = [FusedRungShardedLadders(e, r, W, SHARED, exchange_every=K_EVERY, peers=ptrs) for r, e in enumerate(eng)]
+    for c in range(CYCLES):
+        for d, e in zip(drv, eng):
+            d.run(K_EVERY); e.synchronize()
+    for d, e in zip(drv, eng):
+        d.finish(); e.synchronize()
+    for r in range(W):
+        a, b = _final(ref[r]), _final(eng[r])
+        for u, v in zip(a, b):
+            assert np.array_equal(u, v), r
+    # every exchange appends one record to each edge chain on top of the K_EVERY per-iteration records
+    assert eng[1].get_total_steps() == ref[1].get_total_steps() == L * RPR * K_EVERY * CYCLES + 2 * L * CYCLES
+    for e in ref + eng:
+        e.close()
+
+
+@pytest.mark.gpu
+def test_fused_exchange_across_gpus():
+    """one rank per GPU over CUDA-IPC peer pointers (tests/mgpu_fused_exchange.py): chains identical to the NCCL exchange"""
+    n = min(torch.cuda.device_count(), 4)
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    import subprocess, sys
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "mgpu_fused_exchange.py")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), script], capture_output=True, text=True, timeout=600, env=dict(os.environ, MGPU_LADDERS="256"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "fused == nccl on every rank: True" in r.stdout
