@@ -198,6 +198,7 @@ def main():
     ap.add_argument("--save-every", type=int, default=0, help="add_every_N: store every N-th sample (default: per workload)")
     ap.add_argument("--swap-mode", default="reference", choices=["reference", "even_odd"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--in-launch", action="store_true", help="with --fused-exchange: exchange inside long launches (whole grid must be resident)")
     ap.add_argument("--fused-exchange", action="store_true", help="with --rung-sharded: exchange fused into the step kernel over NVLink peer memory (no collective)")
     ap.add_argument("--rung-sharded", type=int, default=0, metavar="K",
                     help="optional layout: ONE (n_gpus x rungs)-rung ladder family sharded by rung blocks, cross-GPU boundary swaps over NCCL every K PT iterations")
@@ -275,7 +276,7 @@ def main():
         with torch.cuda.stream(stream):
             eng.init_from_prior(); eng.synchronize()
             if args.fused_exchange:
-                drv = FusedRungShardedLadders(eng, rank, world, 0xB2005EED, exchange_every=args.rung_sharded)
+                drv = FusedRungShardedLadders(eng, rank, world, 0xB2005EED, exchange_every=args.rung_sharded, in_launch=args.in_launch, max_launch=S)
             else:
                 drv = RungShardedLadders(eng, rank, world, 0xB2005EED, exchange_every=args.rung_sharded, device="cuda:%d" % local, stream_ordered=True)
             for _ in range(args.warmup):
@@ -302,7 +303,7 @@ def main():
                 eng.synchronize(); torch.cuda.synchronize(); ex_ms = 1e3 * (time.perf_counter() - t1) / 20
         val = sum_over_ranks(n1 - n0) / max_over_ranks(dt)
         config["parallelism"] = "rung-sharded: %d ladders x (%d GPUs x %d rungs), boundary swaps %s every %d PT iterations" % (
-            L, world, R, "fused into the step kernel over NVLink peer memory" if args.fused_exchange else "over NCCL", args.rung_sharded)
+            L, world, R, ("fused into the step kernel over NVLink peer memory" + (", inside %d-iteration launches" % S if args.in_launch else ", one launch per exchange")) if args.fused_exchange else "over NCCL", args.rung_sharded)
         ms_step = 1e3 * max_over_ranks(dt) / args.steps
         if rank == 0:
             print(json.dumps(dict(metric=metric, value=val, unit=unit, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_step,

@@ -250,12 +250,15 @@ int ptg_boundary_swap(ptg_handle *h, int32_t my_rung, const void *neighbour_pack
  *   ptg_xchg_connect  takes the colder / hotter neighbour's handle or pointer (NULL at the ends of the ladder) and the two
  *                     boundary ids (= rank of the pair's lower block);
  *   ptg_step_exchange n_steps (<= 16384, may be 0) PT iterations in one launch; apply_pending runs the pending boundary trials
- *                     first, publish publishes the edges at the end.
- * Engines that wait on each other must run on DIFFERENT GPUs (or be launched strictly one after the other): the prologue spins. */
+ *                     first, publish publishes the edges at the end.  every > 0 (n_steps a multiple of it): the exchange ALSO runs
+ *                     inside the launch after every `every`-th iteration -- each ladder's warp publishes, waits for the neighbour
+ *                     GPU's warp of the same ladder and swaps, while the other warps keep stepping; needs the whole grid resident
+ *                     (one wave: refused otherwise) and the neighbours to run the same schedule.  every = 0: launch boundaries only.
+ * Engines that wait on each other must run on DIFFERENT GPUs (or, with every = 0, be launched strictly one after the other). */
 int ptg_xchg_export(ptg_handle *h, void *ipc_handle_64_bytes, void **local_ptr);
 int ptg_xchg_connect(ptg_handle *h, const void *colder, const void *hotter, int32_t handles_are_ipc, uint64_t shared_seed,
                      int64_t colder_boundary_id, int64_t hotter_boundary_id);
-int ptg_step_exchange(ptg_handle *h, int64_t n_steps, int32_t apply_pending, int32_t publish);
+int ptg_step_exchange(ptg_handle *h, int64_t n_steps, int32_t every, int32_t apply_pending, int32_t publish);
 
 /* FP64 peak microbenchmarks on `device` (the FP64 roofline denominators): out[0] = DFMA TFLOP/s,
  * out[1] = DMUL+DADD pairs (the engine's unfused arithmetic) TFLOP/s, out[2] = DMMA (mma.sync.m8n8k4.f64) TFLOP/s, out[3] = SM count */

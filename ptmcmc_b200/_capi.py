@@ -223,8 +223,8 @@ class CApi:
         self._call("xchg_connect", self.h, self._keep_xchg[0], self._keep_xchg[1], C.c_int32(1 if ipc else 0), C.c_uint64(shared_seed),
                    C.c_int64(colder_boundary_id), C.c_int64(hotter_boundary_id))
 
-    def step_exchange(self, n_steps, apply_pending, publish):
-        self._call("step_exchange", self.h, C.c_int64(n_steps), C.c_int32(1 if apply_pending else 0), C.c_int32(1 if publish else 0))
+    def step_exchange(self, n_steps, apply_pending, publish, every=0):
+        self._call("step_exchange", self.h, C.c_int64(n_steps), C.c_int32(every), C.c_int32(1 if apply_pending else 0), C.c_int32(1 if publish else 0))
 
     def get_total_steps(self):
         t = C.c_int64(); self._call("get_total_steps", self.h, C.byref(t)); return t.value

@@ -1212,13 +1212,21 @@ extern "C" int ptg_xchg_connect(ptg_handle *h, const void *colder, const void *h
 }
 // n_steps PT iterations in ONE launch; apply_pending: first run the boundary swap trials against what the neighbours published at
 // the end of their previous exchange launch; publish: publish this block's edge rungs at the end (exchange index = launches so far)
-extern "C" int ptg_step_exchange(ptg_handle *h, int64_t n_steps, int32_t apply_pending, int32_t publish) {
+extern "C" int ptg_step_exchange(ptg_handle *h, int64_t n_steps, int32_t every, int32_t apply_pending, int32_t publish) {
   int rc = xchg_check(h); if (rc) return rc;
   if (!h->xchg.on) return fail(PTG_EINVAL, "ptg_xchg_connect first");
   if (n_steps < 0 || n_steps > 16384) return fail(PTG_EINVAL, "n_steps must be within one launch (0..16384)");
   if (apply_pending && h->xchg.index == 0) return fail(PTG_EINVAL, "nothing has been published yet");
+  if (every < 0 || (every > 0 && n_steps % every != 0)) return fail(PTG_EINVAL, "n_steps must be a multiple of `every`");
+  const bool in_launch = every > 0 && n_steps > every;
+  if (in_launch) {
+    // warps wait for the neighbour GPU's warp of the same ladder: every CTA of the grid must be resident
+    int W = 0; pick_kernel(h, &W);
+    const long long warps = (h->m.n_ladders + (32 / W) - 1) / (32 / W);
+    if (!ptg_fstep_grid_is_resident(warps)) return fail(PTG_EINVAL, "in-launch exchange needs the whole grid resident (more ladders than one wave holds): use every = 0 and one launch per exchange");
+  }
   PtgXchg x = h->xchg;
-  x.swap_in = apply_pending ? 1 : 0; x.publish_out = publish ? 1 : 0;
+  x.swap_in = apply_pending ? 1 : 0; x.publish_out = publish ? 1 : 0; x.every = in_launch ? every : 0;
   h->xchg_launch = &x;
   if (n_steps == 0) { // prologue / epilogue only
     int W = 0; pick_kernel(h, &W);
@@ -1237,7 +1245,7 @@ extern "C" int ptg_step_exchange(ptg_handle *h, int64_t n_steps, int32_t apply_p
     h->xchg_launch = nullptr;
     if (rc) return rc;
   }
-  if (publish) h->xchg.index++;
+  h->xchg.index += (in_launch ? n_steps / every - 1 : 0) + (publish ? 1 : 0);
   return 0;
 }
 

@@ -161,6 +161,66 @@ __device__ __noinline__ FVec<D> ftransform(const double *__restrict__ M, FVec<D>
 // st_sc = swap_count delta | swap_accept delta << 16   (deltas per launch; the host keeps launches <= 32767 steps)
 #define PTG_FAST_MAX_STEPS 16384
 
+// ---- rung-sharded ladders, exchange over peer memory (PtgXchg, ptg_types.h) ---------------------------------------------------
+// publish p: the lanes that hold this block's edge rungs write (x, llike, lprior, beta) into parity p & 1 of this rank's area, then
+// raise the ladder's flag to p + 1
+template <int D>
+__device__ __forceinline__ void fx_publish(const PtgModel &m, const PtgXchg &xc, long long p, const FChain<D> &ch, long long ladder, int rung, int R) {
+  if (rung != 0 && rung != R - 1) return;
+#pragma unroll 1
+  for (int e = 0; e < 2; e++) {
+    if (rung != (e == 0 ? 0 : R - 1)) continue; // R == 1: the one rung is both edges
+    double *rec = xc.my_edges + (((size_t)(p & 1) * 2 + e) * m.n_ladders + ladder) * (D + 3);
+#pragma unroll
+    for (int k = 0; k < D; k++) rec[k] = ch.x[k];
+    rec[D] = ch.llike; rec[D + 1] = ch.lprior; rec[D + 2] = ch.beta;
+    __threadfence_system();
+    *((volatile int *)(xc.my_flags + (size_t)e * m.n_ladders + ladder)) = (int)(p + 1);
+  }
+}
+// boundary trial of exchange p (ptg_boundary_swap_kernel: chain.cc:1459-1490 + add_state) against the neighbour's record, read from
+// ITS memory over NVLink once its per-ladder flag says publish p is complete
+template <int D>
+__device__ __forceinline__ void fx_swap(const PtgModel &m, const PtgState &s, const PtgXchg &xc, long long p, FChain<D> &ch, int chain, long long ladder, int gl,
+                                     int rung, int R, int *cnt, int &err) {
+  const bool edge_lo = (rung == 0) && xc.has_lo, edge_hi = (rung == R - 1) && xc.has_hi;
+  if (!edge_lo && !edge_hi) return;
+  double *__restrict__ hb = s.hist + chain * ((long long)m.hist_cap * (D + 2));
+#pragma unroll 1
+  for (int e = 0; e < 2; e++) {
+    if (!(e == 0 ? edge_lo : edge_hi)) continue;
+    // e = 0: my coldest rung against the colder neighbour's hottest (I am the pair's upper rung); e = 1: the mirror image
+    const int their_edge = (e == 0) ? 1 : 0;
+    const volatile int *flag = (e == 0 ? xc.lo_flags : xc.hi_flags) + (size_t)their_edge * m.n_ladders + ladder;
+    long long spins = 0;
+    while (*flag < (int)(p + 1)) { if (++spins > (1ll << 24)) { err = 6; break; } __nanosleep(64); }
+    if (err) break;
+    __threadfence_system();
+    const volatile double *rec = (e == 0 ? xc.lo_edges : xc.hi_edges) + (((size_t)(p & 1) * 2 + their_edge) * m.n_ladders + ladder) * (D + 3);
+    const double nb_ll = rec[D], nb_lprior = rec[D + 1], nb_beta = rec[D + 2];
+    const bool i_am_lower = (e == 1);
+    double lla = i_am_lower ? ch.llike : nb_ll; if (!(lla > -1e200)) lla = -1e200;
+    double llb = i_am_lower ? nb_ll : ch.llike; if (!(llb > -1e200)) llb = -1e200;
+    const double ba = i_am_lower ? ch.beta : nb_beta, bb = i_am_lower ? nb_beta : ch.beta;
+    const double lhr = -(bb - ba) * (llb - lla);
+    bool accept = true;
+    if (lhr < 0) {
+      uint32_t q[4];
+      ptg_philox_draw(xc.shared_seed, (uint64_t)gl * PTG_STREAM_STRIDE + PTG_STREAM_LADDER, PTG_DOMAIN_BOUNDARY, (uint64_t)p,
+                      (uint32_t)(e == 0 ? xc.lo_boundary : xc.hi_boundary), q);
+      accept = (log(ptg_u52_to_unit(q[0], q[1])) < lhr);
+    }
+    if (accept) {
+#pragma unroll
+      for (int k = 0; k < D; k++) ch.x[k] = rec[k];
+      ch.llike = nb_ll; ch.lprior = nb_lprior;
+      ch.lpost = nb_lprior + ch.beta * nb_ll; // lpost recomputed = lprior(x) + beta*llike (chain.cc:925-928)
+    }
+    fappend<D>(m, s, ch, chain, hb, cnt);
+    if (i_am_lower) cnt[FC_SC] += 1 + (accept ? (1 << 16) : 0); // counted at the pair's lower rung
+  }
+}
+
 // XCHG: compiled with the rung-boundary exchange prologue / epilogue (ptg_step_exchange); the plain instantiation carries none of it
 template <int D, bool XCHG>
 __global__ void __launch_bounds__(PTG_FSTEP_MAX_THREADS, 1) ptg_fstep_kernel(const __grid_constant__ PtgModel m, PtgState s, long long step0, int n_steps, int W, const __grid_constant__ PtgXchg xc) {
@@ -230,44 +290,8 @@ __global__ void __launch_bounds__(PTG_FSTEP_MAX_THREADS, 1) ptg_fstep_kernel(con
   int err = 0;
 
   // ================================================================= rung-sharded ladders: pending cross-GPU boundary swap
-  // (the trial of ptg_boundary_swap_kernel, chain.cc:1459-1490 + add_state, on the lanes that hold this block's edge rungs; the
-  // neighbour's record comes straight from ITS memory over NVLink once its per-ladder flag says the publish is complete)
-  if (XCHG && xc.on && xc.swap_in && active) {
-    const bool edge_lo = (rung == 0) && xc.has_lo, edge_hi = (rung == R - 1) && xc.has_hi;
-#pragma unroll 1
-    for (int e = 0; e < 2; e++) {
-      if (!(e == 0 ? edge_lo : edge_hi)) continue;
-      // e = 0: my coldest rung against the colder neighbour's hottest (I am the pair's upper rung); e = 1: the mirror image
-      const long long p = xc.index - 1;
-      const int their_edge = (e == 0) ? 1 : 0;
-      const volatile int *flag = (e == 0 ? xc.lo_flags : xc.hi_flags) + (size_t)their_edge * m.n_ladders + ladder;
-      long long spins = 0;
-      while (*flag < (int)(p + 1)) { if (++spins > (1ll << 24)) { err = 6; break; } __nanosleep(64); }
-      if (err) break;
-      __threadfence_system();
-      const volatile double *rec = (e == 0 ? xc.lo_edges : xc.hi_edges) + (((size_t)(p & 1) * 2 + their_edge) * m.n_ladders + ladder) * (D + 3);
-      const double nb_ll = rec[D], nb_lprior = rec[D + 1], nb_beta = rec[D + 2];
-      const bool i_am_lower = (e == 1);
-      double lla = i_am_lower ? ch.llike : nb_ll; if (!(lla > -1e200)) lla = -1e200;
-      double llb = i_am_lower ? nb_ll : ch.llike; if (!(llb > -1e200)) llb = -1e200;
-      const double ba = i_am_lower ? ch.beta : nb_beta, bb = i_am_lower ? nb_beta : ch.beta;
-      const double lhr = -(bb - ba) * (llb - lla);
-      bool accept = true;
-      if (lhr < 0) {
-        uint32_t q[4];
-        ptg_philox_draw(xc.shared_seed, ladder_stream, PTG_DOMAIN_BOUNDARY, (uint64_t)p, (uint32_t)(e == 0 ? xc.lo_boundary : xc.hi_boundary), q);
-        accept = (log(ptg_u52_to_unit(q[0], q[1])) < lhr);
-      }
-      if (accept) {
-#pragma unroll
-        for (int k = 0; k < D; k++) ch.x[k] = rec[k];
-        ch.llike = nb_ll; ch.lprior = nb_lprior;
-        ch.lpost = nb_lprior + ch.beta * nb_ll; // lpost recomputed = lprior(x) + beta*llike (chain.cc:925-928)
-      }
-      fappend<D>(m, s, ch, chain, hbase, cnt);
-      if (i_am_lower) cnt[FC_SC] += 1 + (accept ? (1 << 16) : 0); // counted at the pair's lower rung
-    }
-  }
+  long long xp = xc.index; // running publish index (XCHG instantiation only)
+  if (XCHG && xc.on && xc.swap_in && active) fx_swap<D>(m, s, xc, xp - 1, ch, chain, ladder, gl, rung, R, cnt, err);
 
   const int maxswaps = m.maxswaps;
   const double swap_thresh = (R - 1) * m.swap_rate / maxswaps; // chain.cc:1413
@@ -594,21 +618,21 @@ __global__ void __launch_bounds__(PTG_FSTEP_MAX_THREADS, 1) ptg_fstep_kernel(con
       s.trace_lhr[step * m.n_chains + chain] = do_mh ? lhr : 0.0;
       s.trace_code[step * m.n_chains + chain] = do_mh ? (code | (type & PTG_TRACE_TYPE_MASK)) : PTG_TRACE_SWAPPED;
     }
+    // in-launch exchange: after every xc.every-th iteration (not the launch's last, whose publish the epilogue does) publish the
+    // edges and run the boundary trial as soon as the neighbour's same ladder has published -- warps wait one by one, the rest of
+    // the SM keeps stepping.  The host only uses this when every CTA of the grid is resident (one wave on each GPU).
+    if (XCHG && xc.on && xc.every > 0 && it + 1 < n_steps && (it + 1) % xc.every == 0) {
+      if (active) {
+        fx_publish<D>(m, xc, xp, ch, ladder, rung, R);
+        fx_swap<D>(m, s, xc, xp, ch, chain, ladder, gl, rung, R, cnt, err);
+      }
+      xp++;
+      __syncwarp();
+    }
   }
 
   // ================================================================= rung-sharded ladders: publish this block's edge rungs
-  if (XCHG && xc.on && xc.publish_out && active && (rung == 0 || rung == R - 1)) {
-#pragma unroll 1
-    for (int e = 0; e < 2; e++) {
-      if (rung != (e == 0 ? 0 : R - 1)) continue; // R == 1: the one rung is both edges
-      double *rec = xc.my_edges + (((size_t)(xc.index & 1) * 2 + e) * m.n_ladders + ladder) * (D + 3);
-#pragma unroll
-      for (int k = 0; k < D; k++) rec[k] = ch.x[k];
-      rec[D] = ch.llike; rec[D + 1] = ch.lprior; rec[D + 2] = ch.beta;
-      __threadfence_system();
-      *((volatile int *)(xc.my_flags + (size_t)e * m.n_ladders + ladder)) = (int)(xc.index + 1);
-    }
-  }
+  if (XCHG && xc.on && xc.publish_out && active) fx_publish<D>(m, xc, xp, ch, ladder, rung, R);
 
   if (active) {
 #pragma unroll

@@ -28,16 +28,6 @@ static cudaError_t launch_wstep_t(const PtgModel &m, const PtgState &s, long lon
   return cudaGetLastError();
 }
 // production kernel (Philox draws): ladder-in-a-warp, proposal table + bins + per-thread counters in shared memory
-static inline int ptg_fstep_threads(long long warps) {
-  static const int forced = [] { const char *e = getenv("PTG_FSTEP_THREADS"); return e ? atoi(e) : 0; }(); // experiments only
-  if (forced >= 32 && forced <= PTG_FSTEP_MAX_THREADS && forced % 32 == 0) return forced;
-  int dev = 0, sms = 148;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const long long need = (long long)sms * 95 / 100;
-  if ((warps + 27) / 28 >= need) return 896;
-  if ((warps + 13) / 14 >= need) return 448;
-  return 128;
-}
 template <int D>
 static cudaError_t launch_fstep_t(const PtgModel &m, const PtgState &s, long long step0, int n_steps, int W, const PtgXchg &xc, cudaStream_t st) {
   const long long warps = (m.n_ladders + (32 / W) - 1) / (32 / W);

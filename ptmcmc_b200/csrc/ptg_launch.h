@@ -1,5 +1,6 @@
 // ptg_launch.h -- launchers exported by the per-dimension translation units (ptg_inst_dN.cu)
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include "ptg_types.h"
 // dynamic shared memory of one ladder in the shared-memory step kernel (must match LadderShared::carve in ptg_kernels.cuh)
@@ -12,6 +13,26 @@ static inline size_t ptg_ladder_shared_bytes(int D, int R) {
 #define PTG_DIM_LIST(X) X(3) X(5) X(9)
 #else
 #define PTG_DIM_LIST(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(12) X(16)
+// CTA size of the production kernel (ptg_fstep_kernel) for a batch of `warps` ladder-warps
+static inline int ptg_fstep_threads(long long warps) {
+  static const int forced = [] { const char *e = getenv("PTG_FSTEP_THREADS"); return e ? atoi(e) : 0; }(); // experiments only
+  if (forced >= 32 && forced <= 896 && forced % 32 == 0) return forced;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long need = (long long)sms * 95 / 100;
+  if ((warps + 27) / 28 >= need) return 896;
+  if ((warps + 13) / 14 >= need) return 448;
+  return 128;
+}
+// 1 if every CTA of that grid is resident at once (72 registers: 896 threads per SM), else 0
+static inline int ptg_fstep_grid_is_resident(long long warps) {
+  const int threads = ptg_fstep_threads(warps);
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long blocks = (warps + threads / 32 - 1) / (threads / 32);
+  return blocks <= (long long)(896 / threads) * sms ? 1 : 0;
+}
+
 #endif
 #define PTG_DECLARE(D)                                                                                                      \
   cudaError_t ptg_launch_step_d##D(int mode, const PtgModel &m, const PtgState &s, long long step0, int n_steps, int lpb,   \

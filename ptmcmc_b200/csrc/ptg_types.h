@@ -87,6 +87,7 @@ struct PtgState {
 // neighbour's flag to reach p + 1, reads the neighbour's record through its peer pointer and runs the boundary swap trial.
 struct PtgXchg {
   int on, swap_in, publish_out, has_lo, has_hi;
+  int every;                         // > 0: also exchange INSIDE the launch after every `every`-th iteration
   long long index;                   // publish index of this launch's epilogue; its prologue consumes index - 1
   double *my_edges; int *my_flags;
   const double *lo_edges; const int *lo_flags; // colder neighbour (its hottest rung pairs with my coldest)

@@ -98,9 +98,12 @@ class FusedRungShardedLadders:
     rungs in this rank's own HBM, the prologue of the next launch reads the neighbours' records through CUDA-IPC peer pointers once
     their per-ladder flags are up.  No collective, no extra launch and no host synchronisation inside the loop; one rank per GPU."""
 
-    def __init__(self, api, rank, world, shared_seed, exchange_every=10, peers=None):
-        """peers: {rank: device pointer} for engines of the SAME process (tests); otherwise handles travel over torch.distributed"""
+    def __init__(self, api, rank, world, shared_seed, exchange_every=10, peers=None, in_launch=False, max_launch=1000):
+        """peers: {rank: device pointer} for engines of the SAME process (tests); otherwise handles travel over torch.distributed.
+        in_launch: run up to `max_launch` iterations per launch with the exchange INSIDE the kernel every `exchange_every`
+        iterations (needs one rank per GPU and the whole grid resident); otherwise one launch per exchange."""
         self.api, self.rank, self.world, self.exchange_every = api, rank, world, exchange_every
+        self.in_launch, self.max_launch = bool(in_launch), max(exchange_every, max_launch - max_launch % exchange_every)
         handle, ptr = api.xchg_export()
         if peers is None:
             handles = [None] * world
@@ -120,10 +123,15 @@ class FusedRungShardedLadders:
         previous launch left pending (finish() applies the last one)"""
         done = 0
         while done < n_steps:
-            k = min(self.exchange_every, n_steps - done)
-            self.api.step_exchange(k, self.pending, True)
+            if self.in_launch and n_steps - done >= self.exchange_every:
+                k = min(self.max_launch, (n_steps - done) // self.exchange_every * self.exchange_every)
+                self.api.step_exchange(k, self.pending, True, every=self.exchange_every)
+                self.n_exchanges += k // self.exchange_every
+            else:
+                k = min(self.exchange_every, n_steps - done)
+                self.api.step_exchange(k, self.pending, True)
+                self.n_exchanges += 1
             self.pending = True
-            self.n_exchanges += 1
             done += k
 
     def finish(self):

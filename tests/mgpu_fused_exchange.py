@@ -1,7 +1,8 @@
 """Multi-GPU check of the fused rung-boundary exchange (run under torchrun, one rank per GPU):
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/mgpu_fused_exchange.py
 Every rank runs the rung-sharded ladder twice from the same start -- NCCL neighbour exchange between launches
-(RungShardedLadders) and the exchange fused into the step kernel over CUDA-IPC peer pointers (FusedRungShardedLadders) -- and
+(RungShardedLadders), the exchange fused into the step kernel over CUDA-IPC peer pointers at launch boundaries and INSIDE long
+launches (FusedRungShardedLadders) -- and
 asserts bit-identical chains; then reports the time per cycle of both.  tests/test_rung_sharding.py drives it when >= 2 GPUs exist."""
 import os
 import sys
@@ -32,14 +33,14 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     out = {}
-    for mode in ("nccl", "fused"):
+    for mode in ("nccl", "fused", "in_launch"):
         e = make(rank, world, local)
         stream = torch.cuda.Stream()
         e.set_stream(stream.cuda_stream)
         with torch.cuda.stream(stream):
             e.init_from_prior(); e.synchronize()
             drv = RungShardedLadders(e, rank, world, SHARED, exchange_every=EVERY, device="cuda:%d" % local, stream_ordered=True) if mode == "nccl" \
-                else FusedRungShardedLadders(e, rank, world, SHARED, exchange_every=EVERY)
+                else FusedRungShardedLadders(e, rank, world, SHARED, exchange_every=EVERY, in_launch=(mode == "in_launch"), max_launch=200)
             drv.run(EVERY * 3); drv.finish(); e.synchronize()
             dist.barrier(); torch.cuda.synchronize()
             t0 = time.perf_counter()
@@ -49,12 +50,12 @@ def main():
         c, n = e.get_current(), e.get_counters()
         out[mode] = (c["x"].copy(), c["lpost"].copy(), n["nhist"].copy(), n["naccept"].copy(), e.get_history(0, 0, 0, int(n["nsize"][0]), full=False)["x"].copy(), dt)
         e.close()
-    same = all(np.array_equal(a, b) for a, b in zip(out["nccl"][:5], out["fused"][:5]))
+    same = all(np.array_equal(a, b) for a, b in zip(out["nccl"][:5], out["fused"][:5])) and all(np.array_equal(a, b) for a, b in zip(out["nccl"][:5], out["in_launch"][:5]))
     flags = [None] * world
     dist.all_gather_object(flags, bool(same))
     if rank == 0:
-        print("fused == nccl on every rank:", all(flags), "| ms per cycle of %d iterations: nccl %.4f fused %.4f (%d ladders x %d rungs per GPU, %d GPUs)"
-              % (EVERY, 1e3 * out["nccl"][5] / CYCLES, 1e3 * out["fused"][5] / CYCLES, L, R, world))
+        print("fused == nccl on every rank:", all(flags), "| ms per cycle of %d iterations: nccl %.4f fused %.4f fused in-launch %.4f (%d ladders x %d rungs per GPU, %d GPUs)"
+              % (EVERY, 1e3 * out["nccl"][5] / CYCLES, 1e3 * out["fused"][5] / CYCLES, 1e3 * out["in_launch"][5] / CYCLES, L, R, world))
     dist.barrier()
     dist.destroy_process_group()
     assert all(flags)
