@@ -377,33 +377,39 @@ def main():
     ess = None
     try:
         from ptmcmc_b200.analysis import ess_per_sample
-        nh = min(w["hist"] - 8, 2000)
+        cnt = eng.get_counters()
+        nh = int(min(w["hist"] - 8, 2000, cnt["nsize"][::R].min()))      # never more than the cold chains have stored so far
         tau_dev = eng.get_act(0, nh, min(nh // 2, 1000))                 # device: every ladder's cold chain, per parameter
         eps_dev = float(np.mean(1.0 / tau_dev.max(axis=1)))              # ESS per stored sample, mean over ladders
         nl = min(L, 256)                                                 # host cross-check on a sample of ladders (ACFs averaged, then windowed)
-        cnt = eng.get_counters()
         cold = np.stack([eng.get_history(l, 0, int(cnt["nsize"][l * R]) - nh, nh, full=False)["x"] for l in range(nl)])
         eps_host, taus = ess_per_sample(cold)
         pt_iter_per_s = args.steps * S / (ms_max * 1e-3)
-        # the reference's own estimator (chain::report_effective_samples as the run loop calls it, ptmcmc.cc:645; analysis.py restates
-        # it and tests pin it to the reference build) on the newest ring window of each sampled cold chain
-        from ptmcmc_b200.analysis import report_effective_samples
-        nr = min(w["hist"] - 8, 8000)
+        # the reference's own estimator (chain::report_effective_samples as the run loop calls it, ptmcmc.cc:645) for EVERY ladder's cold
+        # chain over the newest ring window: lag statistics on the device in the reference's summation order
+        # (ptg_get_autocovar_windows), combination on the host; analysis.py restates the recipe and tests pin it to the reference build
+        nr = int(min(w["hist"] - 8, 8000, cnt["nsize"][::R].min()))
         se = w["save_every"]
-        rec = []
-        for l in range(min(L, 32)):
-            xs = eng.get_history(l, 0, int(cnt["nsize"][l * R]) - nr, nr, full=False)["x"][:, :20]
-            e_l, len_l = report_effective_samples(xs, nr * se, n_init=0, add_every=se, width=se * 1000, every=se)
-            if len_l > 0:
-                rec.append(e_l / len_l)
-        eps_recipe = float(np.mean(rec)) if rec else None              # ESS per PT iteration
-        ess = dict(value=eps_dev / w["save_every"] * pt_iter_per_s * L * world, unit="ESS/s", tau_pt_iterations=float(np.median(tau_dev.max(axis=1))) * w["save_every"],
-                   window=nh, ladders=L, estimator="device (ptg_get_act): per cold chain N/tau, tau = Sokal-windowed integrated autocorrelation time, "
-                   "min over parameters, mean over ladders", host_check=dict(value=eps_host / w["save_every"] * pt_iter_per_s * L * world,
-                   tau_pt_iterations=float(taus.max()) * w["save_every"], ladders_sampled=nl),
-                   reference_recipe=dict(value=(eps_recipe * pt_iter_per_s * L * world) if eps_recipe else None, ess_per_pt_iteration=eps_recipe,
-                                         window_records=nr, ladders_sampled=len(rec),
-                                         estimator="chain::report_effective_samples(-1, 1000 save_every, save_every) (chain.cc:457-643) per cold chain"))
+        eps_recipe, n_recipe = None, 0
+        try:
+            ess_l, len_l = eng.report_effective_samples_all(rung=0, window_records=nr)
+            ok = len_l > 0
+            n_recipe = int(ok.sum())
+            if n_recipe:
+                eps_recipe = float(np.mean(ess_l[ok] / len_l[ok]))      # ESS per PT iteration, mean over ladders
+        except Exception as exc:
+            recipe_error = repr(exc)
+        sokal = eps_dev / w["save_every"] * pt_iter_per_s * L * world
+        ess = dict(value=(eps_recipe * pt_iter_per_s * L * world) if eps_recipe else sokal, unit="ESS/s",
+                   estimator=("the reference's chain::report_effective_samples(-1, 1000 save_every, save_every) (chain.cc:457-643) on every cold chain's newest "
+                              "%d records: lag statistics on the device (ptg_get_autocovar_windows), min over parameters, summed over ladders" % nr) if eps_recipe
+                   else "Sokal window (see sokal_device); the ring window is too short for the reference recipe",
+                   ess_per_pt_iteration=eps_recipe, ladders=L, ladders_with_estimate=n_recipe,
+                   sokal_device=dict(value=sokal, tau_pt_iterations=float(np.median(tau_dev.max(axis=1))) * w["save_every"], window=nh,
+                                     estimator="ptg_get_act: per cold chain N/tau, Sokal-windowed integrated autocorrelation time, min over parameters, mean over ladders"), host_check=dict(value=eps_host / w["save_every"] * pt_iter_per_s * L * world,
+                   tau_pt_iterations=float(taus.max()) * w["save_every"], ladders_sampled=nl))
+        if nh > int(cnt["nsize"][::R].min()) - spec.config(n_ladders=1).n_init:
+            ess["note"] = "the run is shorter than the analysis window: it still contains start-up prior draws, the ESS figure is not meaningful"
     except Exception as exc:  # analysis is not part of the timed path
         ess = dict(value=None, error=repr(exc))
 

@@ -223,6 +223,15 @@ int ptg_get_mean_loglike(ptg_handle *h, int32_t n_last, double *mean_ll);
  * its newest n_last stored samples, lags < max_lag -> tau[n_ladders][dim]; ESS of a chain = n_last / max_j tau_j (in stored samples). */
 int ptg_get_act(ptg_handle *h, int32_t rung, int32_t n_last, int32_t max_lag, double *tau);
 int ptg_get_log_evidence(ptg_handle *h, int32_t n_last, double *log_evidence);
+/* The reference's own effective-sample-size recipe, device part: the windowed lag statistics of chain::compute_autocovar_windows
+ * (chain.cc:126-289) of rung `rung` of every ladder, summed in the reference's order.  Windows are counted in stored records:
+ * window k (0 = oldest) of ladder l covers records [end_l - (n_win - k) * swidth, + swidth), end_l = end_rec[l] (NULL: every record
+ * stored so far); lag_rec[n_lag] in records, lag_rec[0] = 0; the first n_feat parameters are the features.
+ *   means[l][f][k][j] = sum_i (f_i + f_{i - lag_j}) / swidth / 2,   covar[l][f][k][j] = sum_i f_i f_{i - lag_j} / swidth - means^2.
+ * chain::compute_effective_samples / report_effective_samples (chain.cc:292-545) combine them on the host
+ * (ptmcmc_b200/analysis.py).  Fails if a window or its lagged copy has left the history ring. */
+int ptg_get_autocovar_windows(ptg_handle *h, int32_t rung, int32_t swidth, int32_t n_win, int32_t n_lag, const int32_t *lag_rec,
+                              const int64_t *end_rec, int32_t n_feat, double *means, double *covar);
 
 /* Rung-sharded ladders (the reference's MPI layout, chain.cc:1290-1311,1433-1435, with block rung assignment): every GPU holds
  * a contiguous block of rungs of EVERY ladder (explicit betas via ptg_set_betas); replica swaps inside a block run in the step

@@ -194,3 +194,62 @@ def report_effective_samples(hist, nstep, n_init=0, add_every=1, width=40000, ev
                 break
             every *= scalestep
     return ess, int(bestwid * nwin)
+
+
+def effective_samples_from_windows(covar, means, lags, width, nevery, swidth):
+    """chain::compute_effective_samples (chain.cc:340-416) for a BATCH of chains at once, from window statistics
+    covar / means [n_chains][n_feat][n_win][n_lag] (e.g. ptg_get_autocovar_windows).  -> ess[n_chains], best_nwin[n_chains]"""
+    oversmall_aclen_fac = 3.0
+    covar, means = np.asarray(covar), np.asarray(means)
+    n, nf, nwin_tot, nlag = covar.shape
+    ess_max, nwin_max = np.zeros(n), np.zeros(n, dtype=np.int64)
+    for nwin in range(1, nwin_tot + 1):
+        sl = slice(nwin_tot - nwin, nwin_tot)
+        ess = np.full(n, 1e100)
+        for f in range(nf):
+            mean = np.zeros(n)
+            for i in range(nwin_tot - nwin, nwin_tot):
+                mean = mean + means[:, f, i, 0]
+            mean = mean / nwin
+            dm = mean[:, None, None] - means[:, f, sl, :]
+            dm0 = (mean[:, None] - means[:, f, sl, 0])[:, :, None]
+            num = np.zeros((n, nlag)); den = np.zeros((n, nlag))
+            for i in range(nwin):                                   # window by window, the reference's summation order
+                num = num + (covar[:, f, sl, :][:, i, :] + dm[:, i, :] * dm[:, i, :]) * swidth
+                den = den + (covar[:, f, sl, 0][:, i, None] + dm0[:, i, :] * dm0[:, i, :]) * swidth
+            ac_len, lastcorr, dacl = np.ones(n), np.ones(n), np.zeros(n)
+            done = np.zeros(n, dtype=bool)
+            last_lag = 0
+            with np.errstate(divide="ignore", invalid="ignore"):
+                for il in range(1, nlag):
+                    corr = num[:, il] / den[:, il]
+                    brk = ~done & (lastcorr < 0) & (corr < 0)          # initially-positive-sequence cut
+                    ac_len[brk] -= dacl[brk]
+                    done |= brk
+                    upd = ~done
+                    lastcorr[upd] = corr[upd]
+                    dacl[upd] = 2.0 * (lags[il] - last_lag) * corr[upd]
+                    ac_len[upd] += dacl[upd]
+                    last_lag = lags[il]
+                essi = nwin * width / ac_len
+            small = ac_len < nevery
+            essi[small] = nwin * width / oversmall_aclen_fac / nevery
+            ess = np.where(essi < ess, essi, ess)
+        better = ess > ess_max
+        ess_max[better] = ess[better]
+        nwin_max[better] = nwin
+    return ess_max, nwin_max
+
+
+def recipe_geometry(nstep, width, every):
+    """the window geometry report_effective_samples settles on for a chain of nstep steps with esslimit < 0 (chain.cc:475-481,
+    549-552 and compute_autocovar_windows :179-222): -> (width, swidth, n_win, lags in steps)"""
+    minburn, maxbins = 2, 20
+    width, every = int(width), max(int(every), 1)
+    while width < nstep * 0.05:
+        width *= 2
+    while width * (maxbins + minburn) < nstep:
+        width *= 2
+    swidth = width // every
+    n_win = max(nstep // (swidth * every) - minburn, 0)
+    return width, swidth, n_win, _lag_grid(swidth, every, minburn, 1.1)

@@ -1048,6 +1048,75 @@ extern "C" int ptg_get_act(ptg_handle *h, int32_t rung, int32_t n_last, int32_t 
   return ptg_synchronize(h);
 }
 
+// The reference's own ESS recipe, device part: the windowed lag statistics of chain::compute_autocovar_windows
+// (chain.cc:126-289) for rung `rung` of every ladder.  One CTA per (window, ladder); thread j owns lag j and walks the window's
+// samples in index order -- the reference's own summation order (`xsum += fi + f[i]; xxsum += fi * f[i]`, chain.cc:268-279), so the
+// numbers equal the C++ reference's to the last bit, and
+//     means[l][f][k][j] = sum(f_i + f_{i-lag_j}) / n / 2 ,  covar[l][f][k][j] = sum(f_i f_{i-lag_j}) / n - means^2        (lag 0: mean, variance)
+// Windows are counted in stored records: window k of ladder l covers records [end_l - (n_win - k) swidth, +swidth), end_l =
+// end_rec[l] (default: all records stored so far).  The combination over windows (chain.cc:292-449) is cheap and stays on the host.
+__global__ void __launch_bounds__(128) ptg_autocovar_kernel(PtgModel m, PtgState s, int rung, int swidth, int n_win, int n_lag, const int *__restrict__ lag_rec,
+                                                            const long long *__restrict__ end_rec, int n_feat, double *means, double *covar, int *bad) {
+  const int k = blockIdx.x;
+  const long long l = blockIdx.y, c = l * m.n_rungs + rung;
+  const long long nsize = s.nsize[c], end = end_rec ? end_rec[l] : nsize;
+  const long long start = end - (long long)(n_win - k) * swidth;
+  const int D = m.dim, cap = m.hist_cap;
+  const double *base = s.hist + c * (long long)cap * (D + 2);
+  for (int j = threadIdx.x; j < n_lag; j += blockDim.x) {
+    const long long first = start - lag_rec[j];
+    if (first < 0 || first < nsize - cap || end > nsize) { if (bad) atomicExch(bad, 1); continue; } // not resident in the ring
+    int p0 = (int)(start % cap), p1 = (int)(first % cap);
+    for (int f0 = 0; f0 < n_feat; f0 += 4) {
+      double sx[4] = {0, 0, 0, 0}, sxx[4] = {0, 0, 0, 0};
+      int q0 = p0, q1 = p1;
+      for (int i = 0; i < swidth; i++) {
+        const double *a = base + (long long)q0 * (D + 2) + f0, *b = base + (long long)q1 * (D + 2) + f0;
+#pragma unroll
+        for (int f = 0; f < 4; f++) if (f0 + f < n_feat) { const double fi = a[f], fl = b[f]; sx[f] += (fl + fi); sxx[f] += fl * fi; }
+        if (++q0 == cap) q0 = 0;
+        if (++q1 == cap) q1 = 0;
+      }
+#pragma unroll
+      for (int f = 0; f < 4; f++) if (f0 + f < n_feat) {
+        const size_t o = (((size_t)l * n_feat + f0 + f) * n_win + k) * n_lag + j;
+        const double mean = sx[f] / swidth / 2;
+        means[o] = mean;
+        covar[o] = sxx[f] / swidth - mean * mean;
+      }
+    }
+  }
+}
+extern "C" int ptg_get_autocovar_windows(ptg_handle *h, int32_t rung, int32_t swidth, int32_t n_win, int32_t n_lag, const int32_t *lag_rec,
+                                         const int64_t *end_rec, int32_t n_feat, double *means, double *covar) {
+  if (!h || !lag_rec || !means || !covar || swidth < 1 || n_win < 1 || n_lag < 1 || n_feat < 1) return fail(PTG_EINVAL, "bad argument");
+  if (!h->inited) return fail(PTG_EINVAL, "not initialised");
+  if (rung < 0 || rung >= h->m.n_rungs) return fail(PTG_EINVAL, "rung %d out of range", rung);
+  if (n_feat > h->m.dim) return fail(PTG_EINVAL, "n_feat exceeds dim");
+  if (n_win > 65535) return fail(PTG_EINVAL, "too many windows");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const size_t L = (size_t)h->m.n_ladders, cnt = L * n_feat * n_win * n_lag;
+  // scratch: means | covar | lags (int) | end_rec (int64) | bad flag
+  const size_t bytes = 2 * cnt * sizeof(double) + ((size_t)n_lag + 2) * sizeof(int) + (L + 1) * sizeof(long long) + 64;
+  int rc = ensure_scratch(h, bytes); if (rc) return rc;
+  double *dm = h->d_scratch, *dc = dm + cnt;
+  long long *dend = (long long *)(dc + cnt);
+  int *dlag = (int *)(dend + L + 1), *dbad = dlag + n_lag;
+  CUDA_TRY(cudaMemcpyAsync(dlag, lag_rec, (size_t)n_lag * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  if (end_rec) CUDA_TRY(cudaMemcpyAsync(dend, end_rec, L * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemsetAsync(dbad, 0, sizeof(int), h->stream));
+  CUDA_TRY(cudaMemsetAsync(dm, 0, 2 * cnt * sizeof(double), h->stream));
+  ptg_autocovar_kernel<<<dim3((unsigned)n_win, (unsigned)L), 128, 0, h->stream>>>(h->m, h->s, rung, swidth, n_win, n_lag, dlag, end_rec ? dend : nullptr, n_feat, dm, dc, dbad);
+  CUDA_TRY(cudaGetLastError());
+  int bad = 0;
+  CUDA_TRY(cudaMemcpyAsync(means, dm, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(covar, dc, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(&bad, dbad, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  rc = ptg_synchronize(h); if (rc) return rc;
+  if (bad) return fail(PTG_EINVAL, "a requested window (or its lagged copy) is no longer in the history ring, or lies beyond the stored records");
+  return 0;
+}
+
 extern "C" int ptg_get_mean_loglike(ptg_handle *h, int32_t n_last, double *mean_ll) {
   if (!h || !mean_ll || n_last < 1) return fail(PTG_EINVAL, "bad argument");
   if (!h->inited) return fail(PTG_EINVAL, "not initialised");

@@ -75,6 +75,48 @@ class Engine(K.CApi):
         return report_effective_samples(x, nhist, n_init=self.cfg.n_init, add_every=se,
                                         width=se * 1000, every=se, esslimit=esslimit, imax=imax)
 
+    def get_autocovar_windows(self, rung, swidth, n_win, lag_rec, n_feat, end_rec=None):
+        """device part of the reference's ESS recipe -> means, covar [n_ladders, n_feat, n_win, n_lag] (ptg_get_autocovar_windows)"""
+        L = self.cfg.n_ladders
+        lag_rec = np.ascontiguousarray(lag_rec, dtype=np.int32)
+        shape = (L, n_feat, n_win, len(lag_rec))
+        means, covar = np.empty(shape), np.empty(shape)
+        end = None if end_rec is None else np.ascontiguousarray(end_rec, dtype=np.int64)
+        self._call("get_autocovar_windows", self.h, C.c_int32(rung), C.c_int32(swidth), C.c_int32(n_win), C.c_int32(len(lag_rec)),
+                   lag_rec.ctypes.data_as(C.POINTER(C.c_int32)), None if end is None else end.ctypes.data_as(C.POINTER(C.c_int64)),
+                   C.c_int32(n_feat), K._dp(means), K._dp(covar))
+        return means, covar
+
+    def report_effective_samples_all(self, rung=0, window_records=None, imax=-1):
+        """(ess[n_ladders], useful length[n_ladders]) of rung `rung` of EVERY ladder by the reference's recipe
+        (chain::report_effective_samples(-1, 1000 save_every, save_every), esslimit < 0): window statistics on the device, in the
+        reference's summation order, combination on the host.  window_records: treat the newest that many stored records of each
+        chain as the chain (a wrapped ring); default: the whole run, which must still be resident."""
+        from .analysis import recipe_geometry, effective_samples_from_windows
+        L, R, se = self.cfg.n_ladders, self.cfg.n_rungs, self.cfg.save_every
+        nf = self.dim if imax < 0 else min(imax, self.dim)
+        nf = min(nf, 20)
+        c = self.get_counters()
+        idx = np.arange(L) * R + rung
+        if window_records is not None:
+            nstep = np.full(L, int(window_records) * se, dtype=np.int64)
+            end = None
+        else:
+            nstep = c["nhist"][idx].astype(np.int64)
+            end = self.cfg.n_init + nstep // se
+        ess, length = np.zeros(L), np.zeros(L, dtype=np.int64)
+        geo = {}
+        for l in range(L):
+            geo.setdefault(recipe_geometry(int(nstep[l]), se * 1000, se)[:3], []).append(l)
+        for (width, swidth, n_win), members in geo.items():
+            if n_win < 1:
+                continue
+            lags = recipe_geometry(int(nstep[members[0]]), se * 1000, se)[3]
+            means, covar = self.get_autocovar_windows(rung, swidth, n_win, [g // se for g in lags], nf, end)
+            e, nw = effective_samples_from_windows(covar[members], means[members], lags, width, se, swidth)
+            ess[members], length[members] = e, nw * width
+        return ess, length
+
     def get_mean_loglike(self, n_last):
         out = np.empty(self.n_chains)
         self._call("get_mean_loglike", self.h, C.c_int32(n_last), K._dp(out))

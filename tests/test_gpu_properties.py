@@ -259,3 +259,31 @@ def test_host_callback_likelihood_equals_device_functor(engine_cls):
     assert (ca == cb).all() and la.tobytes() == lb.tobytes()
     assert len(calls) >= 100 + steps and max(calls) <= L * 6          # one batched call per init round and per PT iteration
     assert np.allclose(b.eval_loglike(np.array([[2.0, -3.0]])), [lnnorm])
+
+
+def test_device_ess_recipe_matches_host_recipe(engine_cls):
+    """ptg_get_autocovar_windows + the batched combination = analysis.report_effective_samples (the restatement pinned to the reference
+    build) applied to each cold chain's history, whole-run and ring-window forms, with thinning."""
+    from ptmcmc_b200.analysis import report_effective_samples
+    from tests.models import Spec
+    for se, steps in ((1, 9000), (3, 21000)):
+        spec = Spec("gauss", 2, 4, centers=[2, -3], halfwidths=[2, 3], save_every=se)
+        L = 12
+        e = engine_cls(spec.config(n_ladders=L, rng_mode=K.RNG_PHILOX, hist_capacity=spec.de_ni * 2 + steps // se * 6 // 5 + 600, record_level=K.RECORD_BASIC, save_every=se))
+        spec.setup(e); e.init_from_prior(); e.step(steps); e.synchronize()
+        ess, length = e.report_effective_samples_all()
+        cnt = e.get_counters()
+        for l in range(L):
+            h_ess, h_len = e.report_effective_samples(ladder=l)
+            assert length[l] == h_len and h_len > 0
+            assert abs(ess[l] - h_ess) <= 1e-9 * h_ess, (l, ess[l], h_ess)
+        nr = 4000
+        ess_w, len_w = e.report_effective_samples_all(window_records=nr)
+        for l in range(0, L, 5):
+            n = int(cnt["nsize"][l * 4])
+            x = e.get_history(l, 0, n - nr, nr, full=False)["x"]
+            h_ess, h_len = report_effective_samples(x, nr * se, n_init=0, add_every=se, width=se * 1000, every=se)
+            assert len_w[l] == h_len and abs(ess_w[l] - h_ess) <= 1e-9 * h_ess
+        with pytest.raises(Exception):
+            e.get_autocovar_windows(0, 1000, 50, [0, 1], 2)       # windows older than the chain
+        e.close()
