@@ -408,7 +408,7 @@ def main():
                    sokal_device=dict(value=sokal, tau_pt_iterations=float(np.median(tau_dev.max(axis=1))) * w["save_every"], window=nh,
                                      estimator="ptg_get_act: per cold chain N/tau, Sokal-windowed integrated autocorrelation time, min over parameters, mean over ladders"), host_check=dict(value=eps_host / w["save_every"] * pt_iter_per_s * L * world,
                    tau_pt_iterations=float(taus.max()) * w["save_every"], ladders_sampled=nl))
-        if nh > int(cnt["nsize"][::R].min()) - spec.config(n_ladders=1).n_init:
+        if nh > int(cnt["nsize"][::R].min()) - eng.cfg.n_init:
             ess["note"] = "the run is shorter than the analysis window: it still contains start-up prior draws, the ESS figure is not meaningful"
     except Exception as exc:  # analysis is not part of the timed path
         ess = dict(value=None, error=repr(exc))
