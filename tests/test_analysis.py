@@ -53,3 +53,25 @@ def test_reference_ess_recipe_on_ar1():
     ess, length = report_effective_samples(x, n, width=1000, every=1)
     assert length > n // 2
     assert abs(length / ess / ((1 + a) / (1 - a)) - 1) < 0.15
+
+
+def test_batched_recipe_equals_per_chain_recipe():
+    """effective_samples_from_windows (the combination used with the device lag statistics) against report_effective_samples chain by chain"""
+    from ptmcmc_b200.analysis import report_effective_samples, autocovar_windows, effective_samples_from_windows, recipe_geometry
+    rng = np.random.default_rng(11)
+    N, se = 24000, 2
+    chains = []
+    for a in (0.3, 0.9, 0.98, 0.0):
+        e = rng.normal(size=(N // se + 50, 2))
+        x = np.empty_like(e); x[0] = e[0]
+        for i in range(1, len(x)):
+            x[i] = a * x[i - 1] + e[i]
+        x[:, 1] = np.abs(x[:, 1])
+        chains.append(x)
+    width, swidth, n_win, lags = recipe_geometry(N, se * 1000, se)
+    assert n_win >= 3 and lags[0] == 0 and lags[1] == se
+    cm = [autocovar_windows(x, N, 50, se, width, se, 2, 0, 1.1) for x in chains]
+    ess, nwin = effective_samples_from_windows(np.stack([c[0] for c in cm]), np.stack([c[1] for c in cm]), lags, width, se, swidth)
+    for i, x in enumerate(chains):
+        e1, l1 = report_effective_samples(x, N, n_init=50, add_every=se, width=se * 1000, every=se)
+        assert l1 == nwin[i] * width and abs(e1 - ess[i]) <= 1e-12 * e1
