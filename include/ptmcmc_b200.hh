@@ -20,6 +20,7 @@
 #include <iostream>
 #include <sstream>
 #include <string>
+#include <utility>
 #include <valarray>
 #include <vector>
 extern "C" {
@@ -436,6 +437,68 @@ public:
     check(ptg_get_swap_stats(h, sc.data(), sa.data(), nullptr, nullptr, nullptr, nullptr), "ptg_get_swap_stats");
     swap_count.assign(sc.begin() + (size_t)ladder * (Ntemps - 1), sc.begin() + (size_t)(ladder + 1) * (Ntemps - 1));
     swap_accept.assign(sa.begin() + (size_t)ladder * (Ntemps - 1), sa.begin() + (size_t)(ladder + 1) * (Ntemps - 1));
+  }
+  // chain::report_effective_samples(imax, width, every, esslimit < 0) (chain.cc:457-481, 549-643) for one chain -> (ess, useful length):
+  // the windowed lag statistics come from the device in the reference's summation order (ptg_get_autocovar_windows), the combination
+  // below is chain::compute_effective_samples (chain.cc:340-416).  The run loop calls it as (-1, save_every*1000, save_every), ptmcmc.cc:645.
+  // The whole run must still be in the history ring.
+  std::pair<double, int> report_effective_samples(int imax = -1, int width = 40000, int every = 100, int ladder = 0, int rung = 0) {
+    sync_counters();
+    const size_t ci = (size_t)ladder * Ntemps + rung;
+    const long long istep = nhist[ci];
+    const int se = cfg.save_every;
+    while (width < istep * 0.05) width *= 2;
+    if (imax < 0 || imax > dim) imax = dim;
+    if (imax > 20) imax = 20;
+    if (every < 1) every = 1;
+    if (every != se) error_handler()("gpu_parallel_tempering_chains::report_effective_samples: `every` must equal add_every_N (as in the run loop)");
+    const int minburn = 2, maxbins = 20;
+    while ((long long)width * (maxbins + minburn) < istep) width *= 2;
+    const int swidth = width / every;
+    width = swidth * every;
+    const int Nwin = (int)(istep / width) - minburn;
+    if (Nwin < 1 || imax < 1) return std::make_pair(0.0, 0);
+    std::vector<int> lags(1, 0);                                      // logarithmic lag grid, dlag = 1.1 (chain.cc:207-222)
+    { double fac = 1; int idx = 1; while (idx < minburn * swidth) { lags.push_back(every * idx); const int last = idx; while (last == idx) { fac *= 1.1; idx = (int)fac; } } }
+    const int Nlag = (int)lags.size();
+    std::vector<int32_t> lag_rec(Nlag);
+    for (int j = 0; j < Nlag; j++) lag_rec[j] = lags[j] / se;
+    std::vector<int64_t> end_rec((size_t)cfg.n_ladders);
+    for (int l = 0; l < cfg.n_ladders; l++) end_rec[l] = Ninit + nhist[(size_t)l * Ntemps + rung] / se;
+    const size_t per = (size_t)imax * Nwin * Nlag;
+    std::vector<double> means((size_t)cfg.n_ladders * per), covar(means.size());
+    check(ptg_get_autocovar_windows(h, rung, swidth, Nwin, Nlag, lag_rec.data(), end_rec.data(), imax, means.data(), covar.data()), "ptg_get_autocovar_windows");
+    const double *M = means.data() + (size_t)ladder * per, *C = covar.data() + (size_t)ladder * per;
+    auto at = [&](const double *a, int f, int k, int j) { return a[((size_t)f * Nwin + k) * Nlag + j]; };
+    double ess_max = 0; int nwin_max = 0;
+    for (int nwin = 1; nwin <= Nwin; nwin++) {
+      double ess = 1e100;
+      for (int f = 0; f < imax; f++) {
+        double sum = 0;
+        for (int i = Nwin - nwin; i < Nwin; i++) sum += at(M, f, i, 0);
+        const double mean = sum / nwin;
+        int last_lag = 0; double ac_len = 1.0, lastcorr = 1, dacl = 0;
+        for (int il = 1; il < Nlag; il++) {
+          double num = 0, denom = 0;
+          for (int iw = Nwin - nwin; iw < Nwin; iw++) {
+            const double dmean = mean - at(M, f, iw, il), dmean0 = mean - at(M, f, iw, 0);
+            num += (at(C, f, iw, il) + dmean * dmean) * swidth;
+            denom += (at(C, f, iw, 0) + dmean0 * dmean0) * swidth;
+          }
+          const double corr = num / denom;
+          if (lastcorr < 0 && corr < 0) { ac_len -= dacl; break; }   // initially-positive-sequence cut
+          lastcorr = corr;
+          dacl = 2.0 * (lags[il] - last_lag) * corr;
+          ac_len += dacl;
+          last_lag = lags[il];
+        }
+        double essi = nwin * (double)width / ac_len;
+        if (ac_len < every) essi = nwin * (double)width / 3.0 / every;
+        if (essi < ess) ess = essi;
+      }
+      if (ess > ess_max) { ess_max = ess; nwin_max = nwin; }
+    }
+    return std::make_pair(ess_max, width * nwin_max);
   }
   long long total_steps() { int64_t t = 0; check(ptg_get_total_steps(h, &t), "ptg_get_total_steps"); return t; }
   void checkpoint(const std::string &path) { check(ptg_checkpoint(h, path.c_str()), "ptg_checkpoint"); }

@@ -70,6 +70,10 @@ int main(int argc, char **argv) {
   state s = ptc.getState();
   printf("facade_driver: size=%d step=%d total=%lld lpost=%.17g llike=%.17g invtemp_hot=%.17g x0=%.17g first=%.17g\n", ptc.size(), ptc.getStep(),
          ptc.total_steps(), ptc.getLogPost(), ptc.getLogLike(), ptc.invTemp(Ntemps - 1), s.get_param(0), ptc.getState(0).get_param(0));
+  if (nsteps >= 6000) { // the run loop's effective-sample report (ptmcmc.cc:645)
+    std::pair<double, int> el = ptc.report_effective_samples(-1, 1000, 1, 0, 0);
+    printf("facade_ess: ess=%.17g length=%d\n", el.first, el.second);
+  }
   delete like;
   return 0;
 }

@@ -81,3 +81,23 @@ def test_facade_driver_matches_engine(model, dim, R, steps, L, evolve, tmp_path,
     assert float(summary["lpost"]) == cur["lpost"][0] and float(summary["x0"]) == cur["x"][0, 0]
     assert float(summary["invtemp_hot"]) == cur["beta"][R - 1]
     assert float(summary["first"]) == e.get_history(0, 0, 50 * dim, 1)["x"][0, 0]
+
+
+@pytest.mark.gpu
+def test_facade_effective_samples_match_python_recipe(tmp_path, engine_cls):
+    """gpu_parallel_tempering_chains::report_effective_samples (device lag statistics + the C++ combination of chain.cc:340-416) against
+    Engine.report_effective_samples (the numpy restatement pinned to the reference build) on the same Philox run"""
+    exe = build_driver(tmp_path)
+    out = os.path.join(str(tmp_path), "chain.dat")
+    dim, R, steps, L = 2, 4, 7000, 2
+    r = subprocess.run([exe, "gauss", str(dim), str(R), str(steps), str(L), out, "0.0"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    line = [x for x in r.stdout.splitlines() if x.startswith("facade_ess:")][0]
+    kv = dict(t.split("=") for t in line.split(":", 1)[1].split())
+    c = np.array([2.0 - 5.0 * (i % 2) for i in range(dim)]); hw = np.array([2.0 + i for i in range(dim)])
+    spec = Spec("gauss", dim, R, centers=c, halfwidths=hw)
+    e = engine_cls(spec.config(n_ladders=L, rng_mode=K.RNG_PHILOX, hist_capacity=50 * dim + 2 * steps + 8, seed=0xB2000003, record_level=K.RECORD_BASIC))
+    spec.setup(e); e.init_from_prior(); e.step(steps); e.synchronize()
+    ess, length = e.report_effective_samples(ladder=0)
+    assert int(kv["length"]) == length and length > 0
+    assert abs(float(kv["ess"]) - ess) <= 1e-9 * ess
