@@ -503,11 +503,18 @@ static int upload_model(ptg_handle *h) {
       for (int r = 0; r < m.n_rungs; r++)
         if (h->betas[(size_t)l * m.n_rungs + r] != h->betas[r]) return fail(PTG_EINVAL, "Tpow > 0 needs identical ladders");
   int rc = 0;
-  rc |= dev_alloc(h, &h->d_lparams, h->lparams.size(), false); rc |= dev_alloc(h, &h->d_ldata, h->ldata.size(), false);
+  rc |= dev_alloc(h, &h->d_lparams, h->lparams.size(), false); // data chi-squared likelihoods: the reciprocals of the N variances ride behind the data block (x | y | S | 1/S); the warp-per-chain
+  // production path multiplies by them, the tape-replay kernels keep the reference's division
+  std::vector<double> ldata_up = h->ldata;
+  if ((m.like_kind == PTG_LIKE_POLY_CHI2 || m.like_kind == PTG_LIKE_SINUSOID_CHI2) && !h->ldata.empty()) {
+    const size_t N = h->ldata.size() / 3;
+    for (size_t i = 0; i < N; i++) ldata_up.push_back(1.0 / h->ldata[2 * N + i]);
+  }
+  rc |= dev_alloc(h, &h->d_ldata, ldata_up.size(), false);
   rc |= dev_alloc(h, &h->d_prop_data, pdata.size(), false); rc |= dev_alloc(h, &h->d_bins, bins.size(), false);
   if (rc) return PTG_ENOMEM;
   CUDA_TRY(cudaMemcpyAsync(h->d_lparams, h->lparams.data(), h->lparams.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  if (!h->ldata.empty()) CUDA_TRY(cudaMemcpyAsync(h->d_ldata, h->ldata.data(), h->ldata.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (!ldata_up.empty()) { CUDA_TRY(cudaMemcpyAsync(h->d_ldata, ldata_up.data(), ldata_up.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream)); CUDA_TRY(cudaStreamSynchronize(h->stream)); }
   CUDA_TRY(cudaMemcpyAsync(h->d_prop_data, pdata.data(), pdata.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(cudaMemcpyAsync(h->d_bins, bins.data(), bins.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   m.lparams = h->d_lparams; m.ldata = h->d_ldata; m.prop_data = h->d_prop_data; m.bins = h->d_bins;

@@ -183,6 +183,28 @@ __device__ __forceinline__ double xsum_tree(const double v[CPL]) {
 // DATA loop spread over the lanes of the chain's warp: lane l takes points l, l+32, ...; the partial sums meet in a shuffle
 // tree.  Used when the batch has too few chains to fill the GPU with one thread per chain (BASELINE config B: 16 384 chains).
 // dim <= 32 (CPL = 1): parameter j lives in lane j.
+// sum over this lane's points of (poly(x_i) - y_i)^2 / S_i for a polynomial with DD coefficients, the reference's Horner-free
+// evaluation order `y += xn*c_j; xn *= x_i` (poly_example.cc:97-101); four independent partial sums per lane; 1/S_i precomputed
+template <int DD>
+__device__ __forceinline__ double xpoly_partial(const double *__restrict__ xs, const double *__restrict__ ys, const double *__restrict__ iS, long long N, const double *cj, int lane) {
+  double p4[4] = {0, 0, 0, 0};
+  for (long long i0 = lane; i0 < N; i0 += 128) {
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const long long i = i0 + 32 * u;
+      if (i < N) {
+        const double xi = __ldg(xs + i);
+        double y = 0, xn = 1;
+#pragma unroll
+        for (int j = 0; j < DD; j++) { y += xn * cj[j]; xn *= xi; }
+        const double dd = y - __ldg(ys + i);
+        p4[u] += dd * dd * __ldg(iS + i);
+      }
+    }
+  }
+  return (p4[0] + p4[1]) + (p4[2] + p4[3]);
+}
+
 __device__ __forceinline__ double xlike_data_parallel(const PtgModel &m, double xmine, int lane) {
   const int D = m.dim;
   const long long N = m.n_ldata / 3;
@@ -193,23 +215,12 @@ __device__ __forceinline__ double xlike_data_parallel(const PtgModel &m, double 
     double cj[16];
 #pragma unroll
     for (int j = 0; j < 16; j++) cj[j] = __shfl_sync(0xffffffffu, xmine, j);
-    // four independent partial sums per lane: the per-point work (D multiply-adds and an fp64 division) pipelines
-    double p4[4] = {0, 0, 0, 0};
-    for (long long i0 = lane; i0 < N; i0 += 128) {
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const long long i = i0 + 32 * u;
-        if (i < N) {
-          const double xi = __ldg(xs + i);
-          double y = 0, xn = 1;
-#pragma unroll
-          for (int j = 0; j < 16; j++) if (j < D) { y += xn * cj[j]; xn *= xi; }
-          const double dd = y - __ldg(ys + i);
-          p4[u] += dd * dd / __ldg(S + i);
-        }
-      }
+    const double *__restrict__ iS = m.ldata + 3 * N; // reciprocals of the variances (uploaded behind the data block)
+    switch (D) { // the coefficient count as a compile-time constant: no predicated-off multiply-adds in the inner loop
+#define X(DD) case DD: part = xpoly_partial<DD>(xs, ys, iS, N, cj, lane); break;
+      X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
+#undef X
     }
-    part = (p4[0] + p4[1]) + (p4[2] + p4[3]);
   } else {
     double cj[18];
 #pragma unroll
@@ -220,7 +231,7 @@ __device__ __forceinline__ double xlike_data_parallel(const PtgModel &m, double 
 #pragma unroll
       for (int k = 0; k + 2 < 18; k += 3) if (k + 2 < D) y += cj[k] * sin(2 * PTG_PI * cj[k + 1] * ti + cj[k + 2]);
       const double dd = y - __ldg(ys + i);
-      part += dd * dd / __ldg(S + i);
+      part += dd * dd * __ldg(m.ldata + 3 * N + i);
     }
   }
 #pragma unroll
