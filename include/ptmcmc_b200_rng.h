@@ -56,8 +56,13 @@
 #define PTG_HD static inline
 #endif
 
+#define PTG_PRAGMA_(x) _Pragma(#x)
+#define PTG_PRAGMA_UNROLL(n) PTG_PRAGMA_(unroll n)
 PTG_HD void ptg_philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                               uint32_t out[4]) {
+#if defined(__CUDA_ARCH__) && defined(PTG_PHILOX_UNROLL)
+  PTG_PRAGMA_UNROLL(PTG_PHILOX_UNROLL)
+#endif
   for (int r = 0; r < 10; r++) {
     uint64_t p0 = (uint64_t)PTG_PHILOX_M0 * c0;
     uint64_t p1 = (uint64_t)PTG_PHILOX_M1 * c2;

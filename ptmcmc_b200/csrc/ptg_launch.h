@@ -13,6 +13,7 @@ static inline size_t ptg_ladder_shared_bytes(int D, int R) {
 #define PTG_DIM_LIST(X) X(3) X(5) X(9)
 #else
 #define PTG_DIM_LIST(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(12) X(16)
+#endif
 // CTA size of the production kernel (ptg_fstep_kernel) for a batch of `warps` ladder-warps
 static inline int ptg_fstep_threads(long long warps) {
   static const int forced = [] { const char *e = getenv("PTG_FSTEP_THREADS"); return e ? atoi(e) : 0; }(); // experiments only
@@ -33,7 +34,6 @@ static inline int ptg_fstep_grid_is_resident(long long warps) {
   return blocks <= (long long)(896 / threads) * sms ? 1 : 0;
 }
 
-#endif
 #define PTG_DECLARE(D)                                                                                                      \
   cudaError_t ptg_launch_step_d##D(int mode, const PtgModel &m, const PtgState &s, long long step0, int n_steps, int lpb,   \
                                    size_t smem, cudaStream_t st);                                                           \
