@@ -221,8 +221,9 @@ __device__ __forceinline__ void fx_swap(const PtgModel &m, const PtgState &s, co
   }
 }
 
-// XCHG: compiled with the rung-boundary exchange prologue / epilogue (ptg_step_exchange); the plain instantiation carries none of it
-template <int D, bool XCHG>
+// XCHG: 0 = plain; 1 = with the rung-boundary exchange in the prologue / epilogue (ptg_step_exchange); 2 = also inside the iteration loop.
+// Separate instantiations: each form's extra code costs registers and stack, and the plain kernel carries none of it
+template <int D, int XCHG>
 __global__ void __launch_bounds__(PTG_FSTEP_MAX_THREADS, 1) ptg_fstep_kernel(const __grid_constant__ PtgModel m, PtgState s, long long step0, int n_steps, int W, const __grid_constant__ PtgXchg xc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int R = m.n_rungs, NP = m.n_props;
@@ -621,7 +622,7 @@ __global__ void __launch_bounds__(PTG_FSTEP_MAX_THREADS, 1) ptg_fstep_kernel(con
     // in-launch exchange: after every xc.every-th iteration (not the launch's last, whose publish the epilogue does) publish the
     // edges and run the boundary trial as soon as the neighbour's same ladder has published -- warps wait one by one, the rest of
     // the SM keeps stepping.  The host only uses this when every CTA of the grid is resident (one wave on each GPU).
-    if (XCHG && xc.on && xc.every > 0 && it + 1 < n_steps && (it + 1) % xc.every == 0) {
+    if (XCHG == 2 && xc.on && xc.every > 0 && it + 1 < n_steps && (it + 1) % xc.every == 0) {
       if (active) {
         fx_publish<D>(m, xc, xp, ch, ladder, rung, R);
         fx_swap<D>(m, s, xc, xp, ch, chain, ladder, gl, rung, R, cnt, err);

@@ -38,8 +38,9 @@ static cudaError_t launch_fstep_t(const PtgModel &m, const PtgState &s, long lon
   const int wpb = threads / 32;
   const int blocks = (int)((warps + wpb - 1) / wpb);
   const size_t smem = (size_t)m.n_rungs * m.n_props * sizeof(double) + (size_t)m.n_props * sizeof(FProp) + (size_t)PTG_FC_STRIDE * threads * sizeof(int);
-  if (xc.on) ptg_fstep_kernel<D, true><<<blocks, threads, smem, st>>>(m, s, step0, n_steps, W, xc);
-  else ptg_fstep_kernel<D, false><<<blocks, threads, smem, st>>>(m, s, step0, n_steps, W, xc);
+  if (xc.on && xc.every > 0) ptg_fstep_kernel<D, 2><<<blocks, threads, smem, st>>>(m, s, step0, n_steps, W, xc);
+  else if (xc.on) ptg_fstep_kernel<D, 1><<<blocks, threads, smem, st>>>(m, s, step0, n_steps, W, xc);
+  else ptg_fstep_kernel<D, 0><<<blocks, threads, smem, st>>>(m, s, step0, n_steps, W, xc);
   return cudaGetLastError();
 }
 template <int D, int MODE>
