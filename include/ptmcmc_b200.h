@@ -43,6 +43,7 @@ extern "C" {
 #define PTG_ETAPE (-3)    /* injected tape exhausted              */
 #define PTG_ESTUCK (-4)   /* init could not draw a valid state (chain.cc:854-866) */
 #define PTG_ENOMEM (-5)
+#define PTG_EXCHANGE (-6) /* a cross-GPU boundary exchange was aborted (neighbour missing / watchdog): the handle refuses further steps */
 
 /* boundary types: states.hh:35-38 */
 enum { PTG_BOUND_OPEN = 0, PTG_BOUND_LIMIT = 1, PTG_BOUND_REFLECT = 2, PTG_BOUND_WRAP = 3 };
@@ -56,7 +57,10 @@ enum {
   PTG_LIKE_POLY_CHI2 = 3,     /* chi^2 of polynomial model over data         (bayesian.hh:595-622, poly_example.cc:85-106) */
   PTG_LIKE_SINUSOID_CHI2 = 4, /* chi^2 of sum of sinusoids over data         (same chi^2) */
   PTG_LIKE_GAUSS_FULLCOV = 5, /* like0 - x^T Cinv x / 2                      (cython/exampleGaussian.py:103-109) */
-  PTG_LIKE_HOST_CALLBACK = 6  /* the caller's own likelihood, evaluated on the host for all chains at once (ptg_register_evaluate_log) */
+  PTG_LIKE_HOST_CALLBACK = 6, /* the caller's own likelihood, evaluated on the host for all chains at once (ptg_register_evaluate_log) */
+  PTG_LIKE_SHELL2D = 7,       /* 2-D double Gaussian shell, reflected in p0  (example.cc:147-222)  params: lnnormfac, twosigmasq, r0, x0[2] */
+  PTG_LIKE_SHELLS = 8         /* d-dim Gaussian shell pair (one or two, optionally in ln p0) (example.cc:226-421)
+                                 params: lnnormfac, twosigmasq, r0, x0, sigmapoverm, lnsigmapoverm, logx (0/1) */
 };
 /* proposal kinds (members of a proposal_distribution_set, proposal_distribution.cc:99-129) */
 enum { PTG_PROP_DE = 1, PTG_PROP_GAUSS = 2, PTG_PROP_PRIOR_DRAW = 3 };
@@ -167,7 +171,8 @@ int ptg_synchronize(ptg_handle *h);
  * Philox draws, PTG_KERNEL_WARP for tape replay), longer ladders the shared-memory kernel (PTG_KERNEL_SHARED).
  * ptg_select_kernel pins PTG_KERNEL_WARP or PTG_KERNEL_SHARED where they apply (tests / profiling: in Philox mode all
  * three produce bit-identical chains); ptg_get_launch_count reports how many step kernels this handle has launched. */
-enum { PTG_KERNEL_AUTO = 0, PTG_KERNEL_SHARED = 1, PTG_KERNEL_WARP = 2, PTG_KERNEL_FAST = 3 };
+enum { PTG_KERNEL_AUTO = 0, PTG_KERNEL_SHARED = 1, PTG_KERNEL_WARP = 2, PTG_KERNEL_FAST = 3,
+       PTG_KERNEL_FAST_GENERAL = 4 /* the production kernel's general instantiation even where a streamlined one applies (tests: bit-identical) */ };
 int ptg_select_kernel(ptg_handle *h, int32_t kernel);
 int ptg_get_launch_count(ptg_handle *h, int64_t *n);
 /* same, end-to-end with host buffers: steps, then copies the cold chains' newest `n_out` stored samples
@@ -203,7 +208,9 @@ int ptg_get_trace(ptg_handle *h, int64_t first, int64_t count, double *lhr, int3
 /* total history appends (= tempered chain-steps, the BASELINE metric) since init */
 int ptg_get_total_steps(ptg_handle *h, int64_t *total);
 /* device pointers + stream for zero-copy consumers (torch / NCCL gather of cold samples): history records
- * hist_dev[chain][hist_capacity][dim+2] = (x[dim], lpost, llike), *hist_stride = doubles per chain;
+ * hist_dev[chain][hist_capacity][hx] = x[dim] padded to hx doubles (hx = dim rounded up to a multiple of 4 for dim <= 16, whole
+ * 32-byte sectors per record; hx = dim for dim > 16), *hist_stride = hist_capacity * hx = doubles per chain; (lpost, llike) of the
+ * same slot live in a separate ring that ptg_get_history reads;
  * cur_x_dev[dim][n_chains] */
 int ptg_get_device_views(ptg_handle *h, void **hist_dev, void **cur_x_dev, void **stream, int64_t *hist_stride);
 /* run all further work of this handle on a caller-owned cudaStream_t (e.g. torch's current stream) */
@@ -268,6 +275,11 @@ int ptg_xchg_export(ptg_handle *h, void *ipc_handle_64_bytes, void **local_ptr);
 int ptg_xchg_connect(ptg_handle *h, const void *colder, const void *hotter, int32_t handles_are_ipc, uint64_t shared_seed,
                      int64_t colder_boundary_id, int64_t hotter_boundary_id);
 int ptg_step_exchange(ptg_handle *h, int64_t n_steps, int32_t every, int32_t apply_pending, int32_t publish);
+/* Watchdog of the fused exchange.  A boundary wait inside a launch is unbounded by itself; the host bounds it: when a launch
+ * overstays the caller's deadline (a neighbour rank died or never launched), ptg_xchg_abort -- callable from another host thread
+ * while ptg_synchronize blocks -- makes every wait give up.  The launch then ends, ptg_synchronize returns PTG_EXCHANGE and the handle
+ * refuses further steps: the skipped trial left the boundary pair inconsistent, continuing would duplicate or lose a state. */
+int ptg_xchg_abort(ptg_handle *h);
 
 /* FP64 peak microbenchmarks on `device` (the FP64 roofline denominators): out[0] = DFMA TFLOP/s,
  * out[1] = DMUL+DADD pairs (the engine's unfused arithmetic) TFLOP/s, out[2] = DMMA (mma.sync.m8n8k4.f64) TFLOP/s, out[3] = SM count */

@@ -16,12 +16,12 @@ MAX_RUNGS = 64
 # enums (include/ptmcmc_b200.h)
 BOUND_OPEN, BOUND_LIMIT, BOUND_REFLECT, BOUND_WRAP = 0, 1, 2, 3
 PRIOR_UNIFORM, PRIOR_GAUSSIAN, PRIOR_POLAR, PRIOR_COPOLAR, PRIOR_LOG = 1, 2, 3, 4, 5
-LIKE_FLAT, LIKE_GAUSS_ISO, LIKE_SINES, LIKE_POLY_CHI2, LIKE_SINUSOID_CHI2, LIKE_GAUSS_FULLCOV, LIKE_HOST_CALLBACK = 0, 1, 2, 3, 4, 5, 6
+LIKE_FLAT, LIKE_GAUSS_ISO, LIKE_SINES, LIKE_POLY_CHI2, LIKE_SINUSOID_CHI2, LIKE_GAUSS_FULLCOV, LIKE_HOST_CALLBACK, LIKE_SHELL2D, LIKE_SHELLS = 0, 1, 2, 3, 4, 5, 6, 7, 8
 PROP_DE, PROP_GAUSS, PROP_PRIOR_DRAW = 1, 2, 3
 SWAP_REFERENCE, SWAP_EVEN_ODD = 0, 1
 RNG_PHILOX, RNG_TAPE = 0, 1
 RECORD_BASIC, RECORD_FULL = 0, 1
-KERNEL_AUTO, KERNEL_SHARED, KERNEL_WARP, KERNEL_FAST = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_SHARED, KERNEL_WARP, KERNEL_FAST, KERNEL_FAST_GENERAL = 0, 1, 2, 3, 4
 TRACE_TYPE_MASK, TRACE_ACCEPT, TRACE_INVALID, TRACE_SWAPPED, TRACE_NOLIKE = 0xFF, 0x100, 0x200, 0x400, 0x800
 
 
@@ -222,6 +222,10 @@ class CApi:
         self._keep_xchg = (arg(colder), arg(hotter))
         self._call("xchg_connect", self.h, self._keep_xchg[0], self._keep_xchg[1], C.c_int32(1 if ipc else 0), C.c_uint64(shared_seed),
                    C.c_int64(colder_boundary_id), C.c_int64(hotter_boundary_id))
+
+    def xchg_abort(self):
+        """watchdog: every boundary wait of this engine gives up (callable from another thread while synchronize blocks)"""
+        self._call("xchg_abort", self.h)
 
     def step_exchange(self, n_steps, apply_pending, publish, every=0):
         self._call("step_exchange", self.h, C.c_int64(n_steps), C.c_int32(every), C.c_int32(1 if apply_pending else 0), C.c_int32(1 if publish else 0))

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <vector>
 #include "ptg_launch.h"
 #include "ptg_device.cuh"
@@ -55,7 +56,9 @@ struct ptg_handle {
   std::vector<double> cb_x, cb_like, cb_xc, cb_lc; std::vector<int32_t> cb_flags; std::vector<int64_t> cb_idx;
   // rung-sharded ladders with the exchange fused into the step kernel (ptg_xchg_*)
   void *d_xchg; size_t xchg_bytes; void *peer_lo, *peer_hi; bool peer_lo_ipc, peer_hi_ipc;
-  PtgXchg xchg; const PtgXchg *xchg_launch; // xchg_launch: parameters of the launch in flight through ptg_step (null = plain step)
+  PtgXchg xchg, xchg_cur; bool xchg_launch;  // xchg_cur: parameters of the exchange launch in flight through ptg_step (xchg_launch = false: plain step)
+  int *h_abort; int *d_abort;               // watchdog word of the fused exchange (mapped pinned host memory) and its device alias
+  bool dead;                                // a boundary exchange was aborted: the ladders of this rank are out of step with their neighbours
 };
 
 template <typename T>
@@ -114,9 +117,10 @@ __global__ void ptg_gather_cold_kernel(PtgModel m, PtgState s, int n_out, double
   long long logical = nsize - n_out + k; // k-th of the newest n_out
   const int D = m.dim;
   if (logical < 0) { for (int i = 0; i < D; i++) out_x[t * D + i] = CUDART_NAN; out_lp[t] = CUDART_NAN; out_ll[t] = CUDART_NAN; return; }
-  const double *h = s.hist + (c * m.hist_cap + (logical % m.hist_cap)) * (D + 2);
+  const long long rec = c * m.hist_cap + (logical % m.hist_cap);
+  const double *h = s.hist + rec * m.hx;
   for (int i = 0; i < D; i++) out_x[t * D + i] = h[i];
-  out_lp[t] = h[D]; out_ll[t] = h[D + 1];
+  out_lp[t] = s.hist_lp[2 * rec]; out_ll[t] = s.hist_lp[2 * rec + 1];
 }
 
 // [chain][dim] -> [dim][chain]
@@ -148,12 +152,19 @@ extern "C" int ptg_create(const ptg_config *cfg, ptg_handle **out) {
     return fail(PTG_ECUDA, "no CUDA device: %s (the ptg engine has no CPU fallback)", e != cudaSuccess ? cudaGetErrorString(e) : "count=0");
   if (cfg->device < 0 || cfg->device >= ndev) return fail(PTG_EINVAL, "device %d out of range (%d devices)", cfg->device, ndev);
   CUDA_TRY(cudaSetDevice(cfg->device));
+  {
+    // DE gathers read single 32-byte sectors at random ring slots: ask L2 not to fetch a second sector with every miss (the default
+    // fetch granularity is 64 bytes).  A hint; PTG_L2_FETCH_GRANULARITY = 32 | 64 | 128 overrides it for experiments.
+    const char *eg = getenv("PTG_L2_FETCH_GRANULARITY");
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, eg ? (size_t)atoi(eg) : (size_t)32);
+    cudaGetLastError();
+  }
   bool supported_dim = false;
 #define X(D) if (cfg->dim == D) supported_dim = true;
   PTG_DIM_LIST(X)
 #undef X
   if (!supported_dim && cfg->dim <= PTG_TPC_MAX_DIM)
-    return fail(PTG_EINVAL, "dim=%d: thread-per-chain kernels are instantiated for 1-10,12,16; dims 17-128 run the warp-per-chain kernels", cfg->dim);
+    return fail(PTG_EINVAL, "dim=%d: thread-per-chain kernels are instantiated for 1-16; dims 17-128 run the warp-per-chain kernels", cfg->dim);
   if (cfg->dim > PTG_TPC_MAX_DIM && cfg->n_rungs > 32) return fail(PTG_EINVAL, "dim > 16 needs n_rungs <= 32 (one CTA per ladder, one warp per rung)");
 
   ptg_handle *h = new ptg_handle();
@@ -165,6 +176,7 @@ extern "C" int ptg_create(const ptg_config *cfg, ptg_handle **out) {
   h->have_space = h->have_prior = h->have_like = h->have_props = h->inited = h->model_uploaded = false; h->model_dirty = true;
   h->d_lparams = h->d_ldata = h->d_prop_data = h->d_bins = nullptr;
   h->d_tape_u = h->d_tape_z = nullptr; h->d_u_end = h->d_z_end = nullptr;
+  h->xchg_launch = false; h->h_abort = h->d_abort = nullptr; h->dead = false; h->d_xchg = nullptr; h->peer_lo = h->peer_hi = nullptr; h->peer_lo_ipc = h->peer_hi_ipc = false;
   h->kernel_choice = PTG_KERNEL_AUTO; h->launches = 0; h->cb_fn = nullptr; h->cb_user = nullptr; h->d_attempt = h->d_nopen = nullptr; h->istep = 0; h->Tpow = 0; h->d_scratch = nullptr; h->scratch_bytes = 0; h->h_pinned = nullptr; h->pinned_bytes = 0;
   cudaError_t es = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (es != cudaSuccess) { delete h; return fail(PTG_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(es)); }
@@ -195,7 +207,8 @@ extern "C" int ptg_create(const ptg_config *cfg, ptg_handle **out) {
   rc |= dev_alloc(h, &s.lprior, n); rc |= dev_alloc(h, &s.beta, n); rc |= dev_alloc(h, &s.map_lpost, n); rc |= dev_alloc(h, &s.map_x, n * d);
   rc |= dev_alloc(h, &s.nhist, n); rc |= dev_alloc(h, &s.nsize, n); rc |= dev_alloc(h, &s.ntries, n); rc |= dev_alloc(h, &s.naccept, n);
   rc |= dev_alloc(h, &s.last_type, n);
-  rc |= dev_alloc(h, &s.hist, n * (size_t)cap * (d + 2), false);
+  m.hx = PTG_HX(cfg->dim);
+  rc |= dev_alloc(h, &s.hist, n * (size_t)cap * (size_t)m.hx, false); rc |= dev_alloc(h, &s.hist_lp, n * (size_t)cap * 2, false);
   if (m.record_full) {
     rc |= dev_alloc(h, &s.hist_acc, n * (size_t)cap, false); rc |= dev_alloc(h, &s.hist_beta, n * (size_t)cap, false);
     rc |= dev_alloc(h, &s.hist_type, n * (size_t)cap, false);
@@ -226,6 +239,7 @@ extern "C" int ptg_destroy(ptg_handle *h) {
   if (h->peer_hi && h->peer_hi_ipc) cudaIpcCloseMemHandle(h->peer_hi);
   for (void *p : h->allocs) cudaFree(p);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
+  if (h->h_abort) cudaFreeHost(h->h_abort);
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
   return 0;
@@ -302,6 +316,8 @@ extern "C" int ptg_set_likelihood(ptg_handle *h, int32_t kind, const double *par
   case PTG_LIKE_FLAT: need = 0; break;
   case PTG_LIKE_GAUSS_ISO: need = 2 + d; break;
   case PTG_LIKE_SINES: need = 2 + 3 * d; break;
+  case PTG_LIKE_SHELL2D: need = 5; break;
+  case PTG_LIKE_SHELLS: need = 7; break;
   case PTG_LIKE_POLY_CHI2: case PTG_LIKE_SINUSOID_CHI2: case PTG_LIKE_GAUSS_FULLCOV: need = 1; break;
   case PTG_LIKE_HOST_CALLBACK: return fail(PTG_EINVAL, "use ptg_register_evaluate_log for a host-callback likelihood");
   default: return fail(PTG_EINVAL, "unknown likelihood kind %d", kind);
@@ -310,6 +326,8 @@ extern "C" int ptg_set_likelihood(ptg_handle *h, int32_t kind, const double *par
   if ((kind == PTG_LIKE_POLY_CHI2 || kind == PTG_LIKE_SINUSOID_CHI2) && (n_data <= 0 || n_data % 3 || !data))
     return fail(PTG_EINVAL, "chi2 likelihoods need data = [x[N], y[N], var[N]] (n_data = 3N)");
   if (kind == PTG_LIKE_SINUSOID_CHI2 && d % 3) return fail(PTG_EINVAL, "sinusoid model needs dim = 3k");
+  if (kind == PTG_LIKE_SHELL2D && d != 2) return fail(PTG_EINVAL, "the 2-D shell likelihood needs dim = 2 (example.cc:147-222)");
+  if ((kind == PTG_LIKE_SHELL2D || kind == PTG_LIKE_SHELLS) && h->wide) return fail(PTG_EINVAL, "shell likelihoods run in the thread-per-chain kernels (dim <= 16)");
   if (kind == PTG_LIKE_GAUSS_FULLCOV && (n_data != (int64_t)d * d || !data)) return fail(PTG_EINVAL, "fullcov needs Cinv[dim*dim]");
   h->lparams.assign(params, params + (n_params > 0 ? n_params : 0));
   if (h->lparams.empty()) h->lparams.push_back(0.0);
@@ -550,6 +568,10 @@ static int check_device_error(ptg_handle *h) {
   if (e == 1) return fail(PTG_ETAPE, "injected tape exhausted");
   if (e == 2) return fail(PTG_EINVAL, "proposal set: no member ready");
   if (e == 4) return fail(PTG_ESTUCK, "init: cannot draw a valid state");
+  if (e == PTG_ERR_XCHG_TIMEOUT) {
+    h->dead = true; // the trial was skipped on this side only: the boundary pair is no longer consistent, stop stepping
+    return fail(PTG_EXCHANGE, "cross-GPU boundary exchange aborted (neighbour did not publish before the watchdog fired): this handle accepts no further steps");
+  }
   if (e) return fail(PTG_ECUDA, "device error flag %d", e);
   return 0;
 }
@@ -650,6 +672,33 @@ static int warp_kernel_width(const ptg_handle *h) {
 // which step kernel runs: PTG_KERNEL_FAST (Philox draws, <= 32 rungs), PTG_KERNEL_WARP (tape replay, <= 32 rungs),
 // PTG_KERNEL_SHARED otherwise; ptg_select_kernel can pin WARP or SHARED where they apply
 static const PtgXchg xchg_off = {};
+// Data chi-squared likelihoods (BASELINE configs B, C2) run one WARP per chain with the data loop spread over its lanes
+// (ptg_wide_mma.cuh) whenever the run is a Philox run with automatic kernel selection.  The rule depends on the WORKLOAD only, never on
+// the batch size: the warp-per-chain reduction sums in a different order than the thread-per-chain loop, so a size-dependent choice
+// would make a ladder's samples depend on how many ladders share its GPU (shard vs full batch).
+static bool routes_warp_per_chain(const ptg_handle *h) {
+  const PtgModel &m = h->m;
+  const bool data_like = m.like_kind == PTG_LIKE_POLY_CHI2 || m.like_kind == PTG_LIKE_SINUSOID_CHI2;
+  bool has_prior_draw = false;
+  for (const HostProp &hp : h->props) if (hp.p.kind == PTG_PROP_PRIOR_DRAW) has_prior_draw = true;
+  return !h->wide && data_like && !has_prior_draw && h->cfg.rng_mode == PTG_RNG_PHILOX && h->kernel_choice == PTG_KERNEL_AUTO && m.n_rungs <= 32 &&
+         m.dim <= (m.like_kind == PTG_LIKE_POLY_CHI2 ? 16 : 18);
+}
+// The production kernel has streamlined instantiations (ptg_fast.cuh, LK >= 0) for the common production configuration; returns the
+// likelihood kind to instantiate for, or -1 when the configuration needs the general instantiation.  Chains are bit-identical either way.
+static int fstep_streamlined_kind(const ptg_handle *h) {
+  const PtgModel &m = h->m;
+  if (h->kernel_choice == PTG_KERNEL_FAST_GENERAL) return -1;
+  if (m.like_kind != PTG_LIKE_SINES && m.like_kind != PTG_LIKE_GAUSS_ISO) return -1;
+  if (m.swap_mode != PTG_SWAP_REFERENCE || m.evolve_rate > 0 || !m.wrap_in_set || m.record_full || m.trace_steps > 0) return -1;
+  if (m.any_bound || !m.all_uniform_prior || !m.zero_valid) return -1;
+  for (const HostProp &hp : h->props) {
+    if (hp.p.kind != PTG_PROP_DE && hp.p.kind != PTG_PROP_GAUSS) return -1;
+    if (hp.p.kind == PTG_PROP_DE && hp.p.unlikely_alpha > 0) return -1;
+    if (hp.p.kind == PTG_PROP_GAUSS && !hp.transform.empty()) return -1;
+  }
+  return m.like_kind;
+}
 static int pick_kernel(const ptg_handle *h, int *W) {
   *W = warp_kernel_width(h);
   int k = PTG_KERNEL_SHARED;
@@ -663,6 +712,7 @@ extern "C" int ptg_step(ptg_handle *h, int64_t n_steps) {
   if (!h) return fail(PTG_EINVAL, "null handle");
   if (!h->inited) return fail(PTG_EINVAL, "MH_chain:step: Can't step before initializing chain (chain.cc:967-971)");
   if (n_steps < 0) return fail(PTG_EINVAL, "negative step count");
+  if (h->dead) return fail(PTG_EXCHANGE, "handle stopped after an aborted boundary exchange");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   PtgModel &m = h->m;
   if (m.like_kind == PTG_LIKE_HOST_CALLBACK) {
@@ -690,6 +740,7 @@ extern "C" int ptg_step(ptg_handle *h, int64_t n_steps) {
   }
   int W = 0;
   const int kern = pick_kernel(h, &W);
+  const int lk = fstep_streamlined_kind(h);
   const int lpb = ladders_per_block(m);
   const size_t smem = (size_t)lpb * ptg_ladder_shared_bytes(m.dim, m.n_rungs) + (size_t)m.n_rungs * m.n_props * sizeof(double);
   const int max_chunk = (kern == PTG_KERNEL_FAST) ? 16384 : (1 << 20); // the fast kernel keeps 16-bit launch-local statistics
@@ -697,13 +748,7 @@ extern "C" int ptg_step(ptg_handle *h, int64_t n_steps) {
   while (left > 0) {
     int chunk = (int)(left > max_chunk ? max_chunk : left);
     cudaError_t e = cudaErrorInvalidValue;
-    // Data chi-squared likelihoods on a batch too small to fill the GPU with one thread per chain (BASELINE config B: 16 384
-    // chains): one WARP per chain, the data loop spread over its lanes (ptg_wide_mma.cuh).  Philox runs, automatic selection only.
-    const bool data_like = m.like_kind == PTG_LIKE_POLY_CHI2 || m.like_kind == PTG_LIKE_SINUSOID_CHI2;
-    bool has_prior_draw = false;
-    for (const HostProp &hp : h->props) if (hp.p.kind == PTG_PROP_PRIOR_DRAW) has_prior_draw = true;
-    const bool warp_per_chain = !h->wide && data_like && !has_prior_draw && h->cfg.rng_mode == PTG_RNG_PHILOX && h->kernel_choice == PTG_KERNEL_AUTO && m.n_rungs <= 32 &&
-                                m.dim <= (m.like_kind == PTG_LIKE_POLY_CHI2 ? 16 : 18) && m.n_chains <= 48 * 1024;
+    const bool warp_per_chain = routes_warp_per_chain(h);
     if (warp_per_chain) e = ptg_launch_xmstep(m, h->s, h->istep, chunk, -1, h->stream);
     else if (h->wide) {
       // Philox runs take the DMMA-batched kernel; tape replay (and PTG_KERNEL_WARP) the exact-summation-order kernel
@@ -712,7 +757,7 @@ extern "C" int ptg_step(ptg_handle *h, int64_t n_steps) {
     }
     else switch (m.dim) {
 #define X(D) case D:                                                                                                       \
-      if (kern == PTG_KERNEL_FAST) e = ptg_launch_fstep_d##D(m, h->s, h->istep, chunk, W, h->xchg_launch ? *h->xchg_launch : xchg_off, h->stream); \
+      if (kern == PTG_KERNEL_FAST) e = ptg_launch_fstep_d##D(m, h->s, h->istep, chunk, W, h->xchg_launch ? h->xchg_cur : xchg_off, lk, h->stream); \
       else if (kern == PTG_KERNEL_WARP) e = ptg_launch_wstep_d##D(h->cfg.rng_mode, m, h->s, h->istep, chunk, W, h->stream); \
       else e = ptg_launch_step_d##D(h->cfg.rng_mode, m, h->s, h->istep, chunk, lpb, smem, h->stream);                       \
       break;
@@ -727,7 +772,7 @@ extern "C" int ptg_step(ptg_handle *h, int64_t n_steps) {
 
 extern "C" int ptg_select_kernel(ptg_handle *h, int32_t kernel) {
   if (!h) return fail(PTG_EINVAL, "null handle");
-  if (kernel < PTG_KERNEL_AUTO || kernel > PTG_KERNEL_FAST) return fail(PTG_EINVAL, "bad kernel id %d", kernel);
+  if (kernel < PTG_KERNEL_AUTO || kernel > PTG_KERNEL_FAST_GENERAL) return fail(PTG_EINVAL, "bad kernel id %d", kernel);
   h->kernel_choice = kernel;
   return 0;
 }
@@ -873,12 +918,19 @@ extern "C" int ptg_get_history(ptg_handle *h, int32_t ladder, int32_t rung, int6
   if (nsize - first > m.hist_cap) return fail(PTG_EINVAL, "history element %lld already overwritten (ring capacity %d)", (long long)first, m.hist_cap);
   if (count == 0) return 0;
   const int D = m.dim;
-  std::vector<double> rec((size_t)count * (D + 2));
+  const int HX = m.hx;
+  std::vector<double> rec((size_t)count * HX), lp((size_t)count * 2);
   // the range may wrap around the ring: at most two contiguous pieces
   long long p0 = first % m.hist_cap, n0 = (p0 + count <= m.hist_cap) ? count : m.hist_cap - p0;
-  const double *base = h->s.hist + c * m.hist_cap * (D + 2);
-  CUDA_TRY(cudaMemcpyAsync(rec.data(), base + p0 * (D + 2), (size_t)n0 * (D + 2) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  if (n0 < count) CUDA_TRY(cudaMemcpyAsync(rec.data() + n0 * (D + 2), base, (size_t)(count - n0) * (D + 2) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  const double *base = h->s.hist + c * m.hist_cap * HX, *lbase = h->s.hist_lp + c * m.hist_cap * 2;
+  if (x) {
+    CUDA_TRY(cudaMemcpyAsync(rec.data(), base + p0 * HX, (size_t)n0 * HX * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (n0 < count) CUDA_TRY(cudaMemcpyAsync(rec.data() + n0 * HX, base, (size_t)(count - n0) * HX * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (lpost || llike) {
+    CUDA_TRY(cudaMemcpyAsync(lp.data(), lbase + p0 * 2, (size_t)n0 * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (n0 < count) CUDA_TRY(cudaMemcpyAsync(lp.data() + n0 * 2, lbase, (size_t)(count - n0) * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  }
   auto piece = [&](auto *dst, const auto *src) -> int {
     if (!dst) return 0;
     CUDA_TRY(cudaMemcpyAsync(dst, src + c * m.hist_cap + p0, (size_t)n0 * sizeof(*dst), cudaMemcpyDeviceToHost, h->stream));
@@ -890,9 +942,9 @@ extern "C" int ptg_get_history(ptg_handle *h, int32_t ladder, int32_t rung, int6
   if (rc) return rc;
   rc = ptg_synchronize(h); if (rc) return rc;
   for (long long k = 0; k < count; k++) {
-    if (x) for (int i = 0; i < D; i++) x[k * D + i] = rec[k * (D + 2) + i];
-    if (lpost) lpost[k] = rec[k * (D + 2) + D];
-    if (llike) llike[k] = rec[k * (D + 2) + D + 1];
+    if (x) for (int i = 0; i < D; i++) x[k * D + i] = rec[k * HX + i];
+    if (lpost) lpost[k] = lp[2 * k];
+    if (llike) llike[k] = lp[2 * k + 1];
   }
   return 0;
 }
@@ -947,7 +999,7 @@ extern "C" int ptg_get_device_views(ptg_handle *h, void **hist_dev, void **cur_x
   if (hist_dev) *hist_dev = h->s.hist;
   if (cur_x_dev) *cur_x_dev = h->s.cur_x;
   if (stream) *stream = (void *)h->stream;
-  if (hist_stride) *hist_stride = (int64_t)h->m.hist_cap * (h->m.dim + 2);
+  if (hist_stride) *hist_stride = (int64_t)h->m.hist_cap * h->m.hx;
   return 0;
 }
 
@@ -970,9 +1022,9 @@ __global__ void ptg_mean_llike_kernel(PtgModel m, PtgState s, int n_last, double
   long long n = n_last;
   if (n > nsize) n = nsize;
   if (n > m.hist_cap) n = m.hist_cap;
-  const double *base = s.hist + c * m.hist_cap * (m.dim + 2);
+  const double *base = s.hist_lp + c * m.hist_cap * 2;
   double sum = 0;
-  for (long long k = lane; k < n; k += 32) sum += base[((nsize - n + k) % m.hist_cap) * (m.dim + 2) + m.dim + 1];
+  for (long long k = lane; k < n; k += 32) sum += base[((nsize - n + k) % m.hist_cap) * 2 + 1];
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   if (lane == 0) out[c] = n > 0 ? sum / (double)n : CUDART_NAN;
 }
@@ -1006,10 +1058,10 @@ __global__ void __launch_bounds__(256) ptg_act_kernel(PtgModel m, PtgState s, in
   int n = n_last;
   if (n > nsize) n = (int)nsize;
   if (n > m.hist_cap) n = m.hist_cap;
-  const double *base = s.hist + c * m.hist_cap * (m.dim + 2);
+  const double *base = s.hist + c * m.hist_cap * m.hx;
   for (int j = 0; j < m.dim; j++) {
     double part = 0;
-    for (int k = threadIdx.x; k < n; k += blockDim.x) { const double v = base[((nsize - n + k) % m.hist_cap) * (m.dim + 2) + j]; y[k] = v; part += v; }
+    for (int k = threadIdx.x; k < n; k += blockDim.x) { const double v = base[((nsize - n + k) % m.hist_cap) * m.hx + j]; y[k] = v; part += v; }
     red[threadIdx.x] = part;
     __syncthreads();
     for (int o = blockDim.x / 2; o > 0; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
@@ -1069,7 +1121,8 @@ __global__ void __launch_bounds__(128) ptg_autocovar_kernel(PtgModel m, PtgState
   const long long nsize = s.nsize[c], end = end_rec ? end_rec[l] : nsize;
   const long long start = end - (long long)(n_win - k) * swidth;
   const int D = m.dim, cap = m.hist_cap;
-  const double *base = s.hist + c * (long long)cap * (D + 2);
+  const int HX = m.hx;
+  const double *base = s.hist + c * (long long)cap * HX;
   for (int j = threadIdx.x; j < n_lag; j += blockDim.x) {
     const long long first = start - lag_rec[j];
     if (first < 0 || first < nsize - cap || end > nsize) { if (bad) atomicExch(bad, 1); continue; } // not resident in the ring
@@ -1078,7 +1131,7 @@ __global__ void __launch_bounds__(128) ptg_autocovar_kernel(PtgModel m, PtgState
       double sx[4] = {0, 0, 0, 0}, sxx[4] = {0, 0, 0, 0};
       int q0 = p0, q1 = p1;
       for (int i = 0; i < swidth; i++) {
-        const double *a = base + (long long)q0 * (D + 2) + f0, *b = base + (long long)q1 * (D + 2) + f0;
+        const double *a = base + (long long)q0 * HX + f0, *b = base + (long long)q1 * HX + f0;
 #pragma unroll
         for (int f = 0; f < 4; f++) if (f0 + f < n_feat) { const double fi = a[f], fl = b[f]; sx[f] += (fl + fi); sxx[f] += fl * fi; }
         if (++q0 == cap) q0 = 0;
@@ -1194,9 +1247,9 @@ __global__ void ptg_boundary_swap_kernel(PtgModel m, PtgState s, int rung, const
   const long long nhist = s.nhist[c];
   if (nhist % m.save_every == 0) {
     const long long nsize = s.nsize[c], slot = nsize % m.hist_cap, r = c * m.hist_cap + slot;
-    double *hrec = s.hist + r * (D + 2);
+    double *hrec = s.hist + r * m.hx;
     for (int k = 0; k < D; k++) hrec[k] = s.cur_x[(long long)k * m.n_chains + c];
-    hrec[D] = lpost; hrec[D + 1] = llike;
+    s.hist_lp[2 * r] = lpost; s.hist_lp[2 * r + 1] = llike;
     if (m.record_full) { s.hist_acc[r] = s.naccept[c] / (double)s.ntries[c]; s.hist_beta[r] = my_beta; s.hist_type[r] = s.last_type[c]; }
     s.nsize[c] = nsize + 1;
   }
@@ -1236,14 +1289,25 @@ static int xchg_alloc(ptg_handle *h) {
   h->allocs.push_back(h->d_xchg);
   CUDA_TRY(cudaMemsetAsync(h->d_xchg, 0, h->xchg_bytes, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
+  // the watchdog word lives in mapped host memory: the host can raise it while a launch is spinning (ptg_xchg_abort)
+  CUDA_TRY(cudaHostAlloc((void **)&h->h_abort, sizeof(int), cudaHostAllocMapped));
+  *h->h_abort = 0;
+  CUDA_TRY(cudaHostGetDevicePointer((void **)&h->d_abort, h->h_abort, 0));
+  return 0;
+}
+// Watchdog of the fused exchange: every boundary wait in flight (and every later one) gives up, the launch ends with the sticky
+// error PTG_EXCHANGE.  Callable from any host thread while ptg_synchronize blocks in another (it only writes one mapped word).
+extern "C" int ptg_xchg_abort(ptg_handle *h) {
+  if (!h) return fail(PTG_EINVAL, "null handle");
+  if (h->h_abort) { *(volatile int *)h->h_abort = 1; __sync_synchronize(); }
   return 0;
 }
 static int xchg_check(ptg_handle *h) {
   if (!h) return fail(PTG_EINVAL, "null handle");
   if (!h->inited) return fail(PTG_EINVAL, "not initialised");
   int W = 0;
-  if (h->wide || h->m.like_kind == PTG_LIKE_HOST_CALLBACK || pick_kernel(h, &W) != PTG_KERNEL_FAST)
-    return fail(PTG_EINVAL, "the fused exchange runs in the production kernel only (Philox draws, n_rungs <= 32, dim <= 16)");
+  if (h->wide || h->m.like_kind == PTG_LIKE_HOST_CALLBACK || pick_kernel(h, &W) != PTG_KERNEL_FAST || routes_warp_per_chain(h))
+    return fail(PTG_EINVAL, "the fused exchange runs in the production kernel only (Philox draws, n_rungs <= 32, dim <= 16, no data-chi^2 likelihood under automatic kernel selection)");
   return 0;
 }
 extern "C" int ptg_xchg_export(ptg_handle *h, void *ipc_handle_64_bytes, void **local_ptr) {
@@ -1283,7 +1347,7 @@ extern "C" int ptg_xchg_connect(ptg_handle *h, const void *colder, const void *h
   x.my_edges = (double *)h->d_xchg; x.my_flags = (int *)((double *)h->d_xchg + ed);
   x.lo_edges = (const double *)h->peer_lo; x.lo_flags = h->peer_lo ? (const int *)((const double *)h->peer_lo + ed) : nullptr;
   x.hi_edges = (const double *)h->peer_hi; x.hi_flags = h->peer_hi ? (const int *)((const double *)h->peer_hi + ed) : nullptr;
-  x.shared_seed = shared_seed; x.lo_boundary = colder_boundary_id; x.hi_boundary = hotter_boundary_id;
+  x.shared_seed = shared_seed; x.lo_boundary = colder_boundary_id; x.hi_boundary = hotter_boundary_id; x.abort = h->d_abort;
   return 0;
 }
 // n_steps PT iterations in ONE launch; apply_pending: first run the boundary swap trials against what the neighbours published at
@@ -1301,24 +1365,25 @@ extern "C" int ptg_step_exchange(ptg_handle *h, int64_t n_steps, int32_t every, 
     const long long warps = (h->m.n_ladders + (32 / W) - 1) / (32 / W);
     if (!ptg_fstep_grid_is_resident(warps)) return fail(PTG_EINVAL, "in-launch exchange needs the whole grid resident (more ladders than one wave holds): use every = 0 and one launch per exchange");
   }
-  PtgXchg x = h->xchg;
+  if (h->dead) return fail(PTG_EXCHANGE, "handle stopped after an aborted boundary exchange");
+  PtgXchg &x = h->xchg_cur; // kept in the handle: nothing points into this frame after an early return
+  x = h->xchg;
   x.swap_in = apply_pending ? 1 : 0; x.publish_out = publish ? 1 : 0; x.every = in_launch ? every : 0;
-  h->xchg_launch = &x;
+  h->xchg_launch = true;
   if (n_steps == 0) { // prologue / epilogue only
     int W = 0; pick_kernel(h, &W);
     cudaError_t e = cudaErrorInvalidValue;
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
-    switch (h->m.dim) {
-#define X(D) case D: e = ptg_launch_fstep_d##D(h->m, h->s, h->istep, 0, W, x, h->stream); break;
+    if (cudaSetDevice(h->cfg.device) == cudaSuccess) switch (h->m.dim) {
+#define X(D) case D: e = ptg_launch_fstep_d##D(h->m, h->s, h->istep, 0, W, x, fstep_streamlined_kind(h), h->stream); break;
       PTG_DIM_LIST(X)
 #undef X
     }
-    h->xchg_launch = nullptr;
+    h->xchg_launch = false;
     CUDA_TRY(e);
     h->launches++;
   } else {
     rc = ptg_step(h, n_steps);
-    h->xchg_launch = nullptr;
+    h->xchg_launch = false;
     if (rc) return rc;
   }
   h->xchg.index += (in_launch ? n_steps / every - 1 : 0) + (publish ? 1 : 0);
@@ -1326,58 +1391,93 @@ extern "C" int ptg_step_exchange(ptg_handle *h, int64_t n_steps, int32_t every, 
 }
 
 // ------------------------------------------------------------------------------------------------- checkpoint
-// One binary file: magic, config, istep, then every device array of PtgState in declaration order.
+// One binary file: magic, config, istep, ring geometry, exchange index, then every device array of PtgState in declaration order.
+// This is the ENGINE's restart blob (all ladders, all rungs, the whole ring); the reference-layout per-chain files
+// (MHchain.cp / PTchain.cp, chain.cc:656-731,1213-1239) are written by the host facade from ptg_get_history.
+// Arrays are streamed through one bounded staging buffer (the history ring of a production batch is tens of GB).
 struct CkArr { void *p; size_t bytes; };
 static std::vector<CkArr> ck_arrays(ptg_handle *h) {
   PtgModel &m = h->m; PtgState &s = h->s;
   const size_t n = (size_t)m.n_chains, d = (size_t)m.dim, cap = (size_t)m.hist_cap;
   std::vector<CkArr> v = {
       {s.cur_x, n * d * 8}, {s.lpost, n * 8}, {s.llike, n * 8}, {s.lprior, n * 8}, {s.beta, n * 8}, {s.map_lpost, n * 8}, {s.map_x, n * d * 8},
-      {s.nhist, n * 8}, {s.nsize, n * 8}, {s.ntries, n * 8}, {s.naccept, n * 8}, {s.last_type, n * 4}, {s.hist, n * cap * (d + 2) * 8},
+      {s.nhist, n * 8}, {s.nsize, n * 8}, {s.ntries, n * 8}, {s.naccept, n * 8}, {s.last_type, n * 4}, {s.hist, n * cap * (size_t)m.hx * 8}, {s.hist_lp, n * cap * 2 * 8},
       {s.swap_count, n * 8}, {s.swap_accept, n * 8}, {s.directions, n * 4}, {s.ups, n * 4}, {s.downs, n * 4}, {s.instances, n * 4},
       {s.u_pos, (n + m.n_ladders) * 8}, {s.z_pos, (n + m.n_ladders) * 8}};
   if (m.record_full) { v.push_back({s.hist_acc, n * cap * 8}); v.push_back({s.hist_beta, n * cap * 8}); v.push_back({s.hist_type, n * cap * 4}); }
   return v;
 }
+static const uint64_t CK_MAGIC = 0x70746763686b3032ull; // "ptgchk02"
+static const size_t CK_CHUNK = (size_t)64 << 20;
+struct CkFile { // closes on every exit path
+  FILE *f;
+  explicit CkFile(FILE *f_) : f(f_) {}
+  ~CkFile() { if (f) fclose(f); }
+  int close() { FILE *g = f; f = nullptr; return g ? fclose(g) : 0; }
+};
+static int checkpoint_impl(ptg_handle *h, const char *path) {
+  int rc = ptg_synchronize(h); if (rc) return rc; // also orders this after every step in flight on h->stream
+  CkFile ck(fopen(path, "wb"));
+  if (!ck.f) return fail(PTG_EINVAL, "cannot open %s", path);
+  const int32_t cap = h->m.hist_cap, hx = h->m.hx;
+  const int64_t istep = h->istep, xindex = h->xchg.index;
+  bool ok = fwrite(&CK_MAGIC, 8, 1, ck.f) == 1 && fwrite(&h->cfg, sizeof(h->cfg), 1, ck.f) == 1 && fwrite(&istep, 8, 1, ck.f) == 1 &&
+            fwrite(&cap, 4, 1, ck.f) == 1 && fwrite(&hx, 4, 1, ck.f) == 1 && fwrite(&xindex, 8, 1, ck.f) == 1;
+  std::vector<char> buf(CK_CHUNK);
+  for (const CkArr &a : ck_arrays(h)) {
+    const uint64_t nb = a.bytes;
+    ok = ok && fwrite(&nb, 8, 1, ck.f) == 1;
+    for (size_t off = 0; ok && off < a.bytes; off += CK_CHUNK) {
+      const size_t n = a.bytes - off < CK_CHUNK ? a.bytes - off : CK_CHUNK;
+      CUDA_TRY(cudaMemcpyAsync(buf.data(), (const char *)a.p + off, n, cudaMemcpyDeviceToHost, h->stream));
+      CUDA_TRY(cudaStreamSynchronize(h->stream));
+      ok = fwrite(buf.data(), 1, n, ck.f) == n;
+    }
+  }
+  if (ck.close() != 0) ok = false;
+  if (!ok) { remove(path); return fail(PTG_EINVAL, "short write to %s (disk full?): checkpoint removed", path); }
+  return 0;
+}
 extern "C" int ptg_checkpoint(ptg_handle *h, const char *path) {
   if (!h || !path) return fail(PTG_EINVAL, "null argument");
   if (!h->inited) return fail(PTG_EINVAL, "not initialised");
-  int rc = ptg_synchronize(h); if (rc) return rc;
-  FILE *f = fopen(path, "wb");
-  if (!f) return fail(PTG_EINVAL, "cannot open %s", path);
-  const uint64_t magic = 0x70746763686b3031ull; // "ptgchk01"
-  fwrite(&magic, 8, 1, f); fwrite(&h->cfg, sizeof(h->cfg), 1, f); fwrite(&h->istep, 8, 1, f); fwrite(&h->m.hist_cap, 4, 1, f);
-  std::vector<char> buf;
+  try { return checkpoint_impl(h, path); }
+  catch (const std::exception &e) { return fail(PTG_ENOMEM, "checkpoint: %s", e.what()); }
+}
+static int restore_impl(ptg_handle *h, const char *path) {
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream)); // nothing of this handle may be in flight while its arrays are overwritten
+  if (!h->model_uploaded) { int rc = upload_model(h); if (rc) return rc; }
+  CkFile ck(fopen(path, "rb"));
+  if (!ck.f) return fail(PTG_EINVAL, "cannot open %s", path);
+  uint64_t magic = 0; ptg_config c; int64_t istep = 0, xindex = 0; int32_t cap = 0, hx = 0;
+  bool ok = fread(&magic, 8, 1, ck.f) == 1 && fread(&c, sizeof(c), 1, ck.f) == 1 && fread(&istep, 8, 1, ck.f) == 1 && fread(&cap, 4, 1, ck.f) == 1 &&
+            fread(&hx, 4, 1, ck.f) == 1 && fread(&xindex, 8, 1, ck.f) == 1;
+  if (!ok || magic != CK_MAGIC) return fail(PTG_EINVAL, "%s is not a ptg checkpoint (format ptgchk02)", path);
+  const ptg_config &g = h->cfg;
+  if (c.n_ladders != g.n_ladders || c.n_rungs != g.n_rungs || c.dim != g.dim || cap != h->m.hist_cap || hx != h->m.hx || c.record_level != g.record_level)
+    return fail(PTG_EINVAL, "checkpoint shape does not match this engine");
+  // the continuation must be the run that was interrupted: same draws, same save cadence, same swap schedule, same ladder ids
+#define CK_SAME(f) if (!(c.f == g.f)) return fail(PTG_EINVAL, "checkpoint was written with a different " #f "; create the engine with the saved value")
+  CK_SAME(seed); CK_SAME(save_every); CK_SAME(n_init); CK_SAME(swap_rate); CK_SAME(swap_mode); CK_SAME(rng_mode); CK_SAME(evolve_rate);
+  CK_SAME(evolve_lpost_cut); CK_SAME(dprior_min); CK_SAME(ladder_offset);
+#undef CK_SAME
+  std::vector<char> buf(CK_CHUNK);
   for (const CkArr &a : ck_arrays(h)) {
-    buf.resize(a.bytes);
-    cudaError_t e = cudaMemcpy(buf.data(), a.p, a.bytes, cudaMemcpyDeviceToHost);
-    if (e != cudaSuccess) { fclose(f); return fail(PTG_ECUDA, "checkpoint copy: %s", cudaGetErrorString(e)); }
-    uint64_t nb = a.bytes; fwrite(&nb, 8, 1, f); fwrite(buf.data(), 1, a.bytes, f);
+    uint64_t nb = 0;
+    if (fread(&nb, 8, 1, ck.f) != 1 || nb != a.bytes) return fail(PTG_EINVAL, "checkpoint array size mismatch");
+    for (size_t off = 0; off < a.bytes; off += CK_CHUNK) {
+      const size_t n = a.bytes - off < CK_CHUNK ? a.bytes - off : CK_CHUNK;
+      if (fread(buf.data(), 1, n, ck.f) != n) return fail(PTG_EINVAL, "checkpoint truncated");
+      CUDA_TRY(cudaMemcpyAsync((char *)a.p + off, buf.data(), n, cudaMemcpyHostToDevice, h->stream));
+      CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
   }
-  fclose(f);
+  h->istep = istep; h->xchg.index = xindex; h->inited = true;
   return 0;
 }
 extern "C" int ptg_restore(ptg_handle *h, const char *path) {
   if (!h || !path) return fail(PTG_EINVAL, "null argument");
-  CUDA_TRY(cudaSetDevice(h->cfg.device));
-  if (!h->model_uploaded) { int rc = upload_model(h); if (rc) return rc; }
-  FILE *f = fopen(path, "rb");
-  if (!f) return fail(PTG_EINVAL, "cannot open %s", path);
-  uint64_t magic = 0; ptg_config c; long long istep = 0; int32_t cap = 0;
-  bool ok = fread(&magic, 8, 1, f) == 1 && fread(&c, sizeof(c), 1, f) == 1 && fread(&istep, 8, 1, f) == 1 && fread(&cap, 4, 1, f) == 1;
-  if (!ok || magic != 0x70746763686b3031ull) { fclose(f); return fail(PTG_EINVAL, "%s is not a ptg checkpoint", path); }
-  if (c.n_ladders != h->cfg.n_ladders || c.n_rungs != h->cfg.n_rungs || c.dim != h->cfg.dim || cap != h->m.hist_cap ||
-      c.record_level != h->cfg.record_level) { fclose(f); return fail(PTG_EINVAL, "checkpoint shape does not match this engine"); }
-  std::vector<char> buf;
-  for (const CkArr &a : ck_arrays(h)) {
-    uint64_t nb = 0;
-    if (fread(&nb, 8, 1, f) != 1 || nb != a.bytes) { fclose(f); return fail(PTG_EINVAL, "checkpoint array size mismatch"); }
-    buf.resize(a.bytes);
-    if (fread(buf.data(), 1, a.bytes, f) != a.bytes) { fclose(f); return fail(PTG_EINVAL, "checkpoint truncated"); }
-    cudaError_t e = cudaMemcpy(a.p, buf.data(), a.bytes, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) { fclose(f); return fail(PTG_ECUDA, "restore copy: %s", cudaGetErrorString(e)); }
-  }
-  fclose(f);
-  h->istep = istep; h->inited = true;
-  return 0;
+  try { return restore_impl(h, path); }
+  catch (const std::exception &e) { return fail(PTG_ENOMEM, "restore: %s", e.what()); }
 }

@@ -183,20 +183,49 @@ __device__ __forceinline__ bool prior_draw(const PtgModel &m, Stream<MODE> &rs, 
 }
 
 // ------------------------------------------------------------------------------------------------- likelihoods
-template <int D>
-__device__ __forceinline__ double like_eval(const PtgModel &m, const double x[D]) {
+// one functor per kind (compile-time KIND: the streamlined production kernels instantiate exactly one of them)
+template <int D, int KIND>
+__device__ __forceinline__ double like_eval_kind(const PtgModel &m, const double x[D]) {
   const double *__restrict__ P = m.lparams;
   double result = 0;
-  switch (m.like_kind) {
-  case PTG_LIKE_FLAT: return 0;
-  case PTG_LIKE_GAUSS_ISO: { // example.cc:116-143
+  if constexpr (KIND == PTG_LIKE_FLAT) return 0;
+  else if constexpr (KIND == PTG_LIKE_GAUSS_ISO) { // example.cc:116-143
     double r2 = 0;
 #pragma unroll
     for (int i = 0; i < D; i++) { double dx = x[i] - __ldg(P + 2 + i); r2 += dx * dx; }
     result = __ldg(P) - r2 / __ldg(P + 1);
-    break;
-  }
-  case PTG_LIKE_SINES: { // sines.hh:22-54
+  } else if constexpr (KIND == PTG_LIKE_SHELL2D) { // example.cc:195-206: Gaussian shell in (|p0|, p1)
+    double dx = fabs(x[0]) - __ldg(P + 3);
+    double r2 = dx * dx;
+    dx = x[D >= 2 ? 1 : 0] - __ldg(P + 4);
+    r2 += dx * dx;
+    dx = sqrt(r2) - __ldg(P + 2);
+    r2 = dx * dx;
+    result = __ldg(P) - r2 / __ldg(P + 1);
+  } else if constexpr (KIND == PTG_LIKE_SHELLS) { // example.cc:373-403: the better of the "plus" and the "minus" shell
+    const double twosigmasq = __ldg(P + 1), r0 = __ldg(P + 2), x0 = __ldg(P + 3), spm = __ldg(P + 4), lnspm = __ldg(P + 5);
+    double xx = x[0];
+    if (__ldg(P + 6) != 0) {
+      if (xx < 0) return -CUDART_INF;
+      xx = log(xx);
+    }
+    double dx = xx - x0;
+    double r2 = dx * dx;
+#pragma unroll
+    for (int i = 1; i < D; i++) { dx = x[i]; r2 += dx * dx; }
+    dx = sqrt(r2) - r0;
+    r2 = dx * dx;
+    const double resultp = -r2 / (twosigmasq * spm) - 0.5 * lnspm;
+    dx = xx + x0;
+    r2 = dx * dx;
+#pragma unroll
+    for (int i = 1; i < D; i++) { dx = x[i]; r2 += dx * dx; }
+    dx = sqrt(r2) - r0;
+    r2 = dx * dx;
+    const double resultm = -r2 / (twosigmasq / spm) + 0.5 * lnspm;
+    result = __ldg(P);
+    if (resultm > resultp) result += resultm; else result += resultp;
+  } else if constexpr (KIND == PTG_LIKE_SINES) { // sines.hh:22-54
     const double height = __ldg(P), step_scale = __ldg(P + 1);
     double lprod = 0; int isum = 0;
     // rolled on purpose: ONE copy of sin() in the instruction stream and one set of temporaries (register budget and
@@ -219,8 +248,7 @@ __device__ __forceinline__ double like_eval(const PtgModel &m, const double x[D]
       isum += (int)(xx * k);
     }
     return lprod + (-isum * step_scale);
-  }
-  case PTG_LIKE_POLY_CHI2: { // bayesian.hh:595-622 + poly_example.cc:85-106
+  } else if constexpr (KIND == PTG_LIKE_POLY_CHI2) { // bayesian.hh:595-622 + poly_example.cc:85-106
     const long long N = m.n_ldata / 3;
     const double *__restrict__ xs = m.ldata, *__restrict__ ys = m.ldata + N, *__restrict__ S = m.ldata + 2 * N;
     double sum = 0;
@@ -234,9 +262,7 @@ __device__ __forceinline__ double like_eval(const PtgModel &m, const double x[D]
     sum += m.like_nsum;
     sum /= -2;
     result = sum - __ldg(P);
-    break;
-  }
-  case PTG_LIKE_SINUSOID_CHI2: {
+  } else if constexpr (KIND == PTG_LIKE_SINUSOID_CHI2) {
     const long long N = m.n_ldata / 3;
     const double *__restrict__ xs = m.ldata, *__restrict__ ys = m.ldata + N, *__restrict__ S = m.ldata + 2 * N;
     double sum = 0;
@@ -250,9 +276,7 @@ __device__ __forceinline__ double like_eval(const PtgModel &m, const double x[D]
     sum += m.like_nsum;
     sum /= -2;
     result = sum - __ldg(P);
-    break;
-  }
-  case PTG_LIKE_GAUSS_FULLCOV: { // cython/exampleGaussian.py:103-109
+  } else if constexpr (KIND == PTG_LIKE_GAUSS_FULLCOV) { // cython/exampleGaussian.py:103-109
     const double *__restrict__ C = m.ldata;
     double q = 0;
 #pragma unroll
@@ -263,9 +287,21 @@ __device__ __forceinline__ double like_eval(const PtgModel &m, const double x[D]
       q += x[i] * y;
     }
     result = __ldg(P) - 0.5 * q;
-    break;
-  }
   }
   if (!isfinite(result)) result = -CUDART_INF; // bayesian.hh:569-575
   return result;
+}
+template <int D>
+__device__ __forceinline__ double like_eval(const PtgModel &m, const double x[D]) {
+  switch (m.like_kind) {
+  case PTG_LIKE_FLAT: return 0;
+  case PTG_LIKE_GAUSS_ISO: return like_eval_kind<D, PTG_LIKE_GAUSS_ISO>(m, x);
+  case PTG_LIKE_SHELL2D: if constexpr (D >= 2) return like_eval_kind<D, PTG_LIKE_SHELL2D>(m, x); else return 0;
+  case PTG_LIKE_SHELLS: return like_eval_kind<D, PTG_LIKE_SHELLS>(m, x);
+  case PTG_LIKE_SINES: return like_eval_kind<D, PTG_LIKE_SINES>(m, x);
+  case PTG_LIKE_POLY_CHI2: return like_eval_kind<D, PTG_LIKE_POLY_CHI2>(m, x);
+  case PTG_LIKE_SINUSOID_CHI2: return like_eval_kind<D, PTG_LIKE_SINUSOID_CHI2>(m, x);
+  case PTG_LIKE_GAUSS_FULLCOV: return like_eval_kind<D, PTG_LIKE_GAUSS_FULLCOV>(m, x);
+  }
+  return 0;
 }

@@ -1,31 +1,40 @@
 // ptg_fast.cuh -- the production step kernel (Philox draws): ladder-in-a-warp like ptg_warp.cuh, restructured around the
-// ncu findings of round 1 (profiles/README.md):
-//   * one wave: chain state is slimmed to <= 72 registers/thread (32-bit launch-local counters, packed ladder statistics)
-//     so that all 4096 warps of BASELINE config C1 are resident at once (7 CTAs x 4 warps per SM);
-//   * swap phase: every lane prepares ITS trial in parallel (candidate pair from its Philox block, log of its
-//     swap draw), the serial part is a 7-iteration bit-mask de-dup plus one shuffle round per surviving trial;
-//   * MH update: member selection, both Philox blocks, all three DE history indices, gathers, prior, likelihood and the
-//     Metropolis test are straight-line code executed by the whole warp; only the snooker override (~8 % of lanes) and
-//     rare paths (unlikely_alpha, prior-draw member, bounded spaces, non-uniform priors) branch;
-//   * Box-Muller normals for the Gaussian-proposal lanes are produced cooperatively by all 32 lanes;
-//   * proposal-member parameters live in shared memory (divergent member indices would serialise constant-bank loads).
+// ncu findings of rounds 1 and 2 (profiles/README.md):
+//   * one wave: chain state is slimmed to <= 72 registers/thread (launch-local counters and the per-chain MAP in shared
+//     memory, packed ladder statistics) so that all 4096 warps of BASELINE config C1 are resident at once;
+//   * compile-time specialisation: LK >= 0 instantiates the kernel for the common production configuration (reference swap
+//     schedule without temperature evolution, open state space, uniform priors, DE + plain Gaussian members, likelihood LK);
+//     every rare-path branch folds away (13.5 k -> ~3 k SASS instructions, +22 % measured).  LK = -1 keeps every feature;
+//   * swap phase: every lane prepares ITS trial in parallel; the serial part is a bit-mask de-dup plus one shuffle round per
+//     surviving trial; the history appends of swapped rungs are deferred to the ONE append at the end of the iteration
+//     that MH lanes execute too (a rung in two trials of one step, SURVEY.md H4, flushes the first before the second);
+//   * pooled work rounds: the few-lane sections of a step share ONE converged call site each --
+//       round 1: Philox block + log of (a) every Box-Muller pair a Gaussian-member lane needs (1-D steps only need the
+//                pair of their axis) and (b) the NEXT iteration's swap-trial draws, spread over all 32 lanes;
+//       round 2: log of the Metropolis draw of every MH lane and, on the lanes that do no MH update this iteration, the
+//                two logarithms of the snooker Hastings term;
+//     values travel through per-warp shared-memory slots, not registers;
+//   * history x-ring in whole 32-byte sectors (PTG_HX): a DE gather at dim <= 4 is one 256-bit load of exactly one sector.
 // The arithmetic is expression-for-expression that of ptg_warp.cuh / ptg_kernels.cuh / the oracle: in Philox mode the
 // three kernels produce bit-identical chains (tests/test_gpu_properties.py::test_kernels_agree_bitwise).
 #pragma once
 #include "ptg_warp.cuh"
 
+// register-resident part of a chain's state; lpost, lprior and the running MAP live in per-thread shared-memory slots (FShared):
+// they are touched a few times per iteration and would otherwise be spilled under the one-wave register budget
 template <int D>
 struct FChain {
   double x[D];
-  double lpost, llike, lprior, beta;
+  double llike, beta;
   int slot, hfill, since_save;           // ring write position, min(nsize, capacity), nhist % save_every
 };
-// Launch-local counters that are touched once per step live in shared memory, one word per thread and counter
-// ([counter][thread]: conflict-free), to keep the register-resident state within the one-wave budget.
 // largest CTA the production kernel is launched with (28 warps = one CTA per SM at 72 registers); smaller batches use smaller CTAs
 #define PTG_FSTEP_MAX_THREADS 896
-#define PTG_FC_STRIDE 7 // per-thread counter row in shared memory, odd stride: conflict-free
-enum { FC_NHIST = 0, FC_NTRIES, FC_NACCEPT, FC_LAST_TYPE, FC_UD, FC_SC, FC_COUNT };
+// Launch-local per-thread words in shared memory ([thread][PTG_FC_STRIDE], odd stride: conflict-free): counters that change rarely
+// and the swap-trial draw this lane prepared for the next iteration
+enum { FC_XAPP = 0, FC_NSWAPPED, FC_NACCEPT, FC_LAST_TYPE, FC_UD, FC_SC, FC_RAW, FC_LOGU_LO, FC_LOGU_HI, FC_COUNT };
+#define PTG_FC_STRIDE 9
+static_assert(FC_COUNT == PTG_FC_STRIDE, "counter row");
 
 // proposal member parameters staged in shared memory
 struct FProp {
@@ -33,22 +42,77 @@ struct FProp {
   int kind, has_transform, sigma_off, trans_off;
 };
 
-// MH_chain::add_state (chain.cc:916-949) of the chain's current state
+// dynamic shared memory of a CTA of `threads` threads
 template <int D>
-__device__ __forceinline__ void fappend(const PtgModel &m, const PtgState &s, FChain<D> &ch, long long chain, double *__restrict__ hbase, int *cnt) {
-  if (ch.lpost > s.map_lpost[chain]) { // MAP update (chain.cc:931-934); the running maximum stays in global memory (L1/L2-resident)
-    s.map_lpost[chain] = ch.lpost;
+struct FShared {
+  static constexpr int NPAIR = (D + 1) / 2;
+  double *bins;     // [R][NP]
+  double *map;      // [threads][3]         per thread: running MAP posterior, current lpost, current lprior (stride 3: conflict-free)
+  double *spar;     // [4 D]                streamlined sines functor: per dimension (min, width or 1/width, k pi, k)
+  double *lus;      // [warps][32]          swap phase: log u of the trial on pair c, handed to the lane of rung c
+  double *pool;     // [warps][2 NPAIR][32] round 1: normals of lane l at [j][l]; round 2 (aliased): [64] arguments / logarithms
+  FProp *prop;      // [NP]
+  int *cnt;         // [threads][PTG_FC_STRIDE]
+  unsigned char *items; // [warps][32 NPAIR]  Box-Muller work list: owner lane << 4 | pair
+  __host__ __device__ static size_t bytes(int threads, int R, int NP) {
+    size_t b = sizeof(double) * ((size_t)R * NP + 3 * (size_t)threads + 4 * D + threads + (size_t)(threads / 32) * 2 * NPAIR * 32) + sizeof(FProp) * NP + sizeof(int) * (size_t)threads * PTG_FC_STRIDE +
+               (size_t)(threads / 32) * 32 * NPAIR;
+    return (b + 15) & ~(size_t)15;
+  }
+  __device__ void carve(unsigned char *base, int threads, int R, int NP) {
+    bins = reinterpret_cast<double *>(base);
+    map = bins + R * NP;
+    spar = map + 3 * threads;
+    lus = spar + 4 * D;
+    pool = lus + threads;
+    prop = reinterpret_cast<FProp *>(pool + (size_t)(threads / 32) * 2 * NPAIR * 32);
+    cnt = reinterpret_cast<int *>(prop + NP);
+    items = reinterpret_cast<unsigned char *>(cnt + (size_t)threads * PTG_FC_STRIDE);
+  }
+};
+
+// ---- history ring access: x-records of PTG_HX(D) doubles (whole 32-byte sectors), (lpost, llike) pairs in their own ring
+struct __align__(32) FRec4 { double a, b, c, d; };
+template <int D>
+__device__ __forceinline__ void fload_rec(const double *__restrict__ p, double v[D]) {
+  constexpr int HX = PTG_HX(D);
+#pragma unroll
+  for (int k = 0; k < HX; k += 4) {
+    double a, b, c, d;
+    // random records with no reuse: one 256-bit load per sector, not allocated in L1
+    asm volatile("ld.global.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p + k) : "memory");
+    v[k] = a;
+    if (k + 1 < D) v[k + 1] = b;
+    if (k + 2 < D) v[k + 2] = c;
+    if (k + 3 < D) v[k + 3] = d;
+  }
+}
+template <int D>
+__device__ __forceinline__ void fstore_rec(double *__restrict__ p, const double v[D]) {
+  constexpr int HX = PTG_HX(D);
+#pragma unroll
+  for (int k = 0; k < HX; k += 4) {
+    FRec4 r;
+    r.a = v[k]; r.b = (k + 1 < D) ? v[k + 1] : 0.0; r.c = (k + 2 < D) ? v[k + 2] : 0.0; r.d = (k + 3 < D) ? v[k + 3] : 0.0;
+    *reinterpret_cast<FRec4 *>(p + k) = r;
+  }
+}
+
+// MH_chain::add_state (chain.cc:916-949) of the chain's current state
+template <int D, bool RECORD_FULL_POSSIBLE>
+__device__ __forceinline__ void fappend(const PtgModel &m, const PtgState &s, FChain<D> &ch, long long chain, double *__restrict__ hbase, int *cnt, double *mapp, int n_mh_so_far) {
+  const double lpost = mapp[1]; // per-thread slots: [0] running MAP, [1] current lpost, [2] current lprior
+  if (lpost > *mapp) { // MAP update (chain.cc:931-934)
+    *mapp = lpost;
 #pragma unroll
     for (int k = 0; k < D; k++) s.map_x[(long long)k * m.n_chains + chain] = ch.x[k];
   }
   if (ch.since_save == 0) {
-    double *h = hbase + ch.slot * (D + 2);
-#pragma unroll
-    for (int k = 0; k < D; k++) h[k] = ch.x[k];
-    h[D] = ch.lpost; h[D + 1] = ch.llike;
-    if (m.record_full) {
-      const long long rec = chain * m.hist_cap + ch.slot;
-      s.hist_acc[rec] = (s.naccept[chain] + cnt[FC_NACCEPT]) / (double)(s.ntries[chain] + cnt[FC_NTRIES]);
+    fstore_rec<D>(hbase + (long long)ch.slot * PTG_HX(D), ch.x);
+    const long long rec = chain * m.hist_cap + ch.slot;
+    *reinterpret_cast<double2 *>(s.hist_lp + 2 * rec) = make_double2(lpost, ch.llike);
+    if (RECORD_FULL_POSSIBLE && m.record_full) {
+      s.hist_acc[rec] = (s.naccept[chain] + cnt[FC_NACCEPT]) / (double)(s.ntries[chain] + n_mh_so_far);
       s.hist_beta[rec] = ch.beta;
       s.hist_type[rec] = cnt[FC_LAST_TYPE];
     }
@@ -56,20 +120,19 @@ __device__ __forceinline__ void fappend(const PtgModel &m, const PtgState &s, FC
     ch.slot = (ch.slot + 1 == m.hist_cap) ? 0 : ch.slot + 1;
   }
   ch.since_save = (ch.since_save + 1 == m.save_every) ? 0 : ch.since_save + 1;
-  cnt[FC_NHIST]++;
 }
 
 // element `index` of the eligible window (newest min(nsize,cap) samples): once the ring is full the oldest sits at `slot`
 template <int D>
-__device__ __forceinline__ const double *fhist(const PtgModel &m, const FChain<D> &ch, const double *__restrict__ hbase, int index) {
+__device__ __forceinline__ int fslot(const PtgModel &m, const FChain<D> &ch, int index) {
   int p = index;
   if (ch.hfill == m.hist_cap) { p = ch.slot + index; if (p >= m.hist_cap) p -= m.hist_cap; }
-  return hbase + p * (D + 2);
+  return p;
 }
 
 // differential_evolution::draw_i_from_chain with unlikely_alpha > 0 or a retry (proposal_distribution.cc:744-778): rare path
 template <int D>
-__device__ __noinline__ int2 fde_index_slow(const PtgModel &m, int hfill, int slot, const double *hbase, double map_lpost, uint64_t seed, uint64_t stream,
+__device__ __noinline__ int2 fde_index_slow(const PtgModel &m, int hfill, int slot, const double *lpbase, double map_lpost, uint64_t seed, uint64_t stream,
                                              uint64_t step, double ignore_frac, double alpha, uint32_t w0, int which, int attempt) {
   const int hsize = hfill; // returns (index, attempts consumed so far)
   int start = 0;
@@ -86,7 +149,7 @@ __device__ __noinline__ int2 fde_index_slow(const PtgModel &m, int hfill, int sl
     if (alpha > 0) {
       int p = index;
       if (hfill == m.hist_cap) { p = slot + index; if (p >= m.hist_cap) p -= m.hist_cap; }
-      const double lpost = hbase[p * (D + 2) + D];
+      const double lpost = lpbase[2 * p];
       if (lpost0 > lpost) {
         const double pr = exp(alpha * (lpost - lpost0));
         if (ptg_u32_to_unit(wr[1]) < pr) return make_int2(index, attempt);
@@ -156,16 +219,45 @@ __device__ __noinline__ FVec<D> ftransform(const double *__restrict__ M, FVec<D>
   return t;
 }
 
+// likelihood of the streamlined instantiations: the one functor, no switch (same expressions as like_eval, ptg_device.cuh)
+template <int D, int LK>
+__device__ __forceinline__ double flike(const PtgModel &m, const double x[D]) {
+  if constexpr (LK < 0) return like_eval<D>(m, x);
+  else return like_eval_kind<D, LK>(m, x);
+}
 
-// packed ladder statistics: st_di = dir (low 2 bits, biased by 1) | inst << 2 ; st_ud = ups delta | downs delta << 16 ;
-// st_sc = swap_count delta | swap_accept delta << 16   (deltas per launch; the host keeps launches <= 32767 steps)
+// sines.hh:22-54 with the per-dimension constants staged in shared memory (spar: min, width or 1/width, k pi, k).  Expression for
+// expression like_eval_kind<D, PTG_LIKE_SINES>; `pow2` (every width a power of two) replaces the division by the exact reciprocal product.
+template <int D>
+__device__ __forceinline__ double flike_sines_staged(const double *__restrict__ spar, bool pow2, const double *__restrict__ P, const double x[D]) {
+  const double height = __ldg(P), step_scale = __ldg(P + 1);
+  double lprod = 0; int isum = 0;
+#pragma unroll 1
+  for (int i = 0; i < D; i++) {
+    double xi = x[0];
+#pragma unroll
+    for (int j = 1; j < D; j++) if (i == j) xi = x[j];
+    const double mn = spar[4 * i], w = spar[4 * i + 1], kpi = spar[4 * i + 2], kd = spar[4 * i + 3];
+    const double t = xi - mn;
+    const double xx = pow2 ? t * w : t / w;
+    double sv = sin(kpi * xx);
+    sv = sv * sv;
+    lprod += (sv * sv - 1) * height;
+    isum += (int)(xx * kd);
+  }
+  const double result = lprod + (-isum * step_scale);
+  return result;
+}
+
+// packed ladder statistics: st_di = dir (low 2 bits, biased by 1) | inst << 2 ; cnt[FC_UD] = ups delta | downs delta << 16 ;
+// cnt[FC_SC] = swap_count delta | swap_accept delta << 16   (deltas per launch; the host keeps launches <= 16384 steps)
 #define PTG_FAST_MAX_STEPS 16384
 
 // ---- rung-sharded ladders, exchange over peer memory (PtgXchg, ptg_types.h) ---------------------------------------------------
 // publish p: the lanes that hold this block's edge rungs write (x, llike, lprior, beta) into parity p & 1 of this rank's area, then
 // raise the ladder's flag to p + 1
 template <int D>
-__device__ __forceinline__ void fx_publish(const PtgModel &m, const PtgXchg &xc, long long p, const FChain<D> &ch, long long ladder, int rung, int R) {
+__device__ __forceinline__ void fx_publish(const PtgModel &m, const PtgXchg &xc, long long p, const FChain<D> &ch, double lprior, long long ladder, int rung, int R) {
   if (rung != 0 && rung != R - 1) return;
 #pragma unroll 1
   for (int e = 0; e < 2; e++) {
@@ -173,19 +265,22 @@ __device__ __forceinline__ void fx_publish(const PtgModel &m, const PtgXchg &xc,
     double *rec = xc.my_edges + (((size_t)(p & 1) * 2 + e) * m.n_ladders + ladder) * (D + 3);
 #pragma unroll
     for (int k = 0; k < D; k++) rec[k] = ch.x[k];
-    rec[D] = ch.llike; rec[D + 1] = ch.lprior; rec[D + 2] = ch.beta;
+    rec[D] = ch.llike; rec[D + 1] = lprior; rec[D + 2] = ch.beta;
     __threadfence_system();
     *((volatile int *)(xc.my_flags + (size_t)e * m.n_ladders + ladder)) = (int)(p + 1);
   }
 }
 // boundary trial of exchange p (ptg_boundary_swap_kernel: chain.cc:1459-1490 + add_state) against the neighbour's record, read from
-// ITS memory over NVLink once its per-ladder flag says publish p is complete
-template <int D>
-__device__ __forceinline__ void fx_swap(const PtgModel &m, const PtgState &s, const PtgXchg &xc, long long p, FChain<D> &ch, int chain, long long ladder, int gl,
-                                     int rung, int R, int *cnt, int &err) {
+// ITS memory over NVLink once its per-ladder flag says publish p is complete.  Returns the number of appends made (0 or 1 per edge).
+// The wait is bounded by a WATCHDOG the host arms (xc.abort: a word in this rank's mapped memory the host sets when a launch overstays
+// its deadline): an aborted wait raises PTG_ERR_XCHG_TIMEOUT, a sticky device error that stops this handle (ptg_step refuses further work).
+template <int D, bool RF>
+__device__ __forceinline__ int fx_swap(const PtgModel &m, const PtgState &s, const PtgXchg &xc, long long p, FChain<D> &ch, int chain, long long ladder, int gl,
+                                       int rung, int R, int *cnt, double *mapp, int n_mh, int &err) {
   const bool edge_lo = (rung == 0) && xc.has_lo, edge_hi = (rung == R - 1) && xc.has_hi;
-  if (!edge_lo && !edge_hi) return;
-  double *__restrict__ hb = s.hist + chain * ((long long)m.hist_cap * (D + 2));
+  if (!edge_lo && !edge_hi) return 0;
+  int napp = 0;
+  double *__restrict__ hb = s.hist + chain * ((long long)m.hist_cap * PTG_HX(D));
 #pragma unroll 1
   for (int e = 0; e < 2; e++) {
     if (!(e == 0 ? edge_lo : edge_hi)) continue;
@@ -193,7 +288,10 @@ __device__ __forceinline__ void fx_swap(const PtgModel &m, const PtgState &s, co
     const int their_edge = (e == 0) ? 1 : 0;
     const volatile int *flag = (e == 0 ? xc.lo_flags : xc.hi_flags) + (size_t)their_edge * m.n_ladders + ladder;
     long long spins = 0;
-    while (*flag < (int)(p + 1)) { if (++spins > (1ll << 24)) { err = 6; break; } __nanosleep(64); }
+    while (*flag < (int)(p + 1)) {
+      if ((++spins & 1023) == 0 && xc.abort && *((volatile int *)xc.abort)) { err = PTG_ERR_XCHG_TIMEOUT; break; }
+      __nanosleep(64);
+    }
     if (err) break;
     __threadfence_system();
     const volatile double *rec = (e == 0 ? xc.lo_edges : xc.hi_edges) + (((size_t)(p & 1) * 2 + their_edge) * m.n_ladders + ladder) * (D + 3);
@@ -213,35 +311,65 @@ __device__ __forceinline__ void fx_swap(const PtgModel &m, const PtgState &s, co
     if (accept) {
 #pragma unroll
       for (int k = 0; k < D; k++) ch.x[k] = rec[k];
-      ch.llike = nb_ll; ch.lprior = nb_lprior;
-      ch.lpost = nb_lprior + ch.beta * nb_ll; // lpost recomputed = lprior(x) + beta*llike (chain.cc:925-928)
+      ch.llike = nb_ll; mapp[2] = nb_lprior;
+      mapp[1] = nb_lprior + ch.beta * nb_ll; // lpost recomputed = lprior(x) + beta*llike (chain.cc:925-928)
     }
-    fappend<D>(m, s, ch, chain, hb, cnt);
+    fappend<D, RF>(m, s, ch, chain, hb, cnt, mapp, n_mh);
+    napp++;
     if (i_am_lower) cnt[FC_SC] += 1 + (accept ? (1 << 16) : 0); // counted at the pair's lower rung
   }
+  return napp;
 }
 
 // XCHG: 0 = plain; 1 = with the rung-boundary exchange in the prologue / epilogue (ptg_step_exchange); 2 = also inside the iteration loop.
+// LK  : -1 = every feature at run time; >= 0 = streamlined configuration (see the head of this file) with likelihood kind LK.
 // Separate instantiations: each form's extra code costs registers and stack, and the plain kernel carries none of it
-template <int D, int XCHG>
+template <int D, int XCHG, int LK>
 __global__ void __launch_bounds__(PTG_FSTEP_MAX_THREADS, 1) ptg_fstep_kernel(const __grid_constant__ PtgModel m, PtgState s, long long step0, int n_steps, int W, const __grid_constant__ PtgXchg xc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr bool SL = (LK >= 0);                 // streamlined: the FS(run-time expression, folded value) flags below are constants
+#define FS(expr, val) (SL ? (val) : (expr))
+  constexpr int NPAIR = (D + 1) / 2;
   const int R = m.n_rungs, NP = m.n_props;
-  double *sbins = reinterpret_cast<double *>(smem_raw);                   // [R][NP]
-  FProp *sprop = reinterpret_cast<FProp *>(sbins + R * NP);               // [NP]
-  int *cnt = reinterpret_cast<int *>(sprop + NP) + threadIdx.x * PTG_FC_STRIDE; // [blockDim][PTG_FC_STRIDE], this thread's row
-  for (int i = threadIdx.x; i < R * NP; i += blockDim.x) sbins[i] = m.bins[i];
+  FShared<D> sh;
+  sh.carve(smem_raw, blockDim.x, R, NP);
+  for (int i = threadIdx.x; i < R * NP; i += blockDim.x) sh.bins[i] = m.bins[i];
   for (int i = threadIdx.x; i < NP; i += blockDim.x) {
     const PtgProp &p = m.props[i];
     FProp q;
     q.snooker = p.snooker; q.g1frac = p.g1frac; q.gamma_std = p.gamma_std; q.reduce_gamma = p.reduce_gamma; q.ignore_frac = p.ignore_frac;
     q.unlikely_alpha = p.unlikely_alpha; q.one_d_frac = p.one_d_frac; q.kind = p.kind; q.has_transform = p.has_transform;
     q.sigma_off = p.sigma_off; q.trans_off = p.trans_off;
-    sprop[i] = q;
+    sh.prop[i] = q;
+  }
+  bool sines_pow2 = true; // every width of the sines surface is a power of two: x / w == x * (1 / w) exactly
+  if (LK == PTG_LIKE_SINES) {
+    // per-dimension constants of sines.hh:22-54 in the order the functor uses them (like_eval_kind<D, PTG_LIKE_SINES>)
+    const double *__restrict__ P = m.lparams;
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+      const double w = __ldg(P + 2 + 2 * D + i) - __ldg(P + 2 + D + i);
+      int e; const double mant = frexp(w, &e);
+      if (!(mant == 0.5 && e > -1000 && e < 1000)) sines_pow2 = false;
+    }
+    if (threadIdx.x < D) {
+      const int i = threadIdx.x;
+      const int k = (int)__ldg(P + 2 + i);
+      const double mn = __ldg(P + 2 + D + i), w = __ldg(P + 2 + 2 * D + i) - mn;
+      sh.spar[4 * i] = mn; sh.spar[4 * i + 1] = sines_pow2 ? 1.0 / w : w; sh.spar[4 * i + 2] = k * PTG_PI; sh.spar[4 * i + 3] = (double)k;
+    }
   }
   __syncthreads();
-
+  const FProp *sprop = sh.prop;
+  int *cnt = sh.cnt + threadIdx.x * PTG_FC_STRIDE;          // this thread's row
+  double *mapp = sh.map + 3 * threadIdx.x;                  // [0] running MAP, [1] current lpost, [2] current lprior
+#define LPOST (mapp[1])
+#define LPRIOR (mapp[2])
   const int lane = threadIdx.x & 31;
+  double *wpool = sh.pool + (size_t)(threadIdx.x >> 5) * (2 * NPAIR * 32); // this warp's slots
+  double *wlus = sh.lus + (threadIdx.x & ~31);
+  unsigned char *witems = sh.items + (size_t)(threadIdx.x >> 5) * (32 * NPAIR);
+
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int gpw = 32 / W, g = lane / W, rung = lane - g * W;
   if (warp * gpw >= m.n_ladders) return; // whole warp beyond the batch
@@ -252,20 +380,12 @@ __global__ void __launch_bounds__(PTG_FSTEP_MAX_THREADS, 1) ptg_fstep_kernel(con
   const int chain = active ? (int)(ladder * R + rung) : 0; // ptg_create guarantees n_chains < 2^31
   // Long-lived values are kept to 32 bits and widened at the point of use (register budget): global ladder id, chain id.
   const int gl = (int)(m.ladder_offset + warp * gpw) + g; // ptg_create guarantees ladder ids < 2^31
-#ifndef PTG_NO_NARROW_IDS
 #define stream_base ((uint64_t)(gl - g) * PTG_STREAM_STRIDE)
 #define my_stream ((uint64_t)gl * PTG_STREAM_STRIDE + (uint64_t)rung)
 #define ladder_stream ((uint64_t)gl * PTG_STREAM_STRIDE + PTG_STREAM_LADDER)
-#define hbase (s.hist + chain * ((long long)m.hist_cap * (D + 2)))
+#define hbase (s.hist + chain * ((long long)m.hist_cap * PTG_HX(D)))
 #define step ((uint64_t)(step0 + it))
-#else
-  const uint64_t stream_base = ((uint64_t)(gl - g) * PTG_STREAM_STRIDE);
-  const uint64_t my_stream = ((uint64_t)gl * PTG_STREAM_STRIDE + (uint64_t)rung);
-  const uint64_t ladder_stream = ((uint64_t)gl * PTG_STREAM_STRIDE + PTG_STREAM_LADDER);
-  double *__restrict__ hbase = (s.hist + chain * ((long long)m.hist_cap * (D + 2)));
-#define step ((uint64_t)(step0 + it))
-#endif
-  const double *bins = sbins + (rung < R ? rung : 0) * NP;
+  const double *bins = sh.bins + (rung < R ? rung : 0) * NP;
 
   FChain<D> ch;
   int st_di = 1;
@@ -274,48 +394,61 @@ __global__ void __launch_bounds__(PTG_FSTEP_MAX_THREADS, 1) ptg_fstep_kernel(con
   if (active) {
 #pragma unroll
     for (int k = 0; k < D; k++) ch.x[k] = s.cur_x[(long long)k * m.n_chains + chain];
-    ch.lpost = s.lpost[chain]; ch.llike = s.llike[chain]; ch.lprior = s.lprior[chain]; ch.beta = s.beta[chain];
+    LPOST = s.lpost[chain]; ch.llike = s.llike[chain]; LPRIOR = s.lprior[chain]; ch.beta = s.beta[chain];
     const long long nsize = s.nsize[chain];
     ch.slot = (int)(nsize % m.hist_cap);
     ch.hfill = (int)(nsize > m.hist_cap ? (long long)m.hist_cap : nsize);
     ch.since_save = (int)(s.nhist[chain] % m.save_every);
     cnt[FC_LAST_TYPE] = s.last_type[chain];
     st_di = (s.directions[chain] + 1) | (s.instances[chain] << 2);
+    mapp[0] = s.map_lpost[chain];
   } else {
 #pragma unroll
     for (int k = 0; k < D; k++) ch.x[k] = 0;
-    ch.lpost = ch.llike = ch.lprior = 0; ch.beta = 1;
+    ch.llike = 0; ch.beta = 1;
     ch.slot = 0; ch.hfill = 0; ch.since_save = 0;
+    mapp[0] = 0; LPOST = 0; LPRIOR = 0;
   }
   const int since_save0 = ch.since_save;
   int err = 0;
 
   // ================================================================= rung-sharded ladders: pending cross-GPU boundary swap
   long long xp = xc.index; // running publish index (XCHG instantiation only)
-  if (XCHG && xc.on && xc.swap_in && active) fx_swap<D>(m, s, xc, xp - 1, ch, chain, ladder, gl, rung, R, cnt, err);
+  if (XCHG && xc.on && xc.swap_in && active) cnt[FC_XAPP] += fx_swap<D, !SL>(m, s, xc, xp - 1, ch, chain, ladder, gl, rung, R, cnt, mapp, 0, err);
 
   const int maxswaps = m.maxswaps;
   const double swap_thresh = (R - 1) * m.swap_rate / maxswaps; // chain.cc:1413
   double ptry = 2 * m.swap_rate; if (ptry > 1) ptry = 1;
-  const bool zero_valid = m.zero_valid != 0;
+  const bool zero_valid = FS(m.zero_valid != 0, true);
+  const bool ref_mode = FS(m.swap_mode == PTG_SWAP_REFERENCE, true);
+  // Without temperature evolution the trials of one iteration that share no rung commute: they run as ONE batch and their history
+  // appends are deferred to the iteration's single append.  pry_temps (chain.cc:1809-1846) changes every rung's beta / lpost after
+  // each accepted trial, so with evolution the trials run one by one and append at once, as the reference does.
+  const bool batched = FS(!(m.evolve_rate > 0), true);
+  // lanes that own a swap-trial draw of their ladder (trial j = lane j of the ladder's group)
+  const bool has_swap_item = ref_mode && ladder_ok && R > 1 && rung < maxswaps;
+  const unsigned swapmask = __ballot_sync(0xffffffffu, has_swap_item);
+  const int nfree = 32 - __popc(swapmask), frank = __popc(~swapmask & ((1u << lane) - 1u));
+  // the trial draws of iteration 0 (later iterations get theirs from pool round 1 of the iteration before)
+  if (has_swap_item) {
+    uint32_t q[4];
+    ptg_philox_draw(m.seed, ladder_stream, PTG_DOMAIN_STEP, (uint64_t)step0, (uint32_t)rung, q);
+    int raw = -2; double logu = 0;
+    if (ptg_u32_to_unit(q[0]) < swap_thresh) { raw = (int)(ptg_u32_to_unit(q[1]) * (R - 1)); logu = log(ptg_u52_to_unit(q[2], q[3])); }
+    cnt[FC_RAW] = raw; cnt[FC_LOGU_LO] = __double2loint(logu); cnt[FC_LOGU_HI] = __double2hiint(logu);
+  } else cnt[FC_RAW] = -2;
 
   for (int it = 0; it < n_steps; it++) {
-    bool swapped = false;
+    bool swapped = false;   // took part in a swap trial: no MH update this iteration (chain.cc:1554-1557)
+    bool pending = false;   // owes the history append of a swap trial (made at the end of the iteration)
+    const int n_mh = it - cnt[FC_NSWAPPED]; // MH updates of this chain so far in this launch
 
     // ================================================================= swap phase (chain.cc:1410-1538)
     if (ladder_ok && R > 1) {
-      if (m.swap_mode == PTG_SWAP_REFERENCE) {
-        // lane j prepares trial j: candidate pair and log of its swap draw, from block j of the ladder's stream
-        int raw = -2;
-        double logu = 0;
-        if (rung < maxswaps) {
-          uint32_t q[4];
-          ptg_philox_draw(m.seed, ladder_stream, PTG_DOMAIN_STEP, step, (uint32_t)rung, q);
-          if (ptg_u32_to_unit(q[0]) < swap_thresh) {
-            raw = (int)(ptg_u32_to_unit(q[1]) * (R - 1));
-            logu = log(ptg_u52_to_unit(q[2], q[3]));
-          }
-        }
+      if (ref_mode) {
+        // lane j holds trial j: candidate pair and log of its swap draw, from block j of the ladder's stream
+        const int raw = cnt[FC_RAW];
+        const double logu = __hiloint2double(cnt[FC_LOGU_HI], cnt[FC_LOGU_LO]);
         // serial de-dup (iswaps[j]==cand or iswaps[j]+1==cand for an earlier surviving j) over the trials that drew a pair
         unsigned used = 0, live = 0; // live: bit j = trial j survives
         unsigned cand = (__ballot_sync(gm, raw >= 0) & gm) >> (g * W);
@@ -325,6 +458,54 @@ __global__ void __launch_bounds__(PTG_FSTEP_MAX_THREADS, 1) ptg_fstep_kernel(con
           const int c = __shfl_sync(gm, raw, i, W);
           if (!((used >> c) & 1u) && !(c > 0 && ((used >> (c - 1)) & 1u))) { used |= 1u << c; live |= 1u << i; }
         }
+        if (batched) {
+          // A surviving trial on pair c can only share a rung with an EARLIER surviving trial on pair c+1 (the de-dup removed the other
+          // overlaps).  Round by round, every live trial whose pair c has no live trial on c+1 runs; all pairs of a round are disjoint.
+          while (live) {
+            const bool mine = ((live >> rung) & 1u) != 0;                            // this lane's trial is live
+            const unsigned pairs_live = __reduce_or_sync(gm, mine ? (1u << raw) : 0u);
+            const bool now = mine && !((pairs_live >> (raw + 1)) & 1u);
+            const unsigned pairs = __reduce_or_sync(gm, now ? (1u << raw) : 0u);     // bit c: pair (c, c+1) is tried in this round
+            live &= ~((__ballot_sync(gm, now) & gm) >> (g * W));
+            if (now) wlus[g * W + raw] = logu;                                       // hand log u to the pair's lower rung
+            __syncwarp(gm);                                                          // (ladder groups of one warp loop independently)
+            const bool is_lo = ((pairs >> rung) & 1u) != 0, is_hi = rung > 0 && ((pairs >> (rung - 1)) & 1u) != 0, involved = is_lo || is_hi;
+            const double lu = is_lo ? wlus[g * W + rung] : 0.0;
+            // every lane r evaluates pair (r, r+1); the lower rung decides
+            const double ll_up = __shfl_down_sync(gm, ch.llike, 1, W), b_up = __shfl_down_sync(gm, ch.beta, 1, W);
+            double lla = ch.llike; if (!(lla > -1e200)) lla = -1e200;
+            double llb = ll_up; if (!(llb > -1e200)) llb = -1e200;
+            const double lhr = -(b_up - ch.beta) * (llb - lla);
+            int acc_mine = is_lo ? 1 : 0;
+            if (is_lo && lhr < 0) acc_mine = (lu < lhr) ? 1 : 0;
+            const int acc_below = __shfl_up_sync(gm, acc_mine, 1, W);
+            const bool accept = is_lo ? (acc_mine != 0) : (is_hi && acc_below != 0);
+            if (is_lo && rung > 0) { // ups / downs of the lower rung before the exchange (chain.cc:1440-1443)
+              const int dir = (st_di & 3) - 1;
+              if (dir > 0) cnt[FC_UD] += 1;
+              if (dir < 0) cnt[FC_UD] += 1 << 16;
+            }
+            // a rung already in an earlier trial of this iteration (H4) stores that trial's state before it changes again
+            if (involved && pending && active) { fappend<D, !SL>(m, s, ch, chain, hbase, cnt, mapp, n_mh); cnt[FC_XAPP]++; pending = false; }
+            const int partner = is_lo ? rung + 1 : (is_hi ? rung - 1 : rung);
+            {
+#pragma unroll
+              for (int k = 0; k < D; k++) { const double v = __shfl_sync(gm, ch.x[k], partner, W); if (accept) ch.x[k] = v; }
+              { const double v = __shfl_sync(gm, ch.llike, partner, W); if (accept) ch.llike = v; }
+              { const int v = __shfl_sync(gm, st_di, partner, W); if (accept) st_di = v; }
+              double nlp = 0;
+              if (accept) nlp = mapp[3 * (partner - rung) + 2];                       // the partner's lprior slot
+              __syncwarp(gm);
+              if (accept) { LPRIOR = nlp; LPOST = nlp + ch.beta * ch.llike; }         // lpost recomputed = lprior(x) + beta*llike (chain.cc:925-928)
+            }
+            if (accept) {
+              if (is_lo && rung == 0) st_di = (st_di & ~3) | 2;          // directions[0] = +1
+              if (is_hi && rung == R - 1) st_di = (st_di & ~3) | 0;      // directions[R-1] = -1
+            }
+            if (is_lo) cnt[FC_SC] += 1 + (accept ? (1 << 16) : 0);
+            if (involved) { if (active) pending = true; swapped = true; }
+          }
+        } else
         while (live) {
           const int j = __ffs(live) - 1;
           live &= live - 1;
@@ -349,11 +530,11 @@ __global__ void __launch_bounds__(PTG_FSTEP_MAX_THREADS, 1) ptg_fstep_kernel(con
 #pragma unroll
             for (int k = 0; k < D; k++) { const double v = __shfl_sync(gm, ch.x[k], partner, W); ch.x[k] = v; }
             { const double v = __shfl_sync(gm, ch.llike, partner, W); ch.llike = v; }
-            { const double v = __shfl_sync(gm, ch.lprior, partner, W); ch.lprior = v; }
-            if (involved) ch.lpost = ch.lprior + ch.beta * ch.llike; // lpost recomputed = lprior(x) + beta*llike (chain.cc:925-928)
+            { const double v = __shfl_sync(gm, LPRIOR, partner, W); LPRIOR = v; }
+            if (involved) LPOST = LPRIOR + ch.beta * ch.llike; // lpost recomputed = lprior(x) + beta*llike (chain.cc:925-928)
           }
           if (involved) {
-            if (active) fappend<D>(m, s, ch, chain, hbase, cnt);
+            if (active) { fappend<D, !SL>(m, s, ch, chain, hbase, cnt, mapp, n_mh); if (swapped) cnt[FC_XAPP]++; }
             swapped = true;
           }
           if (accept) {
@@ -362,12 +543,13 @@ __global__ void __launch_bounds__(PTG_FSTEP_MAX_THREADS, 1) ptg_fstep_kernel(con
             if (c == 0 && is_lo) st_di = (st_di & ~3) | 2;          // directions[0] = +1
             if (c + 1 == R - 1 && is_hi) st_di = (st_di & ~3) | 0;  // directions[R-1] = -1
             if (is_lo) cnt[FC_SC] += 1 << 16;
-            if (m.evolve_rate > 0) {
+            {
               // pry_temps, one pried gap (chain.cc:1809-1846) + resetTemp (chain.cc:1088-1091), reference summation order
               const double rate = m.evolve_rate;
-              const double b_next = __shfl_down_sync(gm, ch.beta, 1, W), lp_next = __shfl_down_sync(gm, ch.lpost, 1, W);
+              const double lp_mine = LPOST;
+              const double b_next = __shfl_down_sync(gm, ch.beta, 1, W), lp_next = __shfl_down_sync(gm, lp_mine, 1, W);
               double sp = ch.beta - b_next;
-              if (m.evolve_lpost_cut >= 0 && ch.lpost - lp_next > m.evolve_lpost_cut * ch.beta) sp *= (1.0 + rate);
+              if (m.evolve_lpost_cut >= 0 && lp_mine - lp_next > m.evolve_lpost_cut * ch.beta) sp *= (1.0 + rate);
               if (is_lo) sp *= 1.0 + rate;
               double sum = 0;
               for (int k = 0; k < R - 1; k++) sum += __shfl_sync(gm, sp, k, W);
@@ -378,7 +560,7 @@ __global__ void __launch_bounds__(PTG_FSTEP_MAX_THREADS, 1) ptg_fstep_kernel(con
                 invtemp -= __shfl_sync(gm, qn, k - 1, W);
                 if (rung == k) mine = invtemp;
               }
-              if (rung >= 1 && rung < R - 1) { ch.beta = mine; ch.lpost = ch.lprior + mine * ch.llike; }
+              if (rung >= 1 && rung < R - 1) { ch.beta = mine; LPOST = LPRIOR + mine * ch.llike; }
             }
           }
           if (is_lo) cnt[FC_SC] += 1;
@@ -411,21 +593,22 @@ __global__ void __launch_bounds__(PTG_FSTEP_MAX_THREADS, 1) ptg_fstep_kernel(con
         double nx[D];
 #pragma unroll
         for (int k = 0; k < D; k++) nx[k] = __shfl_sync(gm, ch.x[k], partner, W);
-        const double nll = __shfl_sync(gm, ch.llike, partner, W), nlp = __shfl_sync(gm, ch.lprior, partner, W);
+        const double nll = __shfl_sync(gm, ch.llike, partner, W), nlp = __shfl_sync(gm, LPRIOR, partner, W);
         const int ndi = __shfl_sync(gm, st_di, partner, W);
         if (tried && accept) {
 #pragma unroll
           for (int k = 0; k < D; k++) ch.x[k] = nx[k];
-          ch.llike = nll; ch.lprior = nlp;
-          ch.lpost = ch.lprior + ch.beta * ch.llike;
+          ch.llike = nll; LPRIOR = nlp;
+          LPOST = nlp + ch.beta * ch.llike;
           st_di = ndi;
           if (rung == 0) st_di = (st_di & ~3) | 2;
           if (rung == R - 1) st_di = (st_di & ~3) | 0;
         }
-        if (tried) { if (active) fappend<D>(m, s, ch, chain, hbase, cnt); swapped = true; }
+        if (tried) { if (active) pending = true; swapped = true; }
       }
     }
     __syncwarp();
+    if (swapped) cnt[FC_NSWAPPED]++;
 
     // ================================================================= MH update (chain.cc:966-1022)
     const bool do_mh = active && !swapped;
@@ -443,7 +626,7 @@ __global__ void __launch_bounds__(PTG_FSTEP_MAX_THREADS, 1) ptg_fstep_kernel(con
 
     // ---- member selection: first ready member with u < bin_max (proposal_distribution.cc:105-112)
     int member = 0;
-    if (m.wrap_in_set) {
+    if (FS(m.wrap_in_set, 1)) {
       const double x = (NP > 1) ? ptg_u32_to_unit(wA[0]) : 0.0;
       if (ch.hfill >= D * 10 || !do_mh) { // every member ready (differential_evolution::is_ready, proposal_distribution.hh:407)
         member = NP - 1;
@@ -456,64 +639,133 @@ __global__ void __launch_bounds__(PTG_FSTEP_MAX_THREADS, 1) ptg_fstep_kernel(con
     }
     const FProp &p = sprop[member];
     const int kind = do_mh ? p.kind : 0;
-    const double oldlprior = ch.lpost - ch.beta * ch.llike;
     double newx[D];
     double prop_lh = 0;
     int type = 0;
     bool valid = zero_valid;
 
-    // ---- Gaussian members: cooperative normals, then x' = x + M (z o sigma)  (proposal_distribution.hh:194-218)
-    {
-      double z[D];
-      wcoop_normals<D>(m.seed, step, stream_base, W, kind == PTG_PROP_GAUSS, z);
-#pragma unroll
-      for (int i = 0; i < D; i++) newx[i] = ch.x[i];
-      if (kind == PTG_PROP_GAUSS) {
-        const double *__restrict__ sig = m.prop_data + p.sigma_off;
-#pragma unroll
-        for (int i = 0; i < D; i++) z[i] = z[i] * __ldg(sig + i) + 0.0;
-        if (p.one_d_frac > 0 && ptg_u32_to_unit(wA[1]) < p.one_d_frac) {
-          const int ia = (int)(D * ptg_u32_to_unit(wA[2]));
-#pragma unroll
-          for (int j = 0; j < D; j++) if (j != ia) z[j] = 0.0;
-          type = 1;
-        }
-        if (p.has_transform) {
-          FVec<D> o;
-#pragma unroll
-          for (int i = 0; i < D; i++) o.v[i] = z[i];
-          o = ftransform<D>(m.prop_data + p.trans_off, o);
-#pragma unroll
-          for (int i = 0; i < D; i++) z[i] = o.v[i];
-        }
-#pragma unroll
-        for (int i = 0; i < D; i++) newx[i] = ch.x[i] + z[i];
-      }
-    }
-    // ---- differential evolution (proposal_distribution.cc:489-591,744-801)
-    if (kind == PTG_PROP_DE) {
+    // ---- differential evolution, part 1: history indices (proposal_distribution.cc:744-778); the records are requested from L2 now
+    //      and read after pool round 1, whose work covers their DRAM latency
+    const bool is_de = (kind == PTG_PROP_DE);
+    bool snooker = false;
+    int i1 = 0, i2 = 0, iz = 0, az = 0;
+    if (is_de) {
       const int hsize = ch.hfill;
       int start = 0;
       if ((hsize - D * 100) * (1 - p.ignore_frac) > D * 10) start = (int)((hsize - D * 100) * p.ignore_frac);
-      const bool snooker = p.snooker > ptg_u32_to_unit(wA[1]);
-      const double ug = ptg_u32_to_unit(wA[2]);
-      int i1, i2, iz = 0, az = 0;
-      const bool slow = p.unlikely_alpha > 0;
+      snooker = p.snooker > ptg_u32_to_unit(wA[1]);
+      const bool slow = FS(p.unlikely_alpha > 0, false);
       if (!slow) {
         i1 = (int)(start + (hsize - start) * ptg_u32_to_unit(wA[3]));
         i2 = (int)(start + (hsize - start) * ptg_u32_to_unit(wB[0]));
         iz = (int)(start + (hsize - start) * ptg_u32_to_unit(wB[1]));
         az = 1;
       } else {
-        const double mapl = s.map_lpost[chain];
-        if (snooker) { const int2 r = fde_index_slow<D>(m, ch.hfill, ch.slot, hbase, mapl, m.seed, my_stream, step, p.ignore_frac, p.unlikely_alpha, wB[1], 0, 0); iz = r.x; az = r.y; }
-        i1 = fde_index_slow<D>(m, ch.hfill, ch.slot, hbase, mapl, m.seed, my_stream, step, p.ignore_frac, p.unlikely_alpha, wA[3], 1, 0).x;
-        i2 = fde_index_slow<D>(m, ch.hfill, ch.slot, hbase, mapl, m.seed, my_stream, step, p.ignore_frac, p.unlikely_alpha, wB[0], 2, 0).x;
+        const double mapl = mapp[0];
+        const double *lpb = s.hist_lp + 2 * (chain * (long long)m.hist_cap);
+        if (snooker) { const int2 r = fde_index_slow<D>(m, ch.hfill, ch.slot, lpb, mapl, m.seed, my_stream, step, p.ignore_frac, p.unlikely_alpha, wB[1], 0, 0); iz = r.x; az = r.y; }
+        i1 = fde_index_slow<D>(m, ch.hfill, ch.slot, lpb, mapl, m.seed, my_stream, step, p.ignore_frac, p.unlikely_alpha, wA[3], 1, 0).x;
+        i2 = fde_index_slow<D>(m, ch.hfill, ch.slot, lpb, mapl, m.seed, my_stream, step, p.ignore_frac, p.unlikely_alpha, wB[0], 2, 0).x;
       }
-      const double *s1 = fhist<D>(m, ch, hbase, i1), *s2 = fhist<D>(m, ch, hbase, i2);
-      double a[D], b[D];
+      i1 = fslot<D>(m, ch, i1); i2 = fslot<D>(m, ch, i2); // physical slots from here on
+#ifndef PTG_F_NO_PREFETCH
+      asm volatile("prefetch.global.L2 [%0];" :: "l"(hbase + (long long)i1 * PTG_HX(D)));
+      asm volatile("prefetch.global.L2 [%0];" :: "l"(hbase + (long long)i2 * PTG_HX(D)));
+      if (snooker) asm volatile("prefetch.global.L2 [%0];" :: "l"(hbase + (long long)fslot<D>(m, ch, iz) * PTG_HX(D)));
+#endif
+    }
+
+    // ---- pool round 1: Box-Muller pairs of the Gaussian-member lanes + the next iteration's swap-trial draws
+    // A Gaussian lane needs all NPAIR pairs, or -- for a single-axis step (proposal_distribution.hh:197-205) -- only the pair of its axis.
+    const bool is_gauss = (kind == PTG_PROP_GAUSS);
+    int axis = -1; // >= 0: single-axis step
+    if (is_gauss && p.one_d_frac > 0 && ptg_u32_to_unit(wA[1]) < p.one_d_frac) axis = (int)(D * ptg_u32_to_unit(wA[2]));
+    {
+      const unsigned many = __ballot_sync(0xffffffffu, is_gauss), mfull = __ballot_sync(0xffffffffu, is_gauss && axis < 0);
+      const unsigned lt = (1u << lane) - 1u;
+      const int total = __popc(many) + (NPAIR - 1) * __popc(mfull);
+      if (is_gauss) {
+        const int off = __popc(many & lt) + (NPAIR - 1) * __popc(mfull & lt);
+        if (axis >= 0) witems[off] = (unsigned char)((lane << 3) | (axis >> 1));
+        else {
 #pragma unroll
-      for (int i = 0; i < D; i++) { a[i] = __ldcg(s1 + i); b[i] = __ldcg(s2 + i); } // random records: no reuse, keep them out of L1
+          for (int q = 0; q < NPAIR; q++) witems[off + q] = (unsigned char)((lane << 3) | q);
+        }
+      }
+      __syncwarp();
+      // round 0: trial lanes take their own draw, the other lanes the first `nfree` pairs; later rounds: 32 pairs each
+      for (int base = 0, first = 1; first || base < total; first = 0) {
+        int typ = 0, k = -1;
+        if (first) { if (has_swap_item) typ = 1; else k = frank; }
+        else k = base + lane;
+        if (k >= 0 && k < total) typ = 2;
+        if (typ) {
+          uint64_t stream = ladder_stream; uint64_t stp = step + 1; uint32_t blk = (uint32_t)rung;
+          int owner = 0, pr = 0;
+          if (typ == 2) {
+            const int code = witems[k];
+            owner = code >> 3; pr = code & 7;
+            // stream of the owner's chain: (global ladder)*128 + rung, with ladder = warp's first ladder + owner / W
+            stream = stream_base + (uint64_t)(owner / W) * PTG_STREAM_STRIDE + (uint64_t)(owner % W);
+            stp = step; blk = PTG_BLK_NORMAL + pr;
+          }
+          uint32_t q[4];
+          ptg_philox_draw(m.seed, stream, PTG_DOMAIN_STEP, stp, blk, q);
+          bool want = true;
+          double ul = ptg_u52_to_unit(q[0], q[1]);
+          if (typ == 1) {
+            want = ptg_u32_to_unit(q[0]) < swap_thresh;
+            ul = ptg_u52_to_unit(q[2], q[3]);
+            cnt[FC_RAW] = want ? (int)(ptg_u32_to_unit(q[1]) * (R - 1)) : -2;
+          }
+          if (want) {
+            const double lg = log(ul);
+            if (typ == 1) { cnt[FC_LOGU_LO] = __double2loint(lg); cnt[FC_LOGU_HI] = __double2hiint(lg); }
+            else { // box_muller (ptg_device.cuh): z0 = r cos, z1 = r sin
+              const double r = sqrt(-2.0 * lg);
+              double sn, cs;
+              sincospi(2.0 * ptg_u52_to_unit(q[2], q[3]), &sn, &cs);
+              wpool[(2 * pr) * 32 + owner] = r * cs;
+              wpool[(2 * pr + 1) * 32 + owner] = r * sn;
+            }
+          }
+        }
+        base += first ? nfree : 32;
+      }
+      __syncwarp();
+    }
+
+    // ---- Gaussian members: x' = x + M (z o sigma)  (proposal_distribution.hh:194-218)
+#pragma unroll
+    for (int i = 0; i < D; i++) newx[i] = ch.x[i];
+    if (is_gauss) {
+      double z[D];
+      const double *__restrict__ sig = m.prop_data + p.sigma_off;
+#pragma unroll
+      for (int i = 0; i < D; i++) {
+        z[i] = 0.0;
+        if (axis < 0 || axis == i) z[i] = wpool[i * 32 + lane] * __ldg(sig + i) + 0.0;
+      }
+      if (axis >= 0) type = 1;
+      if (FS(p.has_transform, 0)) {
+        FVec<D> o;
+#pragma unroll
+        for (int i = 0; i < D; i++) o.v[i] = z[i];
+        o = ftransform<D>(m.prop_data + p.trans_off, o);
+#pragma unroll
+        for (int i = 0; i < D; i++) z[i] = o.v[i];
+      }
+#pragma unroll
+      for (int i = 0; i < D; i++) newx[i] = ch.x[i] + z[i];
+    }
+    __syncwarp(); // the pool slots are reused by round 2
+    // ---- differential evolution, part 2 (proposal_distribution.cc:489-591)
+    double sn_a = 1, sn_b = 1; // arguments of the two snooker logarithms
+    if (is_de) {
+      const double ug = ptg_u32_to_unit(wA[2]);
+      double a[D], b[D];
+      fload_rec<D>(hbase + (long long)i1 * PTG_HX(D), a);
+      fload_rec<D>(hbase + (long long)i2 * PTG_HX(D), b);
       if (!snooker) {
         // draw_standard: prop = (s + gamma s1) + (-gamma s2); the jitter drawn by the reference is discarded (H8-1)
         double gamma = p.gamma_std;
@@ -529,14 +781,15 @@ __global__ void __launch_bounds__(PTG_FSTEP_MAX_THREADS, 1) ptg_fstep_kernel(con
         double smznorm2 = 0, minusz[D], smz[D];
         int isafe = 0;
         while (true) {
-          const double *zz = fhist<D>(m, ch, hbase, iz);
+          double zz[D];
+          fload_rec<D>(hbase + (long long)fslot<D>(m, ch, iz) * PTG_HX(D), zz);
           smznorm2 = 0;
 #pragma unroll
           for (int i = 0; i < D; i++) { minusz[i] = zz[i] * (-1); smz[i] = ch.x[i] + minusz[i]; }
 #pragma unroll
           for (int i = 0; i < D; i++) smznorm2 += smz[i] * smz[i];
           if (smznorm2 != 0 || ++isafe > 1000) break;
-          const int2 r = fde_index_slow<D>(m, ch.hfill, ch.slot, hbase, s.map_lpost[chain], m.seed, my_stream, step, p.ignore_frac, p.unlikely_alpha, wB[1], 0, az);
+          const int2 r = fde_index_slow<D>(m, ch.hfill, ch.slot, s.hist_lp + 2 * (chain * (long long)m.hist_cap), mapp[0], m.seed, my_stream, step, p.ignore_frac, p.unlikely_alpha, wB[1], 0, az);
           iz = r.x; az = r.y;
         }
         double dot = 0;
@@ -553,10 +806,10 @@ __global__ void __launch_bounds__(PTG_FSTEP_MAX_THREADS, 1) ptg_fstep_kernel(con
           const double pmz = newx[i] + minusz[i];
           pmz2 += pmz * pmz;
         }
-        prop_lh = (log(pmz2) - log(smznorm2)) * (D - 1) / 2.0;
+        sn_a = pmz2; sn_b = smznorm2; // prop_lh = (log(pmz2) - log(smznorm2)) (D - 1) / 2, logarithms taken in pool round 2
         type = 1;
       }
-    } else if (kind == PTG_PROP_PRIOR_DRAW) {
+    } else if (FS(kind == PTG_PROP_PRIOR_DRAW, false)) {
       FVec<D> xv;
 #pragma unroll
       for (int i = 0; i < D; i++) xv.v[i] = ch.x[i];
@@ -565,10 +818,35 @@ __global__ void __launch_bounds__(PTG_FSTEP_MAX_THREADS, 1) ptg_fstep_kernel(con
       for (int i = 0; i < D; i++) newx[i] = r.v[i];
       prop_lh = r.aux; valid = r.ok != 0;
     }
-    if (m.wrap_in_set) type = member + 10 * type;
+    if (FS(m.wrap_in_set, 1)) type = member + 10 * type;
+
+    // ---- pool round 2: log of the Metropolis draw on every MH lane; the snooker lanes' two logarithms on the lanes without an MH update
+    double log_uacc = 0;
+    {
+      const unsigned msn = __ballot_sync(0xffffffffu, snooker), midle = __ballot_sync(0xffffffffu, !do_mh);
+      const unsigned lt = (1u << lane) - 1u;
+      const int nitem = 2 * __popc(msn), nidle = __popc(midle), irank = __popc(midle & lt);
+      if (snooker) { const int o = 2 * __popc(msn & lt); wpool[o] = sn_a; wpool[o + 1] = sn_b; }
+      __syncwarp();
+      for (int base = 0, first = 1; first || base < nitem; first = 0) {
+        int k = -1;
+        if (first) { if (!do_mh) k = irank; }
+        else k = base + lane;
+        const bool item = (k >= 0 && k < nitem);
+        if (item || (first && do_mh)) {
+          const double arg = item ? wpool[k] : ptg_u52_to_unit(wB[2], wB[3]);
+          const double lg = log(arg);
+          if (item) wpool[k] = lg; else log_uacc = lg;
+        }
+        base += first ? nidle : 32;
+        __syncwarp();
+      }
+      if (snooker) { const int o = 2 * __popc(msn & lt); prop_lh = (wpool[o] - wpool[o + 1]) * (D - 1) / 2.0; }
+      __syncwarp();
+    }
 
     // ---- enforce, prior, gated likelihood (chain.cc:976-987)
-    if (m.any_bound && valid) {
+    if (FS(m.any_bound, 0) && valid) {
       FVec<D> xv;
 #pragma unroll
       for (int i = 0; i < D; i++) xv.v[i] = newx[i];
@@ -578,7 +856,7 @@ __global__ void __launch_bounds__(PTG_FSTEP_MAX_THREADS, 1) ptg_fstep_kernel(con
       valid = r.ok != 0;
     }
     double newlprior;
-    if (m.all_uniform_prior) {
+    if (FS(m.all_uniform_prior, 1)) {
       bool in = valid;
 #pragma unroll
       for (int i = 0; i < D; i++) in = in && !(newx[i] < m.prior[i].a) && !(newx[i] > m.prior[i].b);
@@ -592,30 +870,34 @@ __global__ void __launch_bounds__(PTG_FSTEP_MAX_THREADS, 1) ptg_fstep_kernel(con
     double newlike = -CUDART_INF, newlpost = -CUDART_INF;
     int code = 0;
     bool accept = true;
-    const bool gate = valid && ((newlprior > -1e200) || (newlprior - oldlprior > m.dprior_min));
+    const double cur_lpost = LPOST;
+    // chain.cc:980.  A proposal outside the prior's support has newlprior = -inf and newlprior - oldlprior > dprior_min is false for every
+    // finite oldlprior, so with an all-uniform prior (every current state inside the box) the second clause never opens the gate
+    const bool gate = valid && ((newlprior > -1e200) || FS(newlprior - (cur_lpost - ch.beta * ch.llike) > m.dprior_min, false));
     if (gate && do_mh) {
-      newlike = like_eval<D>(m, newx);
+      if constexpr (LK == PTG_LIKE_SINES) newlike = flike_sines_staged<D>(sh.spar, sines_pow2, m.lparams, newx);
+      else newlike = flike<D, LK>(m, newx);
       newlpost = newlike * ch.beta + newlprior;
     } else code |= PTG_TRACE_NOLIKE;
     // ---- Metropolis test (chain.cc:989-1001)
     double lhr = prop_lh;
     if (isnan(lhr)) accept = false;
-    lhr += newlpost - ch.lpost;
+    lhr += newlpost - cur_lpost;
     if (!valid) { accept = false; code |= PTG_TRACE_INVALID; }
-    if (accept && lhr < 0) accept = (log(ptg_u52_to_unit(wB[2], wB[3])) < lhr);
+    if (accept && lhr < 0) accept = (log_uacc < lhr);
     if (do_mh) {
-      cnt[FC_NTRIES]++;
       if (accept) {
         cnt[FC_NACCEPT]++;
         cnt[FC_LAST_TYPE] = type;
 #pragma unroll
         for (int i = 0; i < D; i++) ch.x[i] = newx[i];
-        ch.llike = newlike; ch.lpost = newlpost; ch.lprior = newlprior;
+        ch.llike = newlike; LPOST = newlpost; LPRIOR = newlprior;
         code |= PTG_TRACE_ACCEPT;
       }
-      fappend<D>(m, s, ch, chain, hbase, cnt);
     }
-    if (active && (long long)step < m.trace_steps) {
+    // the iteration's history append: the MH lanes' new state, the swapped lanes' pending trial state
+    if (do_mh || pending) fappend<D, !SL>(m, s, ch, chain, hbase, cnt, mapp, n_mh + (do_mh ? 1 : 0));
+    if (FS(active && (long long)step < m.trace_steps, false)) {
       s.trace_lhr[step * m.n_chains + chain] = do_mh ? lhr : 0.0;
       s.trace_code[step * m.n_chains + chain] = do_mh ? (code | (type & PTG_TRACE_TYPE_MASK)) : PTG_TRACE_SWAPPED;
     }
@@ -624,8 +906,8 @@ __global__ void __launch_bounds__(PTG_FSTEP_MAX_THREADS, 1) ptg_fstep_kernel(con
     // the SM keeps stepping.  The host only uses this when every CTA of the grid is resident (one wave on each GPU).
     if (XCHG == 2 && xc.on && xc.every > 0 && it + 1 < n_steps && (it + 1) % xc.every == 0) {
       if (active) {
-        fx_publish<D>(m, xc, xp, ch, ladder, rung, R);
-        fx_swap<D>(m, s, xc, xp, ch, chain, ladder, gl, rung, R, cnt, err);
+        fx_publish<D>(m, xc, xp, ch, LPRIOR, ladder, rung, R);
+        cnt[FC_XAPP] += fx_swap<D, !SL>(m, s, xc, xp, ch, chain, ladder, gl, rung, R, cnt, mapp, it + 1 - cnt[FC_NSWAPPED], err);
       }
       xp++;
       __syncwarp();
@@ -633,16 +915,18 @@ __global__ void __launch_bounds__(PTG_FSTEP_MAX_THREADS, 1) ptg_fstep_kernel(con
   }
 
   // ================================================================= rung-sharded ladders: publish this block's edge rungs
-  if (XCHG && xc.on && xc.publish_out && active) fx_publish<D>(m, xc, xp, ch, ladder, rung, R);
+  if (XCHG && xc.on && xc.publish_out && active) fx_publish<D>(m, xc, xp, ch, LPRIOR, ladder, rung, R);
 
   if (active) {
 #pragma unroll
     for (int k = 0; k < D; k++) s.cur_x[(long long)k * m.n_chains + chain] = ch.x[k];
-    s.lpost[chain] = ch.lpost; s.llike[chain] = ch.llike; s.lprior[chain] = ch.lprior; s.beta[chain] = ch.beta;
+    s.lpost[chain] = LPOST; s.llike[chain] = ch.llike; s.lprior[chain] = LPRIOR; s.beta[chain] = ch.beta;
+    s.map_lpost[chain] = mapp[0];
+    // appends of this launch: one per iteration + the extra ones (second trial of a step, boundary exchanges);
     // saves = appends k in [0, dnhist) with (since_save0 + k) % save_every == 0
-    const int dnhist = cnt[FC_NHIST], se = m.save_every;
+    const int dnhist = n_steps + cnt[FC_XAPP], se = m.save_every;
     const int dnsize = (since_save0 + dnhist + se - 1) / se - (since_save0 + se - 1) / se;
-    s.nhist[chain] += dnhist; s.nsize[chain] += dnsize; s.ntries[chain] += cnt[FC_NTRIES]; s.naccept[chain] += cnt[FC_NACCEPT];
+    s.nhist[chain] += dnhist; s.nsize[chain] += dnsize; s.ntries[chain] += n_steps - cnt[FC_NSWAPPED]; s.naccept[chain] += cnt[FC_NACCEPT];
     s.last_type[chain] = cnt[FC_LAST_TYPE];
     s.directions[chain] = (st_di & 3) - 1; s.instances[chain] = st_di >> 2;
     const int st_ud = cnt[FC_UD], st_sc = cnt[FC_SC];
@@ -650,6 +934,9 @@ __global__ void __launch_bounds__(PTG_FSTEP_MAX_THREADS, 1) ptg_fstep_kernel(con
     s.swap_count[chain] += st_sc & 0xffff; s.swap_accept[chain] += st_sc >> 16;
     if (err) atomicMax(s.err, err);
   }
+#undef FS
+#undef LPOST
+#undef LPRIOR
 }
 #undef stream_base
 #undef my_stream

@@ -27,9 +27,33 @@ static cudaError_t launch_wstep_t(const PtgModel &m, const PtgState &s, long lon
   ptg_wstep_kernel<D, MODE><<<blocks, 128, smem, st>>>(m, s, step0, n_steps, W);
   return cudaGetLastError();
 }
-// production kernel (Philox draws): ladder-in-a-warp, proposal table + bins + per-thread counters in shared memory
+// production kernel (Philox draws): ladder-in-a-warp; proposal table, bins, per-thread counters / MAP and the per-warp pool slots in
+// dynamic shared memory (FShared).  lk = -1: every feature at run time; lk >= 0: the streamlined instantiation for likelihood kind lk
+// (the host checks the configuration, ptg_api.cu:fstep_streamlined_kind)
+template <int D, int XCHG, int LK>
+static cudaError_t launch_fstep_k(const PtgModel &m, const PtgState &s, long long step0, int n_steps, int W, const PtgXchg &xc, int blocks, int threads, size_t smem, cudaStream_t st) {
+  auto k = ptg_fstep_kernel<D, XCHG, LK>;
+  static size_t smem_set[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (smem > 48 * 1024 && smem > smem_set[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    smem_set[dev & 63] = smem;
+  }
+  if (XCHG == 2) {
+    // the in-launch exchange pairs warps across GPUs: every CTA of the grid must be resident at once (measured, not assumed)
+    int per_sm = 0, sms = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, smem);
+    if (e != cudaSuccess) return e;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if ((long long)blocks > (long long)per_sm * sms) return cudaErrorCooperativeLaunchTooLarge;
+  }
+  k<<<blocks, threads, smem, st>>>(m, s, step0, n_steps, W, xc);
+  return cudaGetLastError();
+}
 template <int D>
-static cudaError_t launch_fstep_t(const PtgModel &m, const PtgState &s, long long step0, int n_steps, int W, const PtgXchg &xc, cudaStream_t st) {
+static cudaError_t launch_fstep_t(const PtgModel &m, const PtgState &s, long long step0, int n_steps, int W, const PtgXchg &xc, int lk, cudaStream_t st) {
   const long long warps = (m.n_ladders + (32 / W) - 1) / (32 / W);
   // CTA size: the largest of 28 / 14 / 4 warps that still puts a CTA on (nearly) every SM.  The kernel is compiled for 72
   // registers (launch bound 896 x 1), so 896 resident threads per SM in every geometry; one 28-warp CTA per SM measured
@@ -37,11 +61,14 @@ static cudaError_t launch_fstep_t(const PtgModel &m, const PtgState &s, long lon
   const int threads = ptg_fstep_threads(warps);
   const int wpb = threads / 32;
   const int blocks = (int)((warps + wpb - 1) / wpb);
-  const size_t smem = (size_t)m.n_rungs * m.n_props * sizeof(double) + (size_t)m.n_props * sizeof(FProp) + (size_t)PTG_FC_STRIDE * threads * sizeof(int);
-  if (xc.on && xc.every > 0) ptg_fstep_kernel<D, 2><<<blocks, threads, smem, st>>>(m, s, step0, n_steps, W, xc);
-  else if (xc.on) ptg_fstep_kernel<D, 1><<<blocks, threads, smem, st>>>(m, s, step0, n_steps, W, xc);
-  else ptg_fstep_kernel<D, 0><<<blocks, threads, smem, st>>>(m, s, step0, n_steps, W, xc);
-  return cudaGetLastError();
+  const size_t smem = FShared<D>::bytes(threads, m.n_rungs, m.n_props);
+#define GO(X, L) return launch_fstep_k<D, X, L>(m, s, step0, n_steps, W, xc, blocks, threads, smem, st)
+  if (xc.on && xc.every > 0) GO(2, -1);
+  if (xc.on) { if (lk == PTG_LIKE_SINES) GO(1, PTG_LIKE_SINES); GO(1, -1); }
+  if (lk == PTG_LIKE_SINES) GO(0, PTG_LIKE_SINES);
+  if (lk == PTG_LIKE_GAUSS_ISO) GO(0, PTG_LIKE_GAUSS_ISO);
+  GO(0, -1);
+#undef GO
 }
 template <int D, int MODE>
 static cudaError_t launch_init_t(const PtgModel &m, const PtgState &s, const double *init_x, cudaStream_t st) {
@@ -70,8 +97,8 @@ static cudaError_t launch_init_t(const PtgModel &m, const PtgState &s, const dou
     return mode == PTG_RNG_TAPE ? launch_wstep_t<D, PTG_RNG_TAPE>(m, s, step0, n_steps, W, st)                               \
                                 : launch_wstep_t<D, PTG_RNG_PHILOX>(m, s, step0, n_steps, W, st);                            \
   }                                                                                                                          \
-  cudaError_t ptg_launch_fstep_d##D(const PtgModel &m, const PtgState &s, long long step0, int n_steps, int W, const PtgXchg &xc, cudaStream_t st) { \
-    return launch_fstep_t<D>(m, s, step0, n_steps, W, xc, st);                                                                   \
+  cudaError_t ptg_launch_fstep_d##D(const PtgModel &m, const PtgState &s, long long step0, int n_steps, int W, const PtgXchg &xc, int lk, cudaStream_t st) { \
+    return launch_fstep_t<D>(m, s, step0, n_steps, W, xc, lk, st);                                                                   \
   }                                                                                                                          \
   cudaError_t ptg_launch_init_d##D(int mode, const PtgModel &m, const PtgState &s, const double *init_x, cudaStream_t st) {  \
     return mode == PTG_RNG_TAPE ? launch_init_t<D, PTG_RNG_TAPE>(m, s, init_x, st)                                           \

@@ -62,10 +62,10 @@ __device__ __forceinline__ void chain_append(const PtgModel &m, const PtgState &
   }
   if (ch.since_save == 0) {
     long long rec = ch.chain * m.hist_cap + ch.slot;
-    double *h = s.hist + rec * (D + 2);
+    double *h = s.hist + rec * PTG_HX(D);
 #pragma unroll
     for (int k = 0; k < D; k++) h[k] = x[k];
-    h[D] = lpost; h[D + 1] = llike;
+    s.hist_lp[2 * rec] = lpost; s.hist_lp[2 * rec + 1] = llike;
     if (m.record_full) {
       s.hist_acc[rec] = ch.naccept / (double)ch.ntries;
       s.hist_beta[rec] = beta;
@@ -83,7 +83,14 @@ template <int D>
 __device__ __forceinline__ const double *hist_elem(const PtgModel &m, const PtgState &s, const Chain<D> &ch, int index) {
   int p = index;
   if (ch.nsize > m.hist_cap) { p = ch.slot + index; if (p >= m.hist_cap) p -= m.hist_cap; }
-  return s.hist + (ch.chain * m.hist_cap + p) * (D + 2);
+  return s.hist + (ch.chain * m.hist_cap + p) * PTG_HX(D);
+}
+// lpost of that element (differential_evolution's unlikely_alpha test, proposal_distribution.cc:768)
+template <int D>
+__device__ __forceinline__ double hist_lpost(const PtgModel &m, const PtgState &s, const Chain<D> &ch, int index) {
+  int p = index;
+  if (ch.nsize > m.hist_cap) { p = ch.slot + index; if (p >= m.hist_cap) p -= m.hist_cap; }
+  return s.hist_lp[2 * (ch.chain * m.hist_cap + p)];
 }
 
 // differential_evolution::draw_i_from_chain (proposal_distribution.cc:744-778)
@@ -110,7 +117,7 @@ __device__ __forceinline__ int de_draw_index(const PtgModel &m, const PtgState &
     attempt++;
     int index = (int)(start + (size - start) * xrnd);
     if (alpha > 0) {
-      double lpost = hist_elem<D>(m, s, ch, index)[D];
+      double lpost = hist_lpost<D>(m, s, ch, index);
       if (lpost0 > lpost) {
         double pr = exp(alpha * (lpost - lpost0));
         double x2 = rs.u32(wr, 1);

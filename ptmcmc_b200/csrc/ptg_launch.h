@@ -12,7 +12,7 @@ static inline size_t ptg_ladder_shared_bytes(int D, int R) {
 #ifdef PTG_DEV_DIM3  // developer build: `make DEV=1` compiles only dim = 3, 5, 9 (seconds instead of minutes)
 #define PTG_DIM_LIST(X) X(3) X(5) X(9)
 #else
-#define PTG_DIM_LIST(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(12) X(16)
+#define PTG_DIM_LIST(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
 #endif
 // CTA size of the production kernel (ptg_fstep_kernel) for a batch of `warps` ladder-warps
 static inline int ptg_fstep_threads(long long warps) {
@@ -42,7 +42,7 @@ static inline int ptg_fstep_grid_is_resident(long long warps) {
   /* host-callback likelihood mode: what = 0 propose (shared-memory kernel, phase 1), 1 finish, 2 init draw, 3 init accept */                 \
   cudaError_t ptg_launch_cb_d##D(int what, const PtgModel &m, const PtgState &s, long long step, int lpb, size_t smem, int k, int32_t *attempt,   \
                                  int32_t *n_open, cudaStream_t st);                                                          \
-  cudaError_t ptg_launch_fstep_d##D(const PtgModel &m, const PtgState &s, long long step0, int n_steps, int W, const PtgXchg &xc, cudaStream_t st); \
+  cudaError_t ptg_launch_fstep_d##D(const PtgModel &m, const PtgState &s, long long step0, int n_steps, int W, const PtgXchg &xc, int lk, cudaStream_t st); \
   cudaError_t ptg_launch_init_d##D(int mode, const PtgModel &m, const PtgState &s, const double *init_x, cudaStream_t st);       \
   cudaError_t ptg_launch_eval_d##D(const PtgModel &m, const double *x, long long n, double *ll, double *lp, cudaStream_t st);
 PTG_DIM_LIST(PTG_DECLARE)

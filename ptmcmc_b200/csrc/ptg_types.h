@@ -5,6 +5,10 @@
 #include "../../include/ptmcmc_b200.h"
 
 #define PTG_TPC_MAX_DIM 16   // thread-per-chain kernels
+// doubles per record of the history x-ring: the thread-per-chain kernels (dim <= 16) pad a record to a multiple of 4 doubles so that
+// a record is a whole number of 32-byte sectors (a DE gather at dim <= 4 is exactly one sector, one 256-bit load); the warp-per-chain
+// kernels read whole records coalesced and keep the natural stride
+#define PTG_HX(dim) ((dim) <= PTG_TPC_MAX_DIM ? (((dim) + 3) & ~3) : (dim))
 #define PTG_SWAP_SLOTS 64    // swap trials per PT step: maxswapsperstep = 1+2*swap_rate*Ntemps (chain.cc:1192), capped (the oracle caps at 64 too)
 
 // 1-D prior factor (ProbabilityDist.h:76-257)
@@ -28,7 +32,7 @@ struct PtgModel {
   int32_t save_every, hist_cap, n_init, maxswaps;
   int32_t swap_mode, record_full, wrap_in_set, zero_valid;
   int32_t like_kind, n_lparams, trace_steps, all_uniform_prior;
-  int32_t any_bound, pad0;    // any_bound: some dimension has a non-open boundary (state::enforce does work)
+  int32_t any_bound, hx;      // any_bound: some dimension has a non-open boundary (state::enforce does work); hx: doubles per history x-record (ptg_hx)
   int64_t n_ldata;
   int64_t n_chains;
   double swap_rate, dprior_min, evolve_rate, evolve_lpost_cut;
@@ -59,7 +63,8 @@ struct PtgState {
   double *map_x;      // [dim][n_chains]
   long long *nhist, *nsize, *ntries, *naccept; // [n_chains]
   int32_t *last_type; // [n_chains]
-  double *hist;       // [n_chains][hist_cap][dim+2]  record = x[dim], lpost, llike
+  double *hist;       // [n_chains][hist_cap][hx]  x-ring: record = x[dim], padded to whole 32-byte sectors for dim <= 16 (ptg_hx)
+  double *hist_lp;    // [n_chains][hist_cap][2]   (lpost, llike) of the same slot: read only by dumps, evidence and unlikely_alpha
   double *hist_acc, *hist_beta; // [n_chains][hist_cap] (record_full)
   int32_t *hist_type; // [n_chains][hist_cap]        (record_full)
   long long *swap_count, *swap_accept; // [n_ladders][n_rungs]
@@ -85,6 +90,7 @@ struct PtgState {
 // (x, llike, lprior, beta) followed by flags [2 edge][n_ladders] int32 = number of publishes completed for that ladder's edge.
 // The epilogue of launch p publishes into parity p & 1 and raises the flags to p + 1; the prologue of the NEXT launch waits for the
 // neighbour's flag to reach p + 1, reads the neighbour's record through its peer pointer and runs the boundary swap trial.
+#define PTG_ERR_XCHG_TIMEOUT 6      // device error flag: a boundary-exchange wait was aborted
 struct PtgXchg {
   int on, swap_in, publish_out, has_lo, has_hi;
   int every;                         // > 0: also exchange INSIDE the launch after every `every`-th iteration
@@ -93,6 +99,7 @@ struct PtgXchg {
   const double *lo_edges; const int *lo_flags; // colder neighbour (its hottest rung pairs with my coldest)
   const double *hi_edges; const int *hi_flags; // hotter neighbour (its coldest rung pairs with my hottest)
   unsigned long long shared_seed;
+  const int *abort;                  // watchdog word in mapped host memory: non-zero = every wait gives up (ptg_xchg_abort)
   long long lo_boundary, hi_boundary; // boundary ids for the Philox address (= rank of the pair's lower block)
 };
 

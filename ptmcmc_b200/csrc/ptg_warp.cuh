@@ -218,7 +218,7 @@ __device__ __forceinline__ int wde_index(const PtgModel &m, const PtgState &s, c
     attempt++;
     const int index = (int)(start + (hsize - start) * xrnd);
     if (alpha > 0) {
-      const double lpost = hist_elem<D>(m, s, ch, index)[D];
+      const double lpost = hist_lpost<D>(m, s, ch, index);
       if (lpost0 > lpost) {
         const double pr = exp(alpha * (lpost - lpost0));
         double x2;

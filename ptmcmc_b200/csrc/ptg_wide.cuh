@@ -78,11 +78,11 @@ __device__ __forceinline__ void xappend(const PtgModel &m, const PtgState &s, XC
   }
   if (ch.since_save == 0) {
     const long long rec = ch.chain * m.hist_cap + ch.slot;
-    double *h = s.hist + rec * (D + 2);
+    double *h = s.hist + rec * m.hx;
 #pragma unroll
     for (int k = 0; k < CPL; k++) { const int c = CPL * lane + k; if (c < D) h[c] = x[k]; }
     if (lane == 0) {
-      h[D] = lpost; h[D + 1] = llike;
+      s.hist_lp[2 * rec] = lpost; s.hist_lp[2 * rec + 1] = llike;
       if (m.record_full) { s.hist_acc[rec] = ch.naccept / (double)ch.ntries; s.hist_beta[rec] = beta; s.hist_type[rec] = ch.last_type; }
     }
     ch.nsize++;
@@ -96,7 +96,13 @@ template <int CPL>
 __device__ __forceinline__ const double *xhist(const PtgModel &m, const PtgState &s, const XChain<CPL> &ch, int index) {
   int p = index;
   if (ch.nsize > m.hist_cap) { p = ch.slot + index; if (p >= m.hist_cap) p -= m.hist_cap; }
-  return s.hist + (ch.chain * m.hist_cap + p) * (m.dim + 2);
+  return s.hist + (ch.chain * m.hist_cap + p) * m.hx;
+}
+template <int CPL>
+__device__ __forceinline__ double xhist_lpost(const PtgModel &m, const PtgState &s, const XChain<CPL> &ch, int index) {
+  int p = index;
+  if (ch.nsize > m.hist_cap) { p = ch.slot + index; if (p >= m.hist_cap) p -= m.hist_cap; }
+  return s.hist_lp[2 * (ch.chain * m.hist_cap + p)];
 }
 template <int CPL>
 __device__ __forceinline__ void xload_rec(const double *rec, double v[CPL], int lane, int D) {
@@ -288,7 +294,7 @@ __device__ __forceinline__ int xde_index(const PtgModel &m, const PtgState &s, c
     attempt++;
     const int index = (int)(start + (hsize - start) * xrnd);
     if (alpha > 0) {
-      const double lpost = xhist<CPL>(m, s, ch, index)[D];
+      const double lpost = xhist_lpost<CPL>(m, s, ch, index);
       if (lpost0 > lpost) {
         const double pr = exp(alpha * (lpost - lpost0));
         double x2;

@@ -78,6 +78,48 @@ def test_kernels_agree_bitwise(name, spec, kw, engine_cls):
         assert es[0].get_current()["x"].tobytes() == e.get_current()["x"].tobytes()
 
 
+STREAMLINED_CASES = [
+    ("c1_sines_d3_R32", Spec("sines", 3, 32), 300),
+    ("sines_d3_R8_four_ladders_per_warp", Spec("sines", 3, 8, swap_rate=0.3), 300),
+    ("sines_d3_R24_ghost_lanes_save3", Spec("sines", 3, 24, save_every=3), 301),
+    ("a_gauss_d2_R8", Spec("gauss", 2, 8, centers=[2, -3], halfwidths=[2, 3]), 300),
+    ("gauss_d5_R16_high_swap_rate", Spec("gauss", 5, 16, centers=np.zeros(5), halfwidths=np.full(5, 4.0), swap_rate=0.45), 70),
+    ("gauss_d9_R32", Spec("gauss", 9, 32, centers=np.zeros(9), halfwidths=np.full(9, 4.0)), 64),
+    ("gauss_d16_R12", Spec("gauss", 16, 12, centers=np.zeros(16), halfwidths=np.full(16, 3.0), de_ni=12), 33),
+    ("gauss_d11_R7_gauss_only", Spec("gauss", 11, 7, centers=np.zeros(11), halfwidths=np.full(11, 3.0), prop="gauss"), 40),
+]
+
+
+@pytest.mark.parametrize("name,spec,L", STREAMLINED_CASES, ids=[c[0] for c in STREAMLINED_CASES])
+def test_streamlined_instantiation_is_bit_identical(name, spec, L, engine_cls):
+    """The production kernel's streamlined instantiations (compile-time configuration: reference swap schedule, open space, uniform
+    priors, DE + Gaussian members, one likelihood functor; pooled work rounds; deferred swap appends) against its general instantiation
+    and the tape-capable warp kernel -- which is bit-exact with the reference under injected draws: same chains to the last bit"""
+    def run(kern):
+        e = engine_cls(spec.config(n_ladders=L, rng_mode=K.RNG_PHILOX, record_level=K.RECORD_BASIC, hist_capacity=spec.de_ni * spec.dim + 1300))
+        e.select_kernel(kern)
+        spec.setup(e); e.init_from_prior(); e.step(77); e.step(423); e.step(1); e.synchronize()
+        return e
+    es = [run(k) for k in (K.KERNEL_FAST, K.KERNEL_FAST_GENERAL, K.KERNEL_WARP)]
+    assert len({e.get_total_steps() for e in es}) == 1
+    R = spec.rungs
+    c0, cur0, sw0 = es[0].get_counters(), es[0].get_current(), es[0].get_swap_stats()
+    for e in es[1:]:
+        c, cur, sw = e.get_counters(), e.get_current(), e.get_swap_stats()
+        for k in ("nhist", "nsize", "ntries", "naccept", "last_type", "map_lpost"):
+            assert np.asarray(c0[k]).tobytes() == np.asarray(c[k]).tobytes(), k
+        for k in ("x", "lpost", "llike", "beta"):
+            assert cur0[k].tobytes() == cur[k].tobytes(), k
+        for k in sw0:
+            assert (np.asarray(sw0[k]) == np.asarray(sw[k])).all(), k
+        for l in (0, L // 2, L - 1):
+            for r in (0, R // 2, R - 1):
+                n = int(c0["nsize"][l * R + r])
+                h0 = es[0].get_history(l, r, 0, n, full=False); h1 = e.get_history(l, r, 0, n, full=False)
+                for k in ("x", "lpost", "llike"):
+                    assert h0[k].tobytes() == h1[k].tobytes(), (k, l, r)
+
+
 def test_step_chunking_and_checkpoint_roundtrip(engine_cls, tmp_path):
     a = c1(engine_cls, 64, 300, evolve_rate=0.01)
     b = c1(engine_cls, 64, 300, chunks=[1, 2, 97, 200], evolve_rate=0.01)
