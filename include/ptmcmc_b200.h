@@ -178,6 +178,14 @@ int ptg_get_launch_count(ptg_handle *h, int64_t *n);
 /* same, end-to-end with host buffers: steps, then copies the cold chains' newest `n_out` stored samples
  * of every ladder to host memory x_out[n_ladders][n_out][dim], lpost_out/llike_out[n_ladders][n_out] */
 int ptg_step_host(ptg_handle *h, int64_t n_steps, int32_t n_out, double *x_out, double *lpost_out, double *llike_out);
+/* the same in two halves: _begin enqueues the steps, the gather and the device-to-host copies (on a copy stream of the handle, double-
+ * buffered staging) and returns; _wait blocks until the samples of every begun block have landed.  With pinned host buffers the copy of
+ * block k overlaps the kernel of block k+1: the shape of the reference's run loop, which dumps every cold sample of a block while the
+ * next block is already stepping would (ptmcmc.cc:601-616, chain.cc:1112-1135). */
+int ptg_step_host_begin(ptg_handle *h, int64_t n_steps, int32_t n_out, double *x_out, double *lpost_out, double *llike_out);
+int ptg_step_host_wait(ptg_handle *h);
+/* effective capacity of the history ring (hist_capacity = 0 at creation means n_init + 1024) */
+int ptg_get_hist_capacity(ptg_handle *h, int32_t *capacity);
 
 /* the device functors applied to caller-provided states x[n][dim] (host): log-likelihood (the batched form of
  * bayes_likelihood::evaluate_log, bayesian.hh:553-581) and log-prior after boundary enforcement

@@ -262,6 +262,40 @@ static double like_eval(const pto_handle *h, const double *x) {
     result = P[0] - r2 / P[1];
     break;
   }
+  case PTG_LIKE_SHELL2D: { /* example.cc:195-206: Gaussian shell in (|p0|, p1); P = lnnormfac, twosigmasq, r0, x0[2] */
+    double r2 = 0;
+    double dx = fabs(x[0]) - P[3];
+    r2 += dx * dx;
+    dx = x[1] - P[4];
+    r2 += dx * dx;
+    dx = sqrt(r2) - P[2];
+    r2 = dx * dx;
+    result = P[0] - r2 / P[1];
+    break;
+  }
+  case PTG_LIKE_SHELLS: { /* example.cc:373-403; P = lnnormfac, twosigmasq, r0, x0, sigmapoverm, lnsigmapoverm, logx */
+    const double twosigmasq = P[1], r0 = P[2], x0 = P[3], spm = P[4], lnspm = P[5];
+    double xx = x[0];
+    if (P[6] != 0) {
+      if (xx < 0) return -INFINITY;
+      xx = log(xx);
+    }
+    double dx = xx - x0;
+    double r2 = dx * dx;
+    for (int i = 1; i < d; i++) { dx = x[i]; r2 += dx * dx; }
+    dx = sqrt(r2) - r0;
+    r2 = dx * dx;
+    double resultp = -r2 / (twosigmasq * spm) - 0.5 * lnspm;
+    dx = xx + x0;
+    r2 = dx * dx;
+    for (int i = 1; i < d; i++) { dx = x[i]; r2 += dx * dx; }
+    dx = sqrt(r2) - r0;
+    r2 = dx * dx;
+    double resultm = -r2 / (twosigmasq / spm) + 0.5 * lnspm;
+    result = P[0];
+    if (resultm > resultp) result += resultm; else result += resultp;
+    break;
+  }
   case PTG_LIKE_SINES: { /* sines.hh:22-54 */
     const double height = P[0], step_scale = P[1];
     const double *ks = P + 2, *mins = P + 2 + d, *maxs = P + 2 + 2 * d;

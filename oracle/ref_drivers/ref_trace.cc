@@ -27,6 +27,7 @@
 #include <fstream>
 #include <memory>
 #include <new>
+#include <chrono>
 #include "chain.hh"
 #include "proposal_distribution.hh"
 #include "probability_function.hh"
@@ -113,6 +114,66 @@ public:
   }
 };
 
+// 2-D double Gaussian shell, reflected in p0: arithmetic of gaussian_shell_2D_likelihood::evaluate_log (example.cc:195-206)
+class shell2d_like : public probability_function {
+public:
+  double x0[2], r0, lnnormfac, twosigmasq;
+  shell2d_like(const stateSpace *sp, double x00, double x01, double r0, double sigma) : probability_function(sp), r0(r0) {
+    x0[0] = x00; x0[1] = x01;
+    twosigmasq = 2 * sigma * sigma;
+    lnnormfac = -0.5 * std::log(M_PI * twosigmasq); // example.cc:179
+  }
+  double evaluate_log(state &s) {
+    valarray<double> params = s.get_params();
+    double r2 = 0;
+    double dx = abs(params[0]) - x0[0];
+    r2 += dx * dx;
+    dx = params[1] - x0[1];
+    r2 += dx * dx;
+    dx = sqrt(r2) - r0;
+    r2 = dx * dx;
+    double result = lnnormfac - r2 / twosigmasq;
+    if (!isfinite(result)) result = -INFINITY;
+    return result;
+  }
+};
+// d-dim Gaussian shell pair: arithmetic of gaussian_shell_likelihood::evaluate_log (example.cc:373-403)
+class shells_like : public probability_function {
+public:
+  int dim; bool logx; double x0, r0, lnnormfac, twosigmasq, sigmapoverm, lnsigmapoverm;
+  shells_like(const stateSpace *sp, int dim, double x0, double r0, double sigma, double sigmapoverm, bool logx)
+      : probability_function(sp), dim(dim), logx(logx), x0(x0), r0(r0), sigmapoverm(sigmapoverm) {
+    twosigmasq = 2 * sigma * sigma;
+    lnnormfac = -0.5 * std::log(M_PI * twosigmasq); // example.cc:341-342
+    lnsigmapoverm = std::log(sigmapoverm);
+  }
+  double evaluate_log(state &s) {
+    valarray<double> params = s.get_params();
+    double x = params[0];
+    if (logx) {
+      if (x < 0) return -INFINITY;
+      x = std::log(x);
+    }
+    double dx = x - x0;
+    double r2 = dx * dx;
+    for (int i = 1; i < dim; i++) { dx = params[i]; r2 += dx * dx; }
+    dx = sqrt(r2) - r0;
+    r2 = dx * dx;
+    double resultp = -r2 / (twosigmasq * sigmapoverm) - 0.5 * lnsigmapoverm;
+    dx = x + x0;
+    r2 = dx * dx;
+    for (int i = 1; i < dim; i++) { dx = params[i]; r2 += dx * dx; }
+    dx = sqrt(r2) - r0;
+    r2 = dx * dx;
+    double resultm = -r2 / (twosigmasq / sigmapoverm) + 0.5 * lnsigmapoverm;
+    double result = lnnormfac;
+    if (resultm > resultp) result += resultm;
+    else result += resultp;
+    if (!isfinite(result)) result = -INFINITY;
+    return result;
+  }
+};
+
 static map<string, string> kv;
 static string S(const string &k, const string &def) { return kv.count(k) ? kv[k] : def; }
 static double D(const string &k, double def) { return kv.count(k) ? atof(kv[k].c_str()) : def; }
@@ -194,6 +255,10 @@ int main(int argc, char **argv) {
   } else if (model == "poly" || model == "sinusoid") {
     vector<double> xs = readvec(kv["data_x"]), ys = readvec(kv["data_y"]), dys = readvec(kv["data_dy"]);
     like = new chi2_like(&space, model == "poly" ? 0 : 1, xs, ys, dys);
+  } else if (model == "shell2d") {
+    like = new shell2d_like(&space, D("shell_x0", 3.0), D("shell_x1", 0.0), D("shell_r0", 2.0), D("shell_sigma", 0.1));
+  } else if (model == "shells") {
+    like = new shells_like(&space, d, D("shell_x0", 3.0), D("shell_r0", 2.0), D("shell_sigma", 0.1), D("shell_spm", 1.0), I("shell_logx", 0) != 0);
   } else if (model == "fullcov") {
     vector<double> cinv = readvec(kv["cinv"]);
     like = new fullcov_like(&space, d, cinv, D("like0", 0.0));
@@ -255,7 +320,10 @@ int main(int argc, char **argv) {
     vector<proposal_distribution *> set(2); vector<double> shares(2), hot(2);
     set[0] = de; shares[0] = 1 - D("prior_draw_frac", 0.3);
     set[1] = new draw_from_dist(*prior); shares[1] = D("prior_draw_frac", 0.3);
-    cprop = new proposal_distribution_set(set, shares, 0, 0, hot);
+    // thermal weighting of the prior draws as ptmcmc_sampler::select_proposal sets it up (ptmcmc.cc:95-101): hot share 1 for the prior draw
+    double Tpow = D("Tpow", 0);
+    if (Tpow > 0) { hot[0] = D("hot_de", 0.0); hot[1] = D("hot_prior", 1.0); }
+    cprop = new proposal_distribution_set(set, shares, 0, Tpow, hot);
   } else { cerr << "unknown prop " << prop << endl; return 2; }
 
   // ---- chain: exactly ptmcmc_sampler::initialize (ptmcmc.cc:508-522) ------------------------------
@@ -266,7 +334,9 @@ int main(int argc, char **argv) {
   ptc->initialize(like, prior, Ninit, "");
   ptc->set_proposal(*cprop);
   cprop->set_chain(ptc);
+  chrono::steady_clock::time_point t_begin = chrono::steady_clock::now();
   for (int s = 0; s < nsteps; s++) ptc->step();
+  double step_seconds = chrono::duration<double>(chrono::steady_clock::now() - t_begin).count();
   cout.rdbuf(old);
 
   // ---- dump ---------------------------------------------------------------------------------------
@@ -295,7 +365,7 @@ int main(int argc, char **argv) {
   }
   long long total = 0;
   for (int r = 0; r < nrungs; r++) total += ptc->chains[r].Nhist;
-  printf("ref_trace: model=%s d=%d rungs=%d steps=%d Ninit=%d total_Nhist=%lld cold_Nsize=%d\n",
-         model.c_str(), d, nrungs, nsteps, Ninit, total, ptc->chains[0].Nsize);
+  printf("ref_trace: model=%s d=%d rungs=%d steps=%d Ninit=%d total_Nhist=%lld cold_Nsize=%d step_seconds=%.6f\n",
+         model.c_str(), d, nrungs, nsteps, Ninit, total, ptc->chains[0].Nsize, step_seconds);
   return 0;
 }

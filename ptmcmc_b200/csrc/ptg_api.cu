@@ -57,6 +57,7 @@ struct ptg_handle {
   // rung-sharded ladders with the exchange fused into the step kernel (ptg_xchg_*)
   void *d_xchg; size_t xchg_bytes; void *peer_lo, *peer_hi; bool peer_lo_ipc, peer_hi_ipc;
   PtgXchg xchg, xchg_cur; bool xchg_launch;  // xchg_cur: parameters of the exchange launch in flight through ptg_step (xchg_launch = false: plain step)
+  cudaStream_t copy_stream; cudaEvent_t ev_gathered[2], ev_copied[2]; double *d_stage[2]; size_t stage_bytes[2]; bool stage_used[2]; int stage_next; // ptg_step_host_begin
   int *h_abort; int *d_abort;               // watchdog word of the fused exchange (mapped pinned host memory) and its device alias
   bool dead;                                // a boundary exchange was aborted: the ladders of this rank are out of step with their neighbours
 };
@@ -176,6 +177,7 @@ extern "C" int ptg_create(const ptg_config *cfg, ptg_handle **out) {
   h->have_space = h->have_prior = h->have_like = h->have_props = h->inited = h->model_uploaded = false; h->model_dirty = true;
   h->d_lparams = h->d_ldata = h->d_prop_data = h->d_bins = nullptr;
   h->d_tape_u = h->d_tape_z = nullptr; h->d_u_end = h->d_z_end = nullptr;
+  h->copy_stream = nullptr; h->d_stage[0] = h->d_stage[1] = nullptr; h->stage_bytes[0] = h->stage_bytes[1] = 0; h->stage_used[0] = h->stage_used[1] = false; h->stage_next = 0;
   h->xchg_launch = false; h->h_abort = h->d_abort = nullptr; h->dead = false; h->d_xchg = nullptr; h->peer_lo = h->peer_hi = nullptr; h->peer_lo_ipc = h->peer_hi_ipc = false;
   h->kernel_choice = PTG_KERNEL_AUTO; h->launches = 0; h->cb_fn = nullptr; h->cb_user = nullptr; h->d_attempt = h->d_nopen = nullptr; h->istep = 0; h->Tpow = 0; h->d_scratch = nullptr; h->scratch_bytes = 0; h->h_pinned = nullptr; h->pinned_bytes = 0;
   cudaError_t es = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
@@ -240,6 +242,11 @@ extern "C" int ptg_destroy(ptg_handle *h) {
   for (void *p : h->allocs) cudaFree(p);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   if (h->h_abort) cudaFreeHost(h->h_abort);
+  if (h->copy_stream) {
+    cudaStreamSynchronize(h->copy_stream);
+    for (int b = 0; b < 2; b++) { cudaEventDestroy(h->ev_gathered[b]); cudaEventDestroy(h->ev_copied[b]); if (h->d_stage[b]) cudaFree(h->d_stage[b]); }
+    cudaStreamDestroy(h->copy_stream);
+  }
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
   return 0;
@@ -798,21 +805,64 @@ static int ensure_scratch(ptg_handle *h, size_t bytes) {
   return 0;
 }
 
-extern "C" int ptg_step_host(ptg_handle *h, int64_t n_steps, int32_t n_out, double *x_out, double *lpost_out, double *llike_out) {
+// End-to-end block for a host facade (the run loop's dump of every cold sample, ptmcmc.cc:601-616): n_steps iterations, then the cold
+// chains' newest n_out stored samples of every ladder travel to the caller's host buffers.  _begin only ENQUEUES: the gather into one of two
+// device staging buffers runs on the engine's stream, the three device-to-host copies on a separate copy stream behind an event, so they
+// overlap whatever the caller enqueues next (the next block's kernel); _wait blocks until every begun block's samples have landed.
+// One cudaMemcpyAsync per output array; pass pinned host memory for the overlap to be real.
+static int stage_setup(ptg_handle *h, size_t bytes) {
+  if (!h->copy_stream) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; b++) {
+      CUDA_TRY(cudaEventCreateWithFlags(&h->ev_gathered[b], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&h->ev_copied[b], cudaEventDisableTiming));
+    }
+  }
+  for (int b = 0; b < 2; b++) if (h->stage_bytes[b] < bytes) {
+    if (h->d_stage[b]) { CUDA_TRY(cudaStreamSynchronize(h->copy_stream)); CUDA_TRY(cudaStreamSynchronize(h->stream)); CUDA_TRY(cudaFree(h->d_stage[b])); h->d_stage[b] = nullptr; }
+    CUDA_TRY(cudaMalloc((void **)&h->d_stage[b], bytes));
+    h->stage_bytes[b] = bytes;
+  }
+  return 0;
+}
+extern "C" int ptg_step_host_begin(ptg_handle *h, int64_t n_steps, int32_t n_out, double *x_out, double *lpost_out, double *llike_out) {
   int rc = ptg_step(h, n_steps); if (rc) return rc;
-  if (n_out <= 0) return ptg_synchronize(h);
+  if (n_out <= 0) return 0;
   if (!x_out || !lpost_out || !llike_out) return fail(PTG_EINVAL, "null output");
   if (n_out > h->m.hist_cap) return fail(PTG_EINVAL, "n_out = %d exceeds the history ring (%d slots)", n_out, h->m.hist_cap);
   PtgModel &m = h->m;
   const long long total = (long long)m.n_ladders * n_out;
-  rc = ensure_scratch(h, (size_t)total * (m.dim + 2) * sizeof(double)); if (rc) return rc;
-  double *dx = h->d_scratch, *dlp = dx + total * m.dim, *dll = dlp + total;
+  rc = stage_setup(h, (size_t)total * (m.dim + 2) * sizeof(double)); if (rc) return rc;
+  const int b = h->stage_next; h->stage_next ^= 1;
+  double *dx = h->d_stage[b], *dlp = dx + total * m.dim, *dll = dlp + total;
+  if (h->stage_used[b]) CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_copied[b], 0)); // the copy that last read this buffer
   ptg_gather_cold_kernel<<<grid_for(total), 256, 0, h->stream>>>(m, h->s, n_out, dx, dlp, dll);
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaMemcpyAsync(x_out, dx, (size_t)total * m.dim * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(cudaMemcpyAsync(lpost_out, dlp, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(cudaMemcpyAsync(llike_out, dll, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaEventRecord(h->ev_gathered[b], h->stream));
+  CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_gathered[b], 0));
+  CUDA_TRY(cudaMemcpyAsync(x_out, dx, (size_t)total * m.dim * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
+  CUDA_TRY(cudaMemcpyAsync(lpost_out, dlp, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
+  CUDA_TRY(cudaMemcpyAsync(llike_out, dll, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
+  CUDA_TRY(cudaEventRecord(h->ev_copied[b], h->copy_stream));
+  h->stage_used[b] = true;
+  return 0;
+}
+extern "C" int ptg_step_host_wait(ptg_handle *h) {
+  if (!h) return fail(PTG_EINVAL, "null handle");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  if (h->copy_stream) CUDA_TRY(cudaStreamSynchronize(h->copy_stream));
+  return 0;
+}
+extern "C" int ptg_step_host(ptg_handle *h, int64_t n_steps, int32_t n_out, double *x_out, double *lpost_out, double *llike_out) {
+  int rc = ptg_step_host_begin(h, n_steps, n_out, x_out, lpost_out, llike_out); if (rc) return rc;
+  rc = ptg_step_host_wait(h); if (rc) return rc;
   return ptg_synchronize(h);
+}
+/* effective ring capacity (ptg_create maps hist_capacity = 0 to n_init + 1024) */
+extern "C" int ptg_get_hist_capacity(ptg_handle *h, int32_t *capacity) {
+  if (!h || !capacity) return fail(PTG_EINVAL, "null argument");
+  *capacity = h->m.hist_cap;
+  return 0;
 }
 
 // batched device evaluation of the likelihood functor / the prior at caller-provided states x[n][dim]

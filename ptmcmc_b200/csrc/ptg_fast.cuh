@@ -324,8 +324,10 @@ __device__ __forceinline__ int fx_swap(const PtgModel &m, const PtgState &s, con
 // XCHG: 0 = plain; 1 = with the rung-boundary exchange in the prologue / epilogue (ptg_step_exchange); 2 = also inside the iteration loop.
 // LK  : -1 = every feature at run time; >= 0 = streamlined configuration (see the head of this file) with likelihood kind LK.
 // Separate instantiations: each form's extra code costs registers and stack, and the plain kernel carries none of it
-template <int D, int XCHG, int LK>
-__global__ void __launch_bounds__(PTG_FSTEP_MAX_THREADS, 1) ptg_fstep_kernel(const __grid_constant__ PtgModel m, PtgState s, long long step0, int n_steps, int W, const __grid_constant__ PtgXchg xc) {
+// MAXT: largest CTA of the instantiation = its register budget (896 threads: 72 registers, one wave of 28 warps per SM; 448 threads: 144
+// registers and no spills, for batches that put at most 14 warps on an SM, e.g. BASELINE config 5's 2048 ladders per GPU)
+template <int D, int XCHG, int LK, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) ptg_fstep_kernel(const __grid_constant__ PtgModel m, PtgState s, long long step0, int n_steps, int W, const __grid_constant__ PtgXchg xc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr bool SL = (LK >= 0);                 // streamlined: the FS(run-time expression, folded value) flags below are constants
 #define FS(expr, val) (SL ? (val) : (expr))

@@ -30,9 +30,9 @@ static cudaError_t launch_wstep_t(const PtgModel &m, const PtgState &s, long lon
 // production kernel (Philox draws): ladder-in-a-warp; proposal table, bins, per-thread counters / MAP and the per-warp pool slots in
 // dynamic shared memory (FShared).  lk = -1: every feature at run time; lk >= 0: the streamlined instantiation for likelihood kind lk
 // (the host checks the configuration, ptg_api.cu:fstep_streamlined_kind)
-template <int D, int XCHG, int LK>
+template <int D, int XCHG, int LK, int MAXT>
 static cudaError_t launch_fstep_k(const PtgModel &m, const PtgState &s, long long step0, int n_steps, int W, const PtgXchg &xc, int blocks, int threads, size_t smem, cudaStream_t st) {
-  auto k = ptg_fstep_kernel<D, XCHG, LK>;
+  auto k = ptg_fstep_kernel<D, XCHG, LK, MAXT>;
   static size_t smem_set[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -62,12 +62,13 @@ static cudaError_t launch_fstep_t(const PtgModel &m, const PtgState &s, long lon
   const int wpb = threads / 32;
   const int blocks = (int)((warps + wpb - 1) / wpb);
   const size_t smem = FShared<D>::bytes(threads, m.n_rungs, m.n_props);
-#define GO(X, L) return launch_fstep_k<D, X, L>(m, s, step0, n_steps, W, xc, blocks, threads, smem, st)
-  if (xc.on && xc.every > 0) GO(2, -1);
-  if (xc.on) { if (lk == PTG_LIKE_SINES) GO(1, PTG_LIKE_SINES); GO(1, -1); }
-  if (lk == PTG_LIKE_SINES) GO(0, PTG_LIKE_SINES);
-  if (lk == PTG_LIKE_GAUSS_ISO) GO(0, PTG_LIKE_GAUSS_ISO);
-  GO(0, -1);
+#define GO(X, L, T) return launch_fstep_k<D, X, L, T>(m, s, step0, n_steps, W, xc, blocks, threads, smem, st)
+  const bool small = threads <= 448; // at most 14 warps per SM: the 144-register instantiations
+  if (xc.on && xc.every > 0) GO(2, -1, 896);
+  if (xc.on) { if (lk == PTG_LIKE_SINES) { if (small) GO(1, PTG_LIKE_SINES, 448); GO(1, PTG_LIKE_SINES, 896); } GO(1, -1, 896); }
+  if (lk == PTG_LIKE_SINES) { if (small) GO(0, PTG_LIKE_SINES, 448); GO(0, PTG_LIKE_SINES, 896); }
+  if (lk == PTG_LIKE_GAUSS_ISO) { if (small) GO(0, PTG_LIKE_GAUSS_ISO, 448); GO(0, PTG_LIKE_GAUSS_ISO, 896); }
+  GO(0, -1, 896);
 #undef GO
 }
 template <int D, int MODE>

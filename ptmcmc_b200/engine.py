@@ -68,8 +68,9 @@ class Engine(K.CApi):
         c = self.get_counters()
         i = ladder * self.cfg.n_rungs + rung
         nsize, nhist = int(c["nsize"][i]), int(c["nhist"][i])
-        if nsize > self.cfg.hist_capacity:
-            raise RuntimeError("report_effective_samples: the ring has wrapped (%d records > capacity %d)" % (nsize, self.cfg.hist_capacity))
+        cap = self.hist_capacity()
+        if nsize > cap:
+            raise RuntimeError("report_effective_samples: the ring has wrapped (%d records > capacity %d)" % (nsize, cap))
         x = self.get_history(ladder, rung, 0, nsize, full=False)["x"]
         se = self.cfg.save_every
         return report_effective_samples(x, nhist, n_init=self.cfg.n_init, add_every=se,
@@ -139,6 +140,17 @@ class Engine(K.CApi):
 
     def step_host(self, n_steps, n_out, x_out, lpost_out, llike_out):
         self._call("step_host", self.h, C.c_int64(n_steps), C.c_int32(n_out), K._dp(x_out), K._dp(lpost_out), K._dp(llike_out))
+
+    def step_host_begin(self, n_steps, n_out, x_out, lpost_out, llike_out):
+        """enqueue n_steps iterations + the copy of every ladder's newest n_out cold samples to (pinned) host arrays; returns at once"""
+        self._call("step_host_begin", self.h, C.c_int64(n_steps), C.c_int32(n_out), K._dp(x_out), K._dp(lpost_out), K._dp(llike_out))
+
+    def step_host_wait(self):
+        self._call("step_host_wait", self.h)
+
+    def hist_capacity(self):
+        """effective ring capacity (a config value of 0 means n_init + 1024)"""
+        c = C.c_int32(); self._call("get_hist_capacity", self.h, C.byref(c)); return c.value
 
     def checkpoint(self, path):
         self._call("checkpoint", self.h, path.encode())

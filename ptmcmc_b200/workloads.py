@@ -50,7 +50,28 @@ class Spec:
         return K.make_config(n_ladders, self.rungs, self.dim, **kw)
 
     def scales(self):
-        return self.halfwidths.copy()  # getScales: uniform half-width or Gaussian sigma
+        """getScales: uniform half-width or Gaussian sigma; log-type dimensions of a mixed prior: center * min(1, (h - 1/h) / 2)
+        (probability_function.hh:172-181)"""
+        sc = self.halfwidths.copy()
+        if self.prior == "mixed":
+            for i, t in enumerate(self.prior_types):
+                if int(t) == K.PRIOR_LOG:
+                    fac = (self.halfwidths[i] - 1 / self.halfwidths[i]) / 2
+                    if fac > 1:
+                        fac = 1
+                    sc[i] = self.centers[i] * fac
+        return sc
+
+    def prior_ab(self):
+        """(a, b) of every 1-D factor as ptg_set_prior takes them: (min, max), (x0, sigma) for Gaussian factors, and for log-type factors
+        the multiplicative range (center / halfwidth, center * halfwidth) of mixed_dist_product (probability_function.cc:243-249)"""
+        types = np.asarray(self.prior_types, dtype=np.int32)
+        a = np.where(types == K.PRIOR_GAUSSIAN, self.centers, self.centers - self.halfwidths)
+        b = np.where(types == K.PRIOR_GAUSSIAN, self.halfwidths, self.centers + self.halfwidths)
+        lg = types == K.PRIOR_LOG
+        a = np.where(lg, self.centers / self.halfwidths, a)
+        b = np.where(lg, self.centers * self.halfwidths, b)
+        return types, a, b
 
     def bounds(self):
         code = {"o": K.BOUND_OPEN, "l": K.BOUND_LIMIT, "w": K.BOUND_WRAP, "r": K.BOUND_REFLECT}
@@ -71,16 +92,22 @@ class Spec:
         elif self.prior == "gaussian":
             api.set_prior([K.PRIOR_GAUSSIAN] * d, self.centers, self.halfwidths)
         else:
-            types = np.asarray(self.prior_types, dtype=np.int32)
-            a = np.where(types == K.PRIOR_GAUSSIAN, self.centers, self.centers - self.halfwidths)
-            b = np.where(types == K.PRIOR_GAUSSIAN, self.halfwidths, self.centers + self.halfwidths)
-            api.set_prior(types, a, b)
+            api.set_prior(*self.prior_ab())
         e = self.extra
         if self.model == "gauss":
             sigma = e.get("sigma", 0.5)
             tw = 2 * sigma * sigma
             x0 = np.asarray(e.get("x0", self.centers), dtype=float)
             api.set_likelihood(K.LIKE_GAUSS_ISO, np.concatenate([[-0.5 * d * np.log(np.pi * tw), tw], x0]))
+        elif self.model == "shell2d":   # gaussian_shell_2D_likelihood (example.cc:147-222)
+            sigma = e.get("shell_sigma", 0.1)
+            tw = 2 * sigma * sigma
+            api.set_likelihood(K.LIKE_SHELL2D, [-0.5 * np.log(np.pi * tw), tw, e.get("shell_r0", 2.0), e.get("shell_x0", 3.0), e.get("shell_x1", 0.0)])
+        elif self.model == "shells":    # gaussian_shell_likelihood (example.cc:226-421)
+            sigma, spm = e.get("shell_sigma", 0.1), e.get("shell_spm", 1.0)
+            tw = 2 * sigma * sigma
+            api.set_likelihood(K.LIKE_SHELLS, [-0.5 * np.log(np.pi * tw), tw, e.get("shell_r0", 2.0), e.get("shell_x0", 3.0), spm, np.log(spm),
+                                               float(e.get("shell_logx", 0))])
         elif self.model == "sines":
             k = e.get("k", 2)
             api.set_likelihood(K.LIKE_SINES, np.concatenate([[e.get("height", 64.0), e.get("step_scale", np.log(2.0))],
@@ -117,7 +144,10 @@ class Spec:
         elif self.prop == "prior":
             f = e.get("prior_draw_frac", 0.3)
             de2 = dict(de); de2["share"] = 1 - f
-            api.set_proposals([de2, dict(kind=K.PROP_PRIOR_DRAW, share=f)])
+            # thermal weighting of the prior draws as ptmcmc_sampler::select_proposal sets it up (ptmcmc.cc:95-101, prior_draw_Tpow)
+            Tpow = e.get("Tpow", 0.0)
+            de2["hot_share"] = e.get("hot_de", 0.0) if Tpow > 0 else 0.0
+            api.set_proposals([de2, dict(kind=K.PROP_PRIOR_DRAW, share=f, hot_share=e.get("hot_prior", 1.0) if Tpow > 0 else 0.0)], Tpow=Tpow)
         else:
             raise ValueError(self.prop)
 

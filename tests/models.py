@@ -52,7 +52,7 @@ def compare_dumps(a, b, rtol=0.0, what="", max_report=5, exact_x=True):
     exact_x: positions and acceptance ratios must be bit-identical even when rtol > 0 (tape parity)"""
     bad = []
 
-    def chk(name, u, v, exact=False):
+    def chk(name, u, v, exact=False, scale_to_column=False):
         u = np.asarray(u); v = np.asarray(v)
         if u.shape != v.shape:
             bad.append("%s %s: shape %s vs %s" % (what, name, u.shape, v.shape)); return
@@ -60,7 +60,13 @@ def compare_dumps(a, b, rtol=0.0, what="", max_report=5, exact_x=True):
             ok = (u == v) | ((u != u) & (v != v))
         else:
             with np.errstate(invalid="ignore"):
-                ok = (np.abs(u - v) <= rtol * np.maximum(np.abs(u), np.abs(v))) | (u == v) | ((u != u) & (v != v))
+                ref = np.maximum(np.abs(u), np.abs(v))
+                if scale_to_column and u.ndim == 2 and len(u):
+                    # positions: a proposal x + gamma (a - b) cancels, so an ulp of the parameter's scale is the honest unit near zero
+                    ref = np.maximum(ref, np.nanmax(np.where(np.isfinite(u), np.abs(u), 0.0), axis=0, keepdims=True))
+                if not exact_x:
+                    ref = np.maximum(ref, 1.0)   # libm-dependent positions: log-posteriors that cancel to ~0 are compared on the scale of their terms
+                ok = (np.abs(u - v) <= rtol * ref) | (u == v) | ((u != u) & (v != v))
         if not np.all(ok):
             idx = np.argwhere(~ok)[0]
             bad.append("%s %s: %d mismatches, first at %s: %r vs %r" % (what, name, int((~ok).sum()), tuple(idx), u[tuple(idx)], v[tuple(idx)]))
@@ -72,7 +78,7 @@ def compare_dumps(a, b, rtol=0.0, what="", max_report=5, exact_x=True):
                 bad.append("%s rung %d %s: %r vs %r" % (what, r, k, ra[k], rb[k]))
         if ra["nsize"] != rb["nsize"]:
             continue
-        chk("rung %d x" % r, ra["x"], rb["x"], exact=exact_x)
+        chk("rung %d x" % r, ra["x"], rb["x"], exact=exact_x, scale_to_column=True)
         chk("rung %d htype" % r, ra["htype"], rb["htype"])
         chk("rung %d hacc" % r, ra["hacc"], rb["hacc"], exact=exact_x)
         chk("rung %d hbeta" % r, ra["hbeta"], rb["hbeta"])
@@ -110,6 +116,22 @@ def parity_cases():
         # ready member whose bin covers the draw (proposal_distribution.cc:105-112, proposal_distribution.hh:399-407)
         ("de_not_ready", Spec("gauss", 2, 4, centers=[2, -3], halfwidths=[2, 3], seed=0.83, de_ni=3, Tmax=100), 300, 3),
         ("R3_high_swap_rate", Spec("gauss", 2, 3, centers=[2, -3], halfwidths=[2, 3], seed=0.41, swap_rate=0.9, Tmax=50), 800, 5),
+        # the remaining mixed_dist_product factor types (probability_function.cc:235-249; ProbabilityDist.h:107-139,171-232): polar angle,
+        # co-latitude, logarithmic; with the default proposal mix (scales of log-type dimensions, probability_function.hh:172-181) and with
+        # prior draws, whose Hastings ratio evaluates every pdf and whose draws go through every invcdf
+        ("mixed_polar_copolar_log", Spec("gauss", 4, 5, centers=[np.pi / 2, 0.0, 2.0, 1.0], halfwidths=[np.pi / 2, np.pi / 2, 3.0, 2.0], prior="mixed",
+                                         prior_types=[3, 4, 5, 1], seed=0.37, Tmax=100, extra=dict(sigma=0.6, x0=np.array([1.2, 0.3, 1.5, 0.5]))), 800, 2),
+        ("mixed_types_prior_draw", Spec("gauss", 4, 4, centers=[1.6, 0.1, 3.0, 0.0], halfwidths=[1.2, 1.0, 2.5, 1.5], prior="mixed", prop="prior",
+                                        prior_types=[3, 4, 5, 2], seed=0.29, Tmax=30, extra=dict(sigma=0.8, x0=np.array([1.5, 0.2, 2.0, 0.3]))), 800, 1),
+        # temperature-dependent shares (proposal_distribution.cc:40-54,72-79): hot rungs draw from the prior, as prior_draw_Tpow sets it up
+        ("Tpow_hot_prior_draws", Spec("gauss", 2, 6, centers=[2, -3], halfwidths=[2, 3], prop="prior", seed=0.53, Tmax=1e3,
+                                      extra=dict(Tpow=0.5, prior_draw_frac=0.1)), 1000, 2),
+        ("Tpow2_custom_hot_shares", Spec("sines", 2, 5, prop="prior", seed=0.61, extra=dict(Tpow=2.0, prior_draw_frac=0.2, hot_de=0.3, hot_prior=0.7)), 800, 1),
+        # shell likelihoods of example.cc (2-D reflected shell :147-222; d-dim shell pair :226-421, also in ln p0 with a log-type prior factor)
+        ("shell2d", Spec("shell2d", 2, 8, centers=[0, 0], halfwidths=[6, 6], seed=0.47, Tmax=100), 800, 2),
+        ("shells_d3_pair", Spec("shells", 3, 6, centers=[0, 0, 0], halfwidths=[6, 6, 6], seed=0.43, Tmax=100, extra=dict(shell_spm=1.5)), 600, 1),
+        ("shells_d2_logx", Spec("shells", 2, 6, centers=[np.exp(0.001) * np.sqrt(np.exp(5.998)), 0.0], halfwidths=[np.sqrt(np.exp(5.998)), 6.0], prior="mixed",
+                                prior_types=[5, 1], seed=0.59, Tmax=100, extra=dict(shell_logx=1)), 600, 1),
     ] + wide_cases()
 
 

@@ -89,7 +89,11 @@ def tape_parity(oracle_cls, engine_cls, spec, steps, L=1, what="", **cfg_kw):
     g.init_from_prior()
     g.step(steps)
     g.synchronize()
-    bad = compare_runs(o, g, steps, L, what)
+    # Prior factors whose inverse cdf goes through libm (polar: acos, co-polar: asin, logarithmic: exp; ProbabilityDist.h:131-134,202-205,
+    # 248-251) make the DRAWN POSITIONS differ between glibc and CUDA libm in the last ulp, like the log-likelihoods: those cases compare
+    # positions to 1e-12 relative; decisions, types and counters stay exact.  Every other case: positions bit-exact.
+    libm_positions = spec.prior == "mixed" and any(int(t) in (K.PRIOR_POLAR, K.PRIOR_COPOLAR, K.PRIOR_LOG) for t in spec.prior_types)
+    bad = compare_runs(o, g, steps, L, what, exact_x=not libm_positions)
     o.close(); g.close()
     return bad
 

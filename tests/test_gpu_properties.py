@@ -3,7 +3,7 @@ import os
 import numpy as np
 import pytest
 from ptmcmc_b200 import _capi as K
-from tests.models import Spec, engine_dump, compare_dumps
+from tests.models import Spec, engine_dump, compare_dumps, poly_data, sinusoid_spec, fullcov_spec
 
 pytestmark = pytest.mark.gpu
 
@@ -56,6 +56,17 @@ KERNEL_CASES = [
     ("gaussian_prior_prior_draw", Spec("gauss", 2, 5, centers=[2, -3], halfwidths=[2, 3], prop="prior", prior="mixed", prior_types=[1, 2]), {}),
     ("single_chain", Spec("sines", 2, 1, prop="de"), {}),
     ("de_not_ready_at_start", Spec("gauss", 2, 4, centers=[2, -3], halfwidths=[2, 3], de_ni=3, Tmax=100), {}),
+    # higher dimensions, the data likelihoods of BASELINE configs B / C2 and an eigen-rotated Gaussian proposal
+    ("b_poly_d5_R4", Spec("poly", 5, 4, centers=np.zeros(5), halfwidths=np.full(5, 10.0), prop="de", Tmax=1e6, extra=poly_data(n=120)), dict(L=60)),
+    ("c2_sinusoid_d9_R4", sinusoid_spec(4, n=150, dt=0.05), dict(L=40)),
+    ("fullcov_d16_R6_eigen_rotated", fullcov_spec(16, 6, Tmax=1e3, de_ni=12), dict(L=60)),
+    ("gauss_d9_R32_save2", Spec("gauss", 9, 32, centers=np.zeros(9), halfwidths=np.full(9, 4.0), save_every=2), dict(L=40)),
+    ("gauss_d5_R32_save_every3_full_record", Spec("gauss", 5, 32, centers=np.zeros(5), halfwidths=np.full(5, 4.0), save_every=3), dict(L=40)),
+    ("mixed_polar_copolar_log_d4", Spec("gauss", 4, 5, centers=[np.pi / 2, 0.0, 2.0, 1.0], halfwidths=[np.pi / 2, np.pi / 2, 3.0, 2.0], prior="mixed",
+                                        prior_types=[3, 4, 5, 1], Tmax=100, extra=dict(sigma=0.6, x0=np.array([1.2, 0.3, 1.5, 0.5]))), dict(L=60)),
+    ("Tpow_hot_prior_draws", Spec("gauss", 2, 6, centers=[2, -3], halfwidths=[2, 3], prop="prior", Tmax=1e3, extra=dict(Tpow=0.5, prior_draw_frac=0.1)), dict(L=60)),
+    ("shells_d3", Spec("shells", 3, 6, centers=[0, 0, 0], halfwidths=[6, 6, 6], Tmax=100, extra=dict(shell_spm=1.5)), dict(L=60)),
+    ("dim13_R5", Spec("gauss", 13, 5, centers=np.zeros(13), halfwidths=np.full(13, 3.0), de_ni=12), dict(L=30)),
 ]
 
 
@@ -63,14 +74,17 @@ KERNEL_CASES = [
 def test_kernels_agree_bitwise(name, spec, kw, engine_cls):
     """Philox mode: the production kernel (FAST), the tape-capable warp kernel (WARP, bit-exact with the reference under
     injected draws) and the shared-memory kernel (SHARED) produce bit-identical chains on a 300-ladder batch"""
+    kw = dict(kw)
+    L = kw.pop("L", 300)
+
     def run(kern):
-        e = engine_cls(spec.config(n_ladders=300, rng_mode=K.RNG_PHILOX, hist_capacity=spec.de_ni * spec.dim + 1100, **kw))
+        e = engine_cls(spec.config(n_ladders=L, rng_mode=K.RNG_PHILOX, hist_capacity=spec.de_ni * spec.dim + 1100, **kw))
         e.select_kernel(kern)
         spec.setup(e); e.init_from_prior(); e.step(77); e.step(423); e.synchronize()
         return e
     es = [run(k) for k in (K.KERNEL_FAST, K.KERNEL_WARP, K.KERNEL_SHARED)]
     assert len({e.get_total_steps() for e in es}) == 1
-    for l in (0, 7, 150, 299):
+    for l in (0, 7, L // 2, L - 1):
         d0 = engine_dump(es[0], l)
         for e in es[1:]:
             assert compare_dumps(d0, engine_dump(e, l), rtol=0.0, what=name) == []
@@ -135,6 +149,62 @@ def test_step_chunking_and_checkpoint_roundtrip(engine_cls, tmp_path):
     for l in (0, 31, 63):
         same_ladder(a, l, d, l)
     assert a.get_current()["x"].tobytes() == d.get_current()["x"].tobytes()
+
+
+def test_restore_refuses_a_different_run(engine_cls, tmp_path):
+    """ptg_restore continues the interrupted run or fails: another seed, save cadence or swap schedule is an error, not a silent fork"""
+    spec = Spec("sines", 3, 8)
+    mk = lambda **kw: engine_cls(spec.config(n_ladders=4, rng_mode=K.RNG_PHILOX, hist_capacity=400, **kw))
+    a = mk(); spec.setup(a); a.init_from_prior(); a.step(50)
+    path = os.path.join(str(tmp_path), "a.ckpt")
+    a.checkpoint(path)
+    for kw, word in ((dict(seed=12345), "seed"), (dict(save_every=2), "save_every"), (dict(swap_rate=0.2), "swap_rate"), (dict(swap_mode=K.SWAP_EVEN_ODD), "swap_mode"),
+                     (dict(evolve_rate=0.01), "evolve_rate"), (dict(ladder_offset=4), "ladder_offset")):
+        b = mk(**kw); spec.setup(b)
+        with pytest.raises(K.CApiError, match=word):
+            b.restore(path)
+        b.close()
+    with open(path, "r+b") as f:       # a truncated file is detected, too
+        f.truncate(os.path.getsize(path) // 2)
+    b = mk(); spec.setup(b)
+    with pytest.raises(K.CApiError, match="truncated|mismatch"):
+        b.restore(path)
+
+
+def test_chi2_workload_is_invariant_to_batch_size(engine_cls):
+    """BASELINE config B under automatic kernel selection: a shard of the batch produces the chains the full batch produces for the same
+    global ladders -- the kernel a workload runs in must not depend on how many ladders share the GPU (2048 x 16 chains would have crossed
+    the old 48 k-chain threshold)"""
+    spec = Spec("poly", 5, 16, centers=np.zeros(5), halfwidths=np.full(5, 10.0), prop="de", Tmax=1e6, extra=poly_data(n=100))
+
+    def run(L, off):
+        e = engine_cls(spec.config(n_ladders=L, rng_mode=K.RNG_PHILOX, hist_capacity=400, ladder_offset=off, record_level=K.RECORD_BASIC))
+        spec.setup(e); e.init_from_prior(); e.step(60); e.synchronize()
+        return e
+    big, part = run(3200, 0), run(64, 3000)       # 51 200 chains vs 1024 chains
+    xb, xp = big.get_current()["x"].reshape(3200, 16, 5), part.get_current()["x"].reshape(64, 16, 5)
+    assert xb[3000:3064].tobytes() == xp.tobytes()
+    hb = big.get_history(3010, 0, 0, 300, full=False); hp = part.get_history(10, 0, 0, 300, full=False)
+    assert hb["x"].tobytes() == hp["x"].tobytes() and hb["llike"].tobytes() == hp["llike"].tobytes()
+
+
+def test_async_host_blocks_return_every_cold_sample(engine_cls):
+    """ptg_step_host_begin / _wait: two blocks in flight, every cold sample of each block lands in its own host buffer"""
+    spec = Spec("sines", 3, 8)
+    e = engine_cls(spec.config(n_ladders=32, rng_mode=K.RNG_PHILOX, hist_capacity=2048, record_level=K.RECORD_BASIC))
+    spec.setup(e); e.init_from_prior(); e.step(40)
+    S = 100
+    bufs = [(np.empty((32, S, 3)), np.empty((32, S)), np.empty((32, S))) for _ in range(3)]
+    for b in bufs:
+        e.step_host_begin(S, S, *b)
+    e.step_host_wait(); e.synchronize()
+    cnt = e.get_counters()
+    for l in (0, 17, 31):
+        n = int(cnt["nsize"][l * 8])
+        h = e.get_history(l, 0, n - S, S, full=False)
+        assert bufs[2][0][l].tobytes() == h["x"].tobytes() and bufs[2][1][l].tobytes() == h["lpost"].tobytes()
+    # consecutive blocks are consecutive stretches of the cold chain (up to the few extra swap appends of the cold rung)
+    assert not np.isnan(bufs[0][0]).any() and not (bufs[0][0][0] == bufs[1][0][0]).all()
 
 
 def test_step_host_returns_newest_cold_samples(engine_cls):
@@ -218,8 +288,12 @@ def test_error_behaviour(engine_cls):
     t.inject_tapes(np.full(10, 0.5), np.arange(ns + 1) * 2, np.zeros(10), np.arange(ns + 1) * 2)
     with pytest.raises(K.CApiError, match="tape exhausted"):
         t.init_from_prior()
-    with pytest.raises(K.CApiError, match="dim="):
-        engine_cls(K.make_config(1, 4, 11))
+    with pytest.raises(K.CApiError, match="dim out of range"):
+        engine_cls(K.make_config(1, 4, 129))
+    for d in (11, 13, 14, 15):     # no holes in the dimension range (states.hh is any d)
+        engine_cls(K.make_config(1, 4, d)).close()
+    with pytest.raises(K.CApiError, match="dim = 2"):
+        s2 = Spec("shell2d", 3, 2, centers=[0, 0, 0], halfwidths=[6, 6, 6]); e3 = engine_cls(s2.config(n_ladders=1)); s2.setup(e3)
 
 
 def test_set_current_roundtrip(engine_cls):

@@ -145,3 +145,61 @@ def test_gaussian_proposal_covariance(engine_cls):
     err = np.linalg.norm(sample - cov) / np.linalg.norm(cov)
     assert err < 0.02, err                                   # ~1.3e5 draws: testGaussian.cc prints this norm at powers of two
     assert abs(inc.mean()) < 0.02
+
+
+def test_ring_window_at_the_bench_configuration(engine_cls):
+    """bench.py's own C1 configuration -- 4096 ladders x 32 rungs, d = 3, default proposal mix, save_every 1, an 8192-slot history ring
+    -- run for 30 000 PT iterations, so the ring wraps 3.7 times and differential evolution proposes from a sliding window of the chain's
+    past instead of the reference's unbounded history.  The cold-chain posterior is checked against (a) the analytic peak
+    weights of the sines surface (8 cells, weight 2^-(i+j+k) / (27/8), sines.hh:22-54 / testMH.cpp:186-195), (b) the same workload with a ring
+    that never wraps (512 ladders): peak weights, in-peak variance, and k-NN KL below BASELINE's 0.01-nat bar"""
+    spec = Spec("sines", 3, 32)
+    steps, tail, thin = 30000, 8000, 40
+
+    def run(L, cap, seed):
+        e = engine_cls(spec.config(n_ladders=L, rng_mode=K.RNG_PHILOX, hist_capacity=cap, record_level=K.RECORD_BASIC, seed=seed))
+        spec.setup(e); e.init_from_prior()
+        for _ in range(steps // 1000):
+            e.step(1000)
+        e.synchronize()
+        cnt = e.get_counters()
+        nl = min(L, 512)
+        out = np.empty((nl, tail, 3))
+        for l in range(nl):
+            n = int(cnt["nsize"][l * 32])
+            out[l] = e.get_history(l, 0, n - tail, tail, full=False)["x"]
+        e.close()
+        return out
+    wrapped = run(4096, 8192, 0xB2000003)
+    unwrapped = run(512, spec.de_ni * 3 + steps + steps // 8 + 64, 0xB2000777)   # every append of the run stays resident
+
+    def peak_weights(c):
+        idx = (c[:, ::thin, :].reshape(-1, 3) >= 0.5).astype(int)
+        w = np.bincount(idx[:, 0] * 4 + idx[:, 1] * 2 + idx[:, 2], minlength=8) / float(len(idx))
+        return w
+    theory = np.array([2.0 ** -(i + j + k) for i in (0, 1) for j in (0, 1) for k in (0, 1)]) / (27.0 / 8.0)
+    ww, wu = peak_weights(wrapped), peak_weights(unwrapped)
+    print("peak weights theory   ", np.round(theory, 4)); print("peak weights ring 8192", np.round(ww, 4)); print("peak weights unwrapped", np.round(wu, 4))
+    assert np.abs(ww - theory).max() < 0.012 and np.abs(wu - theory).max() < 0.012
+    assert np.abs(ww - wu).max() < 0.012
+
+    def in_peak_var(c):  # variance of x_0 inside the heaviest cell
+        p = c[:, ::thin, :].reshape(-1, 3)
+        sel = (p < 0.5).all(axis=1)
+        return p[sel, 0].var()
+    vw, vu = in_peak_var(wrapped), in_peak_var(unwrapped)
+    print("in-peak variance: ring 8192 %.6g, unwrapped %.6g, ratio %.4f" % (vw, vu, vw / vu))
+    assert abs(vw / vu - 1) < 0.03
+    pw, pu = wrapped[:, ::thin * 4, :].reshape(-1, 3), unwrapped[:, ::thin * 4, :].reshape(-1, 3)
+    half = len(pu) // 2
+    floor = abs(knn_kl(pu[:half], pu[half:]))
+    kl1, kl2 = knn_kl(pw, pu), knn_kl(pu, pw)
+    print("KL(ring 8192 || unwrapped) = %.4f, reverse %.4f, estimator noise floor %.4f (n = %d)" % (kl1, kl2, floor, len(pw)))
+    assert abs(kl1) < 0.01 and abs(kl2) < 0.01
+    # ESS per PT iteration by the reference's recipe: the sliding window must not change the mixing either
+    def recipe(c):
+        e = np.array([report_effective_samples(c[l], tail, width=1000, every=1) for l in range(0, 256, 2)])
+        return float(np.mean(e[:, 0] / np.maximum(e[:, 1], 1)))
+    rw, ru = recipe(wrapped), recipe(unwrapped)
+    print("ESS per iteration (reference recipe): ring 8192 %.5f, unwrapped %.5f" % (rw, ru))
+    assert abs(rw / ru - 1) < 0.10
