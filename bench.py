@@ -9,8 +9,13 @@ parallel_tempering_chains::step (chain.cc:1393) for every ladder on the GPU, in 
 `value`  = tempered chain-steps (history appends = Nhist increments) of all ranks / device time (CUDA
            events on the engine's stream, max over ranks), state resident in HBM.
 `e2e`    = the same metric through the C-ABI calls a host facade makes per block with HOST buffers inside the timed
-           region: ptg_set_current (H2D of every chain's state from pinned memory) -> ptg_step_host (steps + D2H of
-           the cold chains' newest samples).
+           region: ptg_set_current (H2D of every chain's state from pinned memory) -> ptg_step_host_begin (steps + D2H of
+           EVERY cold-chain sample the block produced, what the reference's run loop dumps, ptmcmc.cc:601-616) with two
+           pinned buffers, so the copy of block k overlaps the kernel of block k+1.
+`sustained` = the device-resident measurement repeated over >= 3 s with the clocks sampled: the number a warm part holds.
+`workloads` (1 GPU) = short runs of BASELINE.json's other configs (A, B, C2, D), each with value, e2e and both rooflines;
+`config5`, `rung_sharded` (N > 1) = config 5's batch (2048 ladders x 32 rungs per GPU) and the rung-sharded layout with the
+           boundary exchange fused into the step kernel over NVLink peer memory (K = 10 iterations per exchange).
 The reference arm (`--impl reference`) times the UNMODIFIED reference (oracle/_ref/ref_trace: our driver compiled
 against the reference sources, stepping parallel_tempering_chains through its public API) on the host cores, one
 ladder per process, all cores busy -- the only CPU parallelism that scales for this code.
@@ -139,9 +144,11 @@ def cpu_threads():
         return os.cpu_count() or 1
 
 
-def run_reference_sample(w, pt_steps, procs):
+def run_reference_sample(w, pt_steps, procs, ess=False):
     """`procs` independent processes, each one ladder of the workload stepped `pt_steps` times by the reference itself
-    (oracle/_ref/ref_trace) or, when that binary is absent, by the oracle port.  Returns (chain_steps, seconds, kind)."""
+    (oracle/_ref/ref_trace) or, when that binary is absent, by the oracle port.
+    Returns dict(chain_steps, seconds [max over processes of the time inside the stepping loop], wall, kind, ess [sum over ladders of
+    the reference's own chain::report_effective_samples, or None])."""
     spec = make_spec(w)
     ref = os.path.join(ROOT, "oracle", "_ref", "ref_trace")
     if os.path.exists(ref):
@@ -150,22 +157,28 @@ def run_reference_sample(w, pt_steps, procs):
             for i in range(procs):
                 spec.seed = 0.05 + 0.9 * (i + 0.5) / procs
                 pd = os.path.join(td, "p%d" % i); os.makedirs(pd)
-                cmds.append([ref] + spec.ref_args(pd, pt_steps, "/dev/null"))
+                cmds.append([ref] + spec.ref_args(pd, pt_steps, "/dev/null") + (["ess=1"] if ess else []))
             t0 = time.perf_counter()
             ps = [subprocess.Popen(c, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True) for c in cmds]
             outs = [p.communicate()[0] for p in ps]
-            dt = time.perf_counter() - t0
-        total = 0
+            wall = time.perf_counter() - t0
+        total, secs, ess_sum, ess_n = 0, 0.0, 0.0, 0
         for o, p in zip(outs, ps):
             if p.returncode != 0:
                 raise RuntimeError("ref_trace failed")
             total += int(o.split("total_Nhist=")[1].split()[0])
-        return total, dt, "reference"
+            secs = max(secs, float(o.split("step_seconds=")[1].split()[0]))
+            if ess and "ref_ess: ess=" in o:
+                v = float(o.split("ref_ess: ess=")[1].split()[0])
+                if v == v and v > 0:
+                    ess_sum += v; ess_n += 1
+        return dict(chain_steps=total, seconds=secs, wall=wall, kind="reference", ess=ess_sum if ess_n else None, ess_ladders=ess_n)
     import multiprocessing as mp
     t0 = time.perf_counter()
     with mp.get_context("spawn").Pool(procs) as pool:
         totals = pool.map(_port_worker, [(w, pt_steps, 0.05 + 0.9 * (i + 0.5) / procs) for i in range(procs)])
-    return sum(totals), time.perf_counter() - t0, "port"
+    dt = time.perf_counter() - t0
+    return dict(chain_steps=sum(totals), seconds=dt, wall=dt, kind="port", ess=None, ess_ladders=0)
 
 
 def _port_worker(args):
@@ -184,11 +197,281 @@ def reference_pt_steps(w, seconds=8.0):
     return max(20, int(seconds / (per_chain_step * w["rungs"])))
 
 
+def cpu_baseline(w, seconds, procs, unit):
+    """the unmodified reference on `procs` host cores (one ladder per process), chain-steps/s and -- from the reference's own
+    report_effective_samples on every process's cold chain -- ESS/s"""
+    n_pt = reference_pt_steps(w, seconds)
+    r = run_reference_sample(w, n_pt, procs, ess=True)
+    out = dict(value=r["chain_steps"] / r["seconds"], unit=unit, cores=procs, kind=r["kind"],
+               sample="%d processes x 1 ladder x %d rungs x %d PT iterations of the same workload (timed: the stepping loop, max over processes)" % (procs, w["rungs"], n_pt))
+    if r["ess"] is not None:
+        out["ess"] = dict(value=r["ess"] / r["seconds"], unit="ESS/s", ladders_with_estimate=r["ess_ladders"],
+                          estimator="chain::report_effective_samples(-1, 1000 save_every, save_every) of the reference itself on each process's cold chain (ref_trace ess=1, chain.cc:549-643), summed")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------- one workload on this rank's GPU
+def peaks():
+    pp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pp):
+        return float(json.load(open(pp))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def fp64_peaks():
+    for name in ("r02_fp64_peaks.json", "r01_fp64_peaks.json"):
+        pp = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(pp):
+            return json.load(open(pp)), "measured: profiles/" + name
+    return None, None
+
+
+def measure(name, w, steps, warmup, rank, world, local, swap_mode="reference", e2e_steps=None, sustain_s=0.0, with_ess=False, with_e2e=True):
+    """device-resident throughput, optional >= sustain_s seconds repeat, ESS, end-to-end blocks and rooflines of one workload"""
+    import torch
+    import torch.distributed as dist
+    from ptmcmc_b200 import _capi as K
+    from ptmcmc_b200.engine import Engine
+    from ptmcmc_b200.sharding import max_over_ranks, sum_over_ranks
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+    spec = make_spec(w)
+    L, R, d, S = w["ladders"], w["rungs"], w["dim"], w["pt_steps"]
+    sm = K.SWAP_REFERENCE if swap_mode == "reference" else K.SWAP_EVEN_ODD
+    eng = Engine(spec.config(n_ladders=L, rng_mode=K.RNG_PHILOX, record_level=K.RECORD_BASIC, hist_capacity=w["hist"], save_every=w["save_every"], swap_mode=sm,
+                             device=local, ladder_offset=rank * L, seed=0xB2000003))
+    spec.setup(eng)
+    stream = torch.cuda.Stream()
+    eng.set_stream(stream.cuda_stream)
+    eng.init_from_prior()
+    eng.synchronize()
+    res = dict(name=name)
+    with torch.cuda.stream(stream):
+        for _ in range(warmup):
+            eng.step(S)
+        eng.synchronize()
+        l0 = eng.launch_count()
+        n0 = eng.get_total_steps()
+        clocks = ClockSampler(local); clocks.start()
+        barrier(); torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(steps):
+            eng.step(S)
+        ev1.record(stream)
+        torch.cuda.synchronize(); barrier()
+        ms = ev0.elapsed_time(ev1)
+        clk = clocks.stop()
+        eng.synchronize()
+        n1 = eng.get_total_steps()
+        launches = eng.launch_count() - l0
+        ms_max = max_over_ranks(ms)
+        res.update(value=sum_over_ranks(n1 - n0) / (ms_max * 1e-3), ms_per_step=ms_max / steps, clocks=clk, gpu_launches=int(launches), steps=steps,
+                   chain_steps_per_launch=(n1 - n0) / max(launches, 1), launch_ms=ms / max(launches, 1))
+        # ---- the same loop over >= sustain_s seconds: what the part holds once it is warm
+        if sustain_s > 0:
+            reps = max(steps, int(np.ceil(sustain_s * 1e3 / (ms / steps))))
+            m0 = eng.get_total_steps()
+            cs = ClockSampler(local); cs.start()
+            barrier(); torch.cuda.synchronize()
+            ev0.record(stream)
+            for _ in range(reps):
+                eng.step(S)
+            ev1.record(stream)
+            torch.cuda.synchronize(); barrier()
+            sms = max_over_ranks(ev0.elapsed_time(ev1))
+            sclk = cs.stop()
+            eng.synchronize()
+            m1 = eng.get_total_steps()
+            res["sustained"] = dict(value=sum_over_ranks(m1 - m0) / (sms * 1e-3), unit="chain-steps/s", seconds=sms * 1e-3, steps=reps, clocks=sclk)
+    if with_ess:
+        res["ess"] = ess_report(eng, w, L * world, res, world)
+    # ---- end to end through the C ABI with host buffers: H2D of every chain's state, steps, D2H of every cold sample of the block
+    if with_e2e:
+        n_chains = L * R
+        n_out = max(1, min(S // w["save_every"], w["hist"]))
+        pin = lambda *shape: torch.empty(*shape, dtype=torch.float64).pin_memory().numpy()
+        hx, hlp, hll, hpr = pin(n_chains, d), pin(n_chains), pin(n_chains), pin(n_chains)
+        bufs = [(pin(L, n_out, d), pin(L, n_out), pin(L, n_out)) for _ in range(2)]
+        cur = eng.get_current(); hx[:] = cur["x"]; hlp[:] = cur["lpost"]; hll[:] = cur["llike"]; hpr[:] = eng.get_lprior()
+        ne = e2e_steps or max(3, min(steps, 30))
+        with torch.cuda.stream(stream):
+            for i in range(2):
+                eng.set_current(hx, hlp, hll, hpr); eng.step_host_begin(S, n_out, *bufs[i])
+            eng.step_host_wait(); eng.synchronize()
+            m0 = eng.get_total_steps()
+            barrier(); torch.cuda.synchronize()
+            t0 = time.perf_counter(); ev0.record(stream)
+            for i in range(ne):
+                eng.set_current(hx, hlp, hll, hpr)
+                eng.step_host_begin(S, n_out, *bufs[i & 1])
+            eng.step_host_wait()
+            ev1.record(stream); torch.cuda.synchronize(); barrier()
+            e2e_ms = max(ev0.elapsed_time(ev1), 1e3 * (time.perf_counter() - t0))
+            eng.synchronize()
+            m1 = eng.get_total_steps()
+        assert not np.isnan(bufs[(ne - 1) & 1][0]).any(), "cold samples missing from the end-to-end read-back"
+        res["e2e"] = dict(value=sum_over_ranks(m1 - m0) / (max_over_ranks(e2e_ms) * 1e-3), unit="chain-steps/s", h2d_bytes_per_step=n_chains * (d + 3) * 8,
+                          d2h_bytes_per_step=L * n_out * (d + 2) * 8, steps=ne, cold_samples_per_ladder_per_step=n_out,
+                          how="ptg_set_current + ptg_step_host_begin per block, two pinned buffers, copy of block k overlaps kernel of block k+1")
+        res["_last_cold"] = bufs[(ne - 1) & 1][0]
+    # ---- rooflines of the dominant kernel (one launch per bench step)
+    peak, peak_src = peaks()
+    bpcs = algorithmic_bytes_per_chain_step(w)
+    achieved = bpcs * res["chain_steps_per_launch"] / (res["launch_ms"] * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    for tname in ("r02_traffic_%s.json" % name, "traffic_%s.json" % name):
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if os.path.exists(tpath):
+            t = json.load(open(tpath))  # ncu --set full capture of the same kernel, dram bytes per chain-step, scaled to this launch
+            if "dram_bytes_per_chain_step" in t:
+                traffic = t["dram_bytes_per_chain_step"] * res["chain_steps_per_launch"]
+            else:
+                traffic = t["dram_bytes_per_pt_iteration"] * S * (L * R) / float(t.get("chains_profiled", 131072))
+            traffic_src = "profiles/" + tname
+            break
+    kernel_name = "ptg_xmstep_kernel" if (d > 16 or w["model"] in ("poly", "sinusoid")) else ("ptg_fstep_kernel" if R <= 32 else "ptg_step_kernel")
+    res["roofline"] = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic, traffic_source=traffic_src, kernel=kernel_name,
+                           algorithmic_bytes_per_chain_step=bpcs, chain_steps_per_launch=res["chain_steps_per_launch"], launch_ms=res["launch_ms"], peak_source=peak_src,
+                           binding_limiter=w.get("limiter", "instruction issue (fp64 libm + Philox integer work), see profiles/README.md"))
+    fl = w.get("flops")
+    pk, pk_src = fp64_peaks()
+    if fl and pk:
+        ach = fl["per_chain_step"] * res["chain_steps_per_launch"] / (res["launch_ms"] * 1e-3) / 1e12
+        res["roofline_fp64"] = dict(bound="fp64", achieved=ach, peak=float(pk[fl["peak_key"]]), unit="TFLOP/s", frac=ach / float(pk[fl["peak_key"]]),
+                                    flops_per_chain_step=fl["per_chain_step"], counted=fl["what"], peak_source=pk_src + " " + fl["peak_key"])
+    eng.close()
+    return res
+
+
+def ess_report(eng, w, ladders_total, res, world):
+    """ESS/s (second half of BASELINE.json's metric): the reference's own estimator (chain::report_effective_samples as the run loop calls
+    it, ptmcmc.cc:645) for EVERY ladder's cold chain over the newest ring window -- lag statistics on the device in the reference's
+    summation order (ptg_get_autocovar_windows), combination on the host -- with a Sokal-window cross-check"""
+    try:
+        L, R = w["ladders"], w["rungs"]
+        cnt = eng.get_counters()
+        pt_iter_per_s = w["pt_steps"] / (res["ms_per_step"] * 1e-3)
+        nh = int(min(w["hist"] - 8, 2000, cnt["nsize"][::R].min()))
+        tau_dev = eng.get_act(0, nh, min(nh // 2, 1000))
+        eps_dev = float(np.mean(1.0 / tau_dev.max(axis=1)))
+        nr = int(min(w["hist"] - 8, 8000, cnt["nsize"][::R].min()))
+        eps_recipe, n_recipe = None, 0
+        ess_l, len_l = eng.report_effective_samples_all(rung=0, window_records=nr)
+        ok = len_l > 0
+        n_recipe = int(ok.sum())
+        if n_recipe:
+            eps_recipe = float(np.mean(ess_l[ok] / len_l[ok]))      # ESS per PT iteration, mean over ladders
+        sokal = eps_dev / w["save_every"] * pt_iter_per_s * ladders_total
+        out = dict(value=(eps_recipe * pt_iter_per_s * ladders_total) if eps_recipe else sokal, unit="ESS/s",
+                   estimator=("the reference's chain::report_effective_samples(-1, 1000 save_every, save_every) (chain.cc:457-643) on every cold chain's newest "
+                              "%d records: lag statistics on the device (ptg_get_autocovar_windows), min over parameters, summed over ladders" % nr) if eps_recipe
+                   else "Sokal window (see sokal_device); the ring window is too short for the reference recipe",
+                   ess_per_pt_iteration=eps_recipe, ladders=ladders_total, ladders_with_estimate=n_recipe * world, pt_iterations_per_s=pt_iter_per_s,
+                   sokal_device=dict(value=sokal, tau_pt_iterations=float(np.median(tau_dev.max(axis=1))) * w["save_every"], window=nh,
+                                     estimator="ptg_get_act: per cold chain N/tau, Sokal-windowed integrated autocorrelation time, min over parameters, mean over ladders"))
+        if nh > int(cnt["nsize"][::R].min()) - eng.cfg.n_init:
+            out["note"] = "the run is shorter than the analysis window: it still contains start-up prior draws, the ESS figure is not meaningful"
+        return out
+    except Exception as exc:  # analysis is not part of the timed path
+        return dict(value=None, error=repr(exc))
+
+
+def brief(r):
+    """what a sub-measurement contributes to the main JSON line"""
+    keep = ("value", "ms_per_step", "steps", "gpu_launches", "e2e", "roofline", "roofline_fp64", "clocks", "sustained", "ess", "config")
+    return {k: r[k] for k in keep if k in r}
+
+
+def workload_config(name, w, swap_mode="reference"):
+    return dict(workload="%s: %s" % (name, w["desc"]), ladders_per_gpu=w["ladders"], rungs=w["rungs"], dim=w["dim"],
+                chains_per_gpu=w["ladders"] * w["rungs"], pt_iterations_per_step=w["pt_steps"], save_every=w["save_every"], hist_capacity=w["hist"],
+                swap_mode=swap_mode, rng="philox4x32-10", parallelism="ladders sharded, %d per GPU, no data-path collective" % w["ladders"],
+                l2="history ring (%.1f GB per GPU) is larger than L2" % (w["ladders"] * w["rungs"] * w["hist"] * 8.0 * (hx(w["dim"]) + 2) / 1e9))
+
+
+def hx(d):
+    return (d + 3) // 4 * 4 if d <= 16 else d
+
+
+# ---------------------------------------------------------------------------------------------------- rung-sharded layout (N > 1)
+def measure_rung_sharded(w, K_ex, steps, warmup, rank, world, local, fused=True, in_launch=False, watchdog_s=120.0):
+    """ONE (world x rungs)-rung ladder family sharded by rung blocks (ptmcmc_b200/rung_sharding.py, the reference's MPI scheme
+    chain.cc:1290-1311 with block assignment): boundary swaps every K_ex PT iterations, fused into the step kernel over NVLink peer
+    memory (or over NCCL send/recv with fused=False)"""
+    import threading
+    import torch
+    import torch.distributed as dist
+    from ptmcmc_b200 import _capi as K
+    from ptmcmc_b200.engine import Engine
+    from ptmcmc_b200.sharding import max_over_ranks, sum_over_ranks
+    from ptmcmc_b200.rung_sharding import RungShardedLadders, FusedRungShardedLadders, rank_betas, rank_chain_seed
+    spec = make_spec(w)
+    L, R, d, S = w["ladders"], w["rungs"], w["dim"], w["pt_steps"]
+    eng = Engine(spec.config(n_ladders=L, rng_mode=K.RNG_PHILOX, record_level=K.RECORD_BASIC, hist_capacity=w["hist"], save_every=w["save_every"], device=local,
+                             seed=rank_chain_seed(0xB2000003, rank)))
+    spec.setup(eng)
+    eng.set_betas(rank_betas(L, R, rank, world, spec.Tmax))
+    stream = torch.cuda.Stream()
+    eng.set_stream(stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+    with torch.cuda.stream(stream):
+        eng.init_from_prior(); eng.synchronize()
+        if fused:
+            drv = FusedRungShardedLadders(eng, rank, world, 0xB2005EED, exchange_every=K_ex, in_launch=in_launch, max_launch=S)
+        else:
+            drv = RungShardedLadders(eng, rank, world, 0xB2005EED, exchange_every=K_ex, device="cuda:%d" % local, stream_ordered=True)
+        dog = threading.Timer(watchdog_s, eng.xchg_abort) if fused else None   # a neighbour that never launches must not hang this rank
+        if dog:
+            dog.daemon = True; dog.start()
+        for _ in range(warmup):
+            drv.run(S)
+        eng.synchronize(); n0 = eng.get_total_steps(); l0 = eng.launch_count()
+        barrier(); torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter(); ev0.record(stream)
+        for _ in range(steps):
+            drv.run(S)
+        drv.finish()
+        ev1.record(stream)
+        eng.synchronize(); torch.cuda.synchronize(); barrier()
+        dt = max(ev0.elapsed_time(ev1) * 1e-3, time.perf_counter() - t0) if not fused else ev0.elapsed_time(ev1) * 1e-3
+        if dog:
+            dog.cancel()
+        n1 = eng.get_total_steps(); launches = eng.launch_count() - l0
+        # the same launches without any exchange (what a cycle costs on its own)
+        torch.cuda.synchronize(); ev0.record(stream)
+        for _ in range(100):
+            eng.step(K_ex)
+        ev1.record(stream); eng.synchronize(); torch.cuda.synchronize()
+        bare_ms = ev0.elapsed_time(ev1) / 100
+    cycles = steps * ((S + K_ex - 1) // K_ex)
+    dt_max = max_over_ranks(dt)
+    out = dict(value=sum_over_ranks(n1 - n0) / dt_max, unit="chain-steps/s", steps=steps, pt_iterations_per_step=S, exchange_every=K_ex,
+               layout="%d ladders x (%d GPUs x %d rungs): rank g owns rungs [%d g, %d (g+1)) of every ladder" % (L, world, R, R, R),
+               exchange=("fused into the step kernel over NVLink peer memory (CUDA IPC, per-ladder flags): peer loads in the prologue of the next launch, no collective"
+                         + (", inside %d-iteration launches" % S if in_launch else ", one launch per exchange")) if fused else "NCCL neighbour send/recv, stream-ordered with the pack / swap kernels",
+               ms_per_cycle=1e3 * dt_max / cycles, ms_per_cycle_without_exchange=max_over_ranks(bare_ms), gpu_launches=int(launches),
+               nvlink_bytes_per_exchange_per_rank=int((2 if 0 < rank < world - 1 else 1) * L * (d + 3) * 8),
+               nvlink_bytes_per_exchange_interior_rank=int(2 * L * (d + 3) * 8))
+    over = out["ms_per_cycle"] - out["ms_per_cycle_without_exchange"]
+    out["exchange_overhead_ms_per_cycle"] = over
+    out["limiter"] = ("launch boundary: one launch per exchange costs the launch latency plus the wait for the slower neighbour's previous launch; the peer loads themselves "
+                      "(%d bytes per ladder edge) are latency-, not bandwidth-bound" % ((d + 3) * 8))
+    eng.close()
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=0, help="timed bench steps (default: enough for a >= 3 s timed region)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c1_sines", choices=sorted(WORKLOADS))
@@ -198,10 +481,11 @@ def main():
     ap.add_argument("--save-every", type=int, default=0, help="add_every_N: store every N-th sample (default: per workload)")
     ap.add_argument("--swap-mode", default="reference", choices=["reference", "even_odd"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="only the main workload: no `workloads` / `config5` / `rung_sharded` objects, no sustained repeat")
     ap.add_argument("--in-launch", action="store_true", help="with --fused-exchange: exchange inside long launches (whole grid must be resident)")
     ap.add_argument("--fused-exchange", action="store_true", help="with --rung-sharded: exchange fused into the step kernel over NVLink peer memory (no collective)")
     ap.add_argument("--rung-sharded", type=int, default=0, metavar="K",
-                    help="optional layout: ONE (n_gpus x rungs)-rung ladder family sharded by rung blocks, cross-GPU boundary swaps over NCCL every K PT iterations")
+                    help="main line = the rung-sharded layout: ONE (n_gpus x rungs)-rung ladder family sharded by rung blocks, cross-GPU boundary swaps every K PT iterations")
     ap.add_argument("--peaks", action="store_true", help="measure the FP64 peaks (DFMA, DMUL+DADD, DMMA) of cuda:0, print them as JSON and exit")
     args = ap.parse_args()
     if args.peaks:
@@ -222,252 +506,114 @@ def main():
     if args.save_every: w["save_every"] = args.save_every
     w.setdefault("save_every", 1)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    config = dict(workload="%s: %s" % (args.workload, w["desc"]), ladders_per_gpu=w["ladders"], rungs=w["rungs"], dim=w["dim"],
-                  chains_per_gpu=w["ladders"] * w["rungs"], pt_iterations_per_step=w["pt_steps"], save_every=w["save_every"], hist_capacity=w["hist"],
-                  swap_mode=args.swap_mode, rng="philox4x32-10", parallelism="ladders sharded, %d per GPU, no data-path collective" % w["ladders"],
-                  l2="history ring (%.1f GB per GPU) is larger than L2" % (w["ladders"] * w["rungs"] * w["hist"] * 8.0 * (w["dim"] + 2) / 1e9))
+    config = workload_config(args.workload, w, args.swap_mode)
     metric, unit = "tempered chain-steps/s", "chain-steps/s"
 
     if args.impl == "reference":
         if rank != 0:
             return 0
+        steps = args.steps or 5
         procs = cpu_threads()
         n_pt = reference_pt_steps(w, 6.0)
         for _ in range(min(args.warmup, 1)):
             run_reference_sample(w, max(20, n_pt // 10), procs)
-        tot, secs = 0, 0.0
-        for _ in range(args.steps):
-            t, dt, kind = run_reference_sample(w, n_pt, procs)
-            tot += t; secs += dt
+        tot, secs, ess_sum, ess_ok, kind = 0, 0.0, 0.0, True, "reference"
+        for _ in range(steps):
+            r = run_reference_sample(w, n_pt, procs, ess=True)
+            tot += r["chain_steps"]; secs += r["seconds"]; kind = r["kind"]
+            if r["ess"] is None: ess_ok = False
+            else: ess_sum += r["ess"]
         val = tot / secs
-        sample = "%d processes x 1 ladder x %d rungs x %d PT iterations per step" % (procs, w["rungs"], n_pt)
-        print(json.dumps(dict(metric=metric, value=val, unit=unit, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                              ms_per_step=1e3 * secs / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
-                              data="synthetic", impl="reference", config=config,
-                              cpu_baseline=dict(value=val, unit=unit, cores=procs, kind=kind, sample=sample),
-                              e2e=dict(value=val, unit=unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+        sample = "%d processes x 1 ladder x %d rungs x %d PT iterations per step (timed: the stepping loop, max over processes)" % (procs, w["rungs"], n_pt)
+        line = dict(metric=metric, value=val, unit=unit, n_gpus=args.gpus, steps=steps, warmup=args.warmup,
+                    ms_per_step=1e3 * secs / steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+                    data="synthetic", impl="reference", config=config,
+                    cpu_baseline=dict(value=val, unit=unit, cores=procs, kind=kind, sample=sample),
+                    e2e=dict(value=val, unit=unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        if ess_ok and ess_sum > 0:
+            line["ess"] = dict(value=ess_sum / secs, unit="ESS/s", estimator="chain::report_effective_samples of the reference itself on every process's cold chain (ref_trace ess=1), summed over processes and steps")
+            line["cpu_baseline"]["ess"] = line["ess"]
+        print(json.dumps(line))
         return 0
 
     import torch
     import torch.distributed as dist
-    from ptmcmc_b200 import _capi as K
-    from ptmcmc_b200.engine import Engine
-    from ptmcmc_b200.sharding import max_over_ranks, sum_over_ranks
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    def barrier():
-        if world > 1:
-            dist.barrier(device_ids=[local])
-
-    spec = make_spec(w)
-    L, R, d, S = w["ladders"], w["rungs"], w["dim"], w["pt_steps"]
     if args.rung_sharded:
-        # ---- optional rung-sharded layout (ptmcmc_b200/rung_sharding.py): the same ladders on every rank, a different rung block
-        from ptmcmc_b200.rung_sharding import RungShardedLadders, FusedRungShardedLadders, rank_betas
-        eng = Engine(spec.config(n_ladders=L, rng_mode=K.RNG_PHILOX, record_level=K.RECORD_BASIC, hist_capacity=w["hist"], save_every=w["save_every"], device=local,
-                                 seed=0xB2000003 + 977 * rank))
-        spec.setup(eng)
-        eng.set_betas(rank_betas(L, R, rank, world, spec.Tmax))
-        stream = torch.cuda.Stream()
-        eng.set_stream(stream.cuda_stream)
-        with torch.cuda.stream(stream):
-            eng.init_from_prior(); eng.synchronize()
-            if args.fused_exchange:
-                drv = FusedRungShardedLadders(eng, rank, world, 0xB2005EED, exchange_every=args.rung_sharded, in_launch=args.in_launch, max_launch=S)
-            else:
-                drv = RungShardedLadders(eng, rank, world, 0xB2005EED, exchange_every=args.rung_sharded, device="cuda:%d" % local, stream_ordered=True)
-            for _ in range(args.warmup):
-                drv.run(S)
-            eng.synchronize(); n0 = eng.get_total_steps()
-            barrier(); torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for _ in range(args.steps):
-                drv.run(S)
-            drv.finish()
-            eng.synchronize(); torch.cuda.synchronize(); barrier()
-            dt = time.perf_counter() - t0
-            n1 = eng.get_total_steps()
-            # the same launches without any exchange (what a cycle costs on its own), and the exchange step alone
-            torch.cuda.synchronize(); t1 = time.perf_counter()
-            for _ in range(100):
-                eng.step(args.rung_sharded)
-            eng.synchronize(); torch.cuda.synchronize(); bare_ms = 1e3 * (time.perf_counter() - t1) / 100
-            ex_ms = None
-            if not args.fused_exchange:
-                torch.cuda.synchronize(); t1 = time.perf_counter()
-                for _ in range(20):
-                    drv.exchange()
-                eng.synchronize(); torch.cuda.synchronize(); ex_ms = 1e3 * (time.perf_counter() - t1) / 20
-        val = sum_over_ranks(n1 - n0) / max_over_ranks(dt)
-        config["parallelism"] = "rung-sharded: %d ladders x (%d GPUs x %d rungs), boundary swaps %s every %d PT iterations" % (
-            L, world, R, ("fused into the step kernel over NVLink peer memory" + (", inside %d-iteration launches" % S if args.in_launch else ", one launch per exchange")) if args.fused_exchange else "over NCCL", args.rung_sharded)
-        ms_step = 1e3 * max_over_ranks(dt) / args.steps
+        steps = args.steps or 20
+        r = measure_rung_sharded(w, args.rung_sharded, steps, args.warmup, rank, world, local, fused=args.fused_exchange, in_launch=args.in_launch)
+        config["parallelism"] = "rung-sharded: " + r["layout"] + "; " + r["exchange"]
         if rank == 0:
-            print(json.dumps(dict(metric=metric, value=val, unit=unit, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_step,
-                                  higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", config=config,
-                                  exchange=dict(ms=ex_ms, ms_per_cycle=ms_step / ((S + args.rung_sharded - 1) // args.rung_sharded), ms_per_cycle_without_exchange=bare_ms,
-                                                bytes_per_rank=int((2 if 0 < rank < world - 1 else 1) * L * (d + 3) * 8),
-                                                collective="none: peer-memory loads in the step kernel's prologue, per-ladder flags" if args.fused_exchange else
-                                                "neighbour send/recv pairs (NCCL batch_isend_irecv), stream-ordered with the pack / swap kernels"),
-                                  gpu_launches=args.steps * ((S + args.rung_sharded - 1) // args.rung_sharded) * (1 if args.fused_exchange else 5))))
-        eng.close()
+            print(json.dumps(dict(metric=metric, value=r["value"], unit=unit, n_gpus=world, steps=steps, warmup=args.warmup, ms_per_step=r["ms_per_cycle"] * ((w["pt_steps"] + args.rung_sharded - 1) // args.rung_sharded),
+                                  higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", config=config, exchange=r, gpu_launches=r["gpu_launches"])))
         if world > 1:
             dist.destroy_process_group()
         return 0
-    swap_mode = K.SWAP_REFERENCE if args.swap_mode == "reference" else K.SWAP_EVEN_ODD
-    eng = Engine(spec.config(n_ladders=L, rng_mode=K.RNG_PHILOX, record_level=K.RECORD_BASIC, hist_capacity=w["hist"], save_every=w["save_every"], swap_mode=swap_mode,
-                             device=local, ladder_offset=rank * L, seed=0xB2000003))
-    spec.setup(eng)
-    stream = torch.cuda.Stream()
-    eng.set_stream(stream.cuda_stream)
-    eng.init_from_prior()
-    eng.synchronize()
 
-    # ---- device-resident throughput
-    with torch.cuda.stream(stream):
-        for _ in range(args.warmup):
-            eng.step(S)
-        eng.synchronize()
-        n0 = eng.get_total_steps()
-        clocks = ClockSampler(local); clocks.start()
-        barrier(); torch.cuda.synchronize()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record(stream)
-        for _ in range(args.steps):
-            eng.step(S)
-        ev1.record(stream)
-        torch.cuda.synchronize(); barrier()
-        ms = ev0.elapsed_time(ev1)
-        clk = clocks.stop()
-        eng.synchronize()
-        n1 = eng.get_total_steps()
-    ms_max = max_over_ranks(ms)
-    chain_steps = sum_over_ranks(n1 - n0)
-    value = chain_steps / (ms_max * 1e-3)
-
-    # ---- end to end through the C ABI with host buffers
-    n_chains = L * R
-    n_out = min(S, 64)
-    pin = lambda *shape: torch.empty(*shape, dtype=torch.float64).pin_memory().numpy()
-    hx, hlp, hll, hpr = pin(n_chains, d), pin(n_chains), pin(n_chains), pin(n_chains)
-    ox, olp, oll = pin(L, n_out, d), pin(L, n_out), pin(L, n_out)
-    cur = eng.get_current(); hx[:] = cur["x"]; hlp[:] = cur["lpost"]; hll[:] = cur["llike"]; hpr[:] = eng.get_lprior()
-    e2e_steps = max(3, min(args.steps, 10))
-    with torch.cuda.stream(stream):
-        for _ in range(2):
-            eng.set_current(hx, hlp, hll, hpr); eng.step_host(S, n_out, ox, olp, oll)
-        m0 = eng.get_total_steps()
-        barrier(); torch.cuda.synchronize()
-        t0 = time.perf_counter(); ev0.record(stream)
-        for _ in range(e2e_steps):
-            eng.set_current(hx, hlp, hll, hpr)
-            eng.step_host(S, n_out, ox, olp, oll)
-        ev1.record(stream); torch.cuda.synchronize(); barrier()
-        e2e_ms = max(ev0.elapsed_time(ev1), 1e3 * (time.perf_counter() - t0))
-        m1 = eng.get_total_steps()
-    e2e_val = sum_over_ranks(m1 - m0) / (max_over_ranks(e2e_ms) * 1e-3)
-    h2d = n_chains * (d + 3) * 8
-    d2h = L * n_out * (d + 2) * 8
-
-    # ---- ESS/s (second half of BASELINE.json's metric): integrated autocorrelation time of the cold chains over the newest
-    # history-ring window of a sample of ladders; ESS/s = (cold-chain steps per second over all ladders) / tau
-    ess = None
-    try:
-        from ptmcmc_b200.analysis import ess_per_sample
-        cnt = eng.get_counters()
-        nh = int(min(w["hist"] - 8, 2000, cnt["nsize"][::R].min()))      # never more than the cold chains have stored so far
-        tau_dev = eng.get_act(0, nh, min(nh // 2, 1000))                 # device: every ladder's cold chain, per parameter
-        eps_dev = float(np.mean(1.0 / tau_dev.max(axis=1)))              # ESS per stored sample, mean over ladders
-        nl = min(L, 256)                                                 # host cross-check on a sample of ladders (ACFs averaged, then windowed)
-        cold = np.stack([eng.get_history(l, 0, int(cnt["nsize"][l * R]) - nh, nh, full=False)["x"] for l in range(nl)])
-        eps_host, taus = ess_per_sample(cold)
-        pt_iter_per_s = args.steps * S / (ms_max * 1e-3)
-        # the reference's own estimator (chain::report_effective_samples as the run loop calls it, ptmcmc.cc:645) for EVERY ladder's cold
-        # chain over the newest ring window: lag statistics on the device in the reference's summation order
-        # (ptg_get_autocovar_windows), combination on the host; analysis.py restates the recipe and tests pin it to the reference build
-        nr = int(min(w["hist"] - 8, 8000, cnt["nsize"][::R].min()))
-        se = w["save_every"]
-        eps_recipe, n_recipe = None, 0
-        try:
-            ess_l, len_l = eng.report_effective_samples_all(rung=0, window_records=nr)
-            ok = len_l > 0
-            n_recipe = int(ok.sum())
-            if n_recipe:
-                eps_recipe = float(np.mean(ess_l[ok] / len_l[ok]))      # ESS per PT iteration, mean over ladders
-        except Exception as exc:
-            recipe_error = repr(exc)
-        sokal = eps_dev / w["save_every"] * pt_iter_per_s * L * world
-        ess = dict(value=(eps_recipe * pt_iter_per_s * L * world) if eps_recipe else sokal, unit="ESS/s",
-                   estimator=("the reference's chain::report_effective_samples(-1, 1000 save_every, save_every) (chain.cc:457-643) on every cold chain's newest "
-                              "%d records: lag statistics on the device (ptg_get_autocovar_windows), min over parameters, summed over ladders" % nr) if eps_recipe
-                   else "Sokal window (see sokal_device); the ring window is too short for the reference recipe",
-                   ess_per_pt_iteration=eps_recipe, ladders=L, ladders_with_estimate=n_recipe,
-                   sokal_device=dict(value=sokal, tau_pt_iterations=float(np.median(tau_dev.max(axis=1))) * w["save_every"], window=nh,
-                                     estimator="ptg_get_act: per cold chain N/tau, Sokal-windowed integrated autocorrelation time, min over parameters, mean over ladders"), host_check=dict(value=eps_host / w["save_every"] * pt_iter_per_s * L * world,
-                   tau_pt_iterations=float(taus.max()) * w["save_every"], ladders_sampled=nl))
-        if nh > int(cnt["nsize"][::R].min()) - eng.cfg.n_init:
-            ess["note"] = "the run is shorter than the analysis window: it still contains start-up prior draws, the ESS figure is not meaningful"
-    except Exception as exc:  # analysis is not part of the timed path
-        ess = dict(value=None, error=repr(exc))
-
-    # ---- roofline of the dominant kernel (ptg_step_kernel: one launch per bench step)
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    bpcs = algorithmic_bytes_per_chain_step(w)
-    launch_s = ms * 1e-3 / args.steps
-    achieved = bpcs * ((n1 - n0) / args.steps) / launch_s / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.workload)
-    if os.path.exists(tpath):
-        t = json.load(open(tpath))  # ncu capture of the same kernel at 100 PT iterations per launch, scaled to this launch
-        traffic = t["dram_bytes_per_pt_iteration"] * S * (L * R) / float(t.get("chains_profiled", 131072))
-    kernel_name = "ptg_xmstep_kernel" if d > 16 else ("ptg_fstep_kernel" if R <= 32 else "ptg_step_kernel")
-    roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic, kernel=kernel_name,
-                    algorithmic_bytes_per_chain_step=bpcs, chain_steps_per_launch=(n1 - n0) / args.steps, launch_ms=launch_s * 1e3, peak_source=peak_src,
-                    note="latency/ALU-bound fp64+Philox kernel: HBM is the stated roofline, see DESIGN.md section 5")
-
-    # compute-side view for the workloads with a dense fp64 flop count: algorithmic flops against the FP64 peaks measured by
-    # `bench.py --peaks` on this pool (profiles/r01_fp64_peaks.json; MEASURED_PEAKS.json carries HBM and bf16 only)
-    roofline_fp64 = None
-    fl = w.get("flops")
-    ppath = os.path.join(ROOT, "profiles", "r01_fp64_peaks.json")
-    if fl and os.path.exists(ppath):
-        pk = float(json.load(open(ppath))[fl["peak_key"]])
-        ach = fl["per_chain_step"] * ((n1 - n0) / args.steps) / launch_s / 1e12
-        roofline_fp64 = dict(bound="fp64", achieved=ach, peak=pk, unit="TFLOP/s", frac=ach / pk, flops_per_chain_step=fl["per_chain_step"],
-                             counted=fl["what"], peak_source="measured: profiles/r01_fp64_peaks.json " + fl["peak_key"])
-
-    out = dict(metric=metric, value=value, unit=unit, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_max / args.steps,
-               higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", config=config, clocks=clk,
-               e2e=dict(value=e2e_val, unit=unit, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=e2e_steps),
-               gpu_launches=args.steps, roofline=roofline, ess=ess)
-    if roofline_fp64:
-        out["roofline_fp64"] = roofline_fp64
+    # ---- the main workload
+    est_ms = dict(c1_sines=10.5, a_gauss=11.0, b_poly=1.3, c2_sinusoid=11.0, d_fullcov=16.0).get(args.workload, 10.0)
+    steps = args.steps or int(np.ceil(3000.0 / est_ms))
+    r = measure(args.workload, w, steps, args.warmup, rank, world, local, swap_mode=args.swap_mode, sustain_s=0.0 if args.no_extras else 3.0, with_ess=True)
+    out = dict(metric=metric, value=r["value"], unit=unit, n_gpus=world, steps=steps, warmup=args.warmup, ms_per_step=r["ms_per_step"],
+               higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", config=config, clocks=r["clocks"],
+               e2e=r["e2e"], gpu_launches=r["gpu_launches"], roofline=r["roofline"], ess=r.get("ess"))
+    for k in ("roofline_fp64", "sustained"):
+        if k in r:
+            out[k] = r[k]
     # ---- N > 1: the one collective of the ladder-sharded layout, the gather of cold-chain samples to rank 0 (off the hot path)
     if world > 1:
         from ptmcmc_b200.sharding import gather_cold_samples
-        local_t = torch.from_numpy(np.ascontiguousarray(ox)).cuda(local)
+        ox = r["_last_cold"]
+        local_t = torch.from_numpy(np.ascontiguousarray(ox[:, -64:, :])).cuda(local)
         torch.cuda.synchronize(); tg = time.perf_counter()
-        full = gather_cold_samples(local_t, L * world, device=torch.device("cuda", local))
+        full = gather_cold_samples(local_t, w["ladders"] * world, device=torch.device("cuda", local))
         torch.cuda.synchronize(); tg = time.perf_counter() - tg
         if rank == 0:
-            assert tuple(full.shape) == (L * world, n_out, d)
-            out["cold_gather"] = dict(ms=1e3 * tg, bytes=int(full.numel() * 8), backend="nccl", samples_per_ladder=n_out)
+            assert tuple(full.shape) == (w["ladders"] * world, local_t.shape[1], w["dim"])
+            out["cold_gather"] = dict(ms=1e3 * tg, bytes=int(full.numel() * 8), backend="nccl", samples_per_ladder=int(local_t.shape[1]))
+    if not args.no_extras:
+        torch.cuda.empty_cache()
+        if world == 1:
+            # BASELINE.json's other configs, short runs: value, e2e and both rooflines each
+            subs = {}
+            short = dict(a_gauss=30, b_poly=200, c2_sinusoid=30, d_fullcov=12)
+            for name in ("a_gauss", "b_poly", "c2_sinusoid", "d_fullcov"):
+                if name == args.workload:
+                    continue
+                ws = dict(WORKLOADS[name]); ws.setdefault("save_every", 1)
+                try:
+                    rr = measure(name, ws, short[name], 3, rank, world, local, e2e_steps=5)
+                    rr["config"] = workload_config(name, ws)
+                    subs[name] = brief(rr)
+                except Exception as exc:
+                    subs[name] = dict(error=repr(exc))
+                torch.cuda.empty_cache()
+            out["workloads"] = subs
+        else:
+            # BASELINE config 5: 65 536 chains per GPU (2048 ladders x 32 rungs), ladder-sharded and rung-sharded with cross-GPU swaps
+            w5 = dict(WORKLOADS["c1_sines"]); w5.setdefault("save_every", 1); w5["ladders"] = 2048
+            try:
+                r5 = measure("c1_sines", w5, 60, 3, rank, world, local, e2e_steps=5)
+                r5["config"] = workload_config("c1_sines", w5)
+                out["config5"] = brief(r5)
+            except Exception as exc:
+                out["config5"] = dict(error=repr(exc))
+            torch.cuda.empty_cache()
+            wr = dict(WORKLOADS["c1_sines"]); wr.setdefault("save_every", 1)
+            try:
+                out["rung_sharded"] = measure_rung_sharded(wr, 10, 10, 3, rank, world, local, fused=True)
+                wr5 = dict(wr); wr5["ladders"] = 2048
+                out["rung_sharded_config5"] = measure_rung_sharded(wr5, 10, 10, 3, rank, world, local, fused=True)
+            except Exception as exc:
+                out["rung_sharded"] = dict(error=repr(exc))
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        procs = cpu_threads()
-        n_pt = reference_pt_steps(w, 10.0)
-        tot, secs, kind = run_reference_sample(w, n_pt, procs)
-        out["cpu_baseline"] = dict(value=tot / secs, unit=unit, cores=procs, kind=kind,
-                                   sample="%d processes x 1 ladder x %d rungs x %d PT iterations of the same workload" % (procs, R, n_pt))
+        out["cpu_baseline"] = cpu_baseline(w, 10.0, cpu_threads(), unit)
     if rank == 0:
         print(json.dumps(out))
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

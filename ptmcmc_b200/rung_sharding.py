@@ -35,6 +35,23 @@ def rank_betas(n_ladders, rungs_per_rank, rank, world, Tmax):
     return np.tile(b, n_ladders)
 
 
+def rank_chain_seed(base_seed, rank):
+    """Philox key of rank `rank`'s chain streams.  Every rank numbers its ladders and LOCAL rungs identically, so with one shared key the
+    rung k of rank 0 and the rung k of rank 1 would consume identical streams: each rank steps its chains under its own key (the boundary
+    trials use the SHARED key given to the drivers)."""
+    return (int(base_seed) + 977 * int(rank)) & 0xFFFFFFFFFFFFFFFF
+
+
+def _check_distinct_chain_seeds(api, world, peers):
+    """the drivers refuse a family whose ranks share a chain key (correlated proposals across rung blocks)"""
+    if world <= 1 or peers is not None or not dist.is_initialized():
+        return
+    seeds = [None] * world
+    dist.all_gather_object(seeds, int(api.cfg.seed))
+    if len(set(seeds)) != world:
+        raise ValueError("rung-sharded ladders: every rank needs its own chain seed (use rank_chain_seed(base, rank)); got %r" % (seeds,))
+
+
 class RungShardedLadders:
     """Drives one rank's engine (anything with the C-ABI methods step / boundary_pack / boundary_swap) in the rung-sharded layout."""
 
@@ -43,6 +60,7 @@ class RungShardedLadders:
         `with torch.cuda.stream(...)`), so packs, the NCCL all_gather and the swap kernels are ordered on the device and the host
         never waits inside the loop.  Otherwise the host synchronises around the collective."""
         self.api, self.rank, self.world, self.shared_seed, self.exchange_every = api, rank, world, int(shared_seed), exchange_every
+        _check_distinct_chain_seeds(api, world, None)
         self.device = torch.device(device)
         self.stream_ordered = bool(stream_ordered) and self.device.type == "cuda"
         L, d = api.cfg.n_ladders, api.cfg.dim
@@ -104,6 +122,7 @@ class FusedRungShardedLadders:
         iterations (needs one rank per GPU and the whole grid resident); otherwise one launch per exchange."""
         self.api, self.rank, self.world, self.exchange_every = api, rank, world, exchange_every
         self.in_launch, self.max_launch = bool(in_launch), max(exchange_every, max_launch - max_launch % exchange_every)
+        _check_distinct_chain_seeds(api, world, peers)
         handle, ptr = api.xchg_export()
         if peers is None:
             handles = [None] * world
