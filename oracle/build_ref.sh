@@ -36,9 +36,20 @@ done
 for p in "${pids[@]}"; do wait "$p"; done
 rm -f "$OUT/libptmcmc_ref.a"
 ar rc "$OUT/libptmcmc_ref.a" "$OUT"/obj/*.o
+ENG="$HERE/../ptmcmc_b200/csrc"
 for d in "$HERE"/ref_drivers/*.cc; do
   [ -e "$d" ] || continue
   b="$(basename "${d%.cc}")"
+  if [ "$b" = "gpu_dropin" ]; then
+    # the reference-side binding of the engine compiled against the real reference headers (include/gpu_parallel_tempering_chains.hh) and
+    # linked with the engine's C ABI; needs the engine library to be built first
+    if [ -f "$ENG/libptmcmc_b200.so" ]; then
+      $CXX $CF -std=c++11 -fno-access-control -I"$HERE/../include" "$d" -o "$OUT/$b" "$OUT/libptmcmc_ref.a" -L"$ENG" -lptmcmc_b200 -Wl,-rpath,"\$ORIGIN/../../ptmcmc_b200/csrc"
+    else
+      echo "build_ref: skipping $b (ptmcmc_b200/csrc/libptmcmc_b200.so not built yet)" >&2
+    fi
+    continue
+  fi
   $CXX $CF -fno-access-control "$d" -o "$OUT/$b" "$OUT/libptmcmc_ref.a"
 done
 echo "build_ref: built $(ls "$OUT" | tr '\n' ' ')"

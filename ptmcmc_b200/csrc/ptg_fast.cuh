@@ -26,14 +26,14 @@ template <int D>
 struct FChain {
   double x[D];
   double llike, beta;
-  int slot, hfill, since_save;           // ring write position, min(nsize, capacity), nhist % save_every
 };
 // largest CTA the production kernel is launched with (28 warps = one CTA per SM at 72 registers); smaller batches use smaller CTAs
 #define PTG_FSTEP_MAX_THREADS 896
 // Launch-local per-thread words in shared memory ([thread][PTG_FC_STRIDE], odd stride: conflict-free): counters that change rarely
-// and the swap-trial draw this lane prepared for the next iteration
-enum { FC_XAPP = 0, FC_NSWAPPED, FC_NACCEPT, FC_LAST_TYPE, FC_UD, FC_SC, FC_RAW, FC_LOGU_LO, FC_LOGU_HI, FC_COUNT };
-#define PTG_FC_STRIDE 9
+// the swap-trial draw this lane prepared for the next iteration, and the chain's ring position (FC_SLOT write position, FC_HFILL = min(nsize,
+// capacity), FC_SSAVE = nhist % save_every) and packed replica direction / instance (FC_DI): read a few times per iteration, kept out of registers
+enum { FC_XAPP = 0, FC_NSWAPPED, FC_NACCEPT, FC_LAST_TYPE, FC_UD, FC_SC, FC_RAW, FC_LOGU_LO, FC_LOGU_HI, FC_SLOT, FC_HFILL, FC_SSAVE, FC_DI, FC_K0, FC_K1, FC_K2, FC_K3, FC_K4, FC_K5, FC_SS0, FC_PAD, FC_COUNT };
+#define PTG_FC_STRIDE 21
 static_assert(FC_COUNT == PTG_FC_STRIDE, "counter row");
 
 // proposal member parameters staged in shared memory
@@ -42,45 +42,51 @@ struct FProp {
   int kind, has_transform, sigma_off, trans_off;
 };
 
-// dynamic shared memory of a CTA of `threads` threads
+// Dynamic shared memory of a CTA.  Every offset is a compile-time constant of D (fixed-size tables first, then one block per warp), so an
+// address is `window base + constant (+ warp * W_BYTES) (+ lane * stride)`: with run-time offsets the compiler re-derived the bases
+// inside the step loop (~10 % of the issued instructions, profiles/README.md).
 template <int D>
 struct FShared {
   static constexpr int NPAIR = (D + 1) / 2;
-  double *bins;     // [R][NP]
-  double *map;      // [threads][3]         per thread: running MAP posterior, current lpost, current lprior (stride 3: conflict-free)
-  double *spar;     // [4 D]                streamlined sines functor: per dimension (min, width or 1/width, k pi, k)
-  double *lus;      // [warps][32]          swap phase: log u of the trial on pair c, handed to the lane of rung c
-  double *pool;     // [warps][2 NPAIR][32] round 1: normals of lane l at [j][l]; round 2 (aliased): [64] arguments / logarithms
-  FProp *prop;      // [NP]
-  int *cnt;         // [threads][PTG_FC_STRIDE]
-  unsigned char *items; // [warps][32 NPAIR]  Box-Muller work list: owner lane << 4 | pair
-  __host__ __device__ static size_t bytes(int threads, int R, int NP) {
-    size_t b = sizeof(double) * ((size_t)R * NP + 3 * (size_t)threads + 4 * D + threads + (size_t)(threads / 32) * 2 * NPAIR * 32) + sizeof(FProp) * NP + sizeof(int) * (size_t)threads * PTG_FC_STRIDE +
-               (size_t)(threads / 32) * 32 * NPAIR;
-    return (b + 15) & ~(size_t)15;
-  }
-  __device__ void carve(unsigned char *base, int threads, int R, int NP) {
-    bins = reinterpret_cast<double *>(base);
-    map = bins + R * NP;
-    spar = map + 3 * threads;
-    lus = spar + 4 * D;
-    pool = lus + threads;
-    prop = reinterpret_cast<FProp *>(pool + (size_t)(threads / 32) * 2 * NPAIR * 32);
-    cnt = reinterpret_cast<int *>(prop + NP);
-    items = reinterpret_cast<unsigned char *>(cnt + (size_t)threads * PTG_FC_STRIDE);
-  }
+  static constexpr int OFF_SPAR = 0;                                        // [4 D] doubles   streamlined sines functor: per dimension (min, width or 1/width, k pi, k)
+  static constexpr int OFF_PROP = OFF_SPAR + 8 * 4 * D;                     // [16] FProp      proposal members
+  static constexpr int OFF_BINS = OFF_PROP + (int)sizeof(FProp) * PTG_MAX_PROPOSALS; // [32][16] doubles bins[rung][member] (n_rungs <= 32)
+  static constexpr int OFF_WARP = OFF_BINS + 8 * 32 * PTG_MAX_PROPOSALS;    // per-warp blocks
+  static constexpr int W_MAP = 0;                                           // [32][3] doubles  per lane: running MAP posterior, current lpost, current lprior (stride 3: conflict-free)
+  static constexpr int W_CNT = W_MAP + 8 * 3 * 32;                          // [32][PTG_FC_STRIDE] ints  per lane: launch-local counters, prepared swap-trial draw, ring position
+  static constexpr int W_LUS = W_CNT + 4 * PTG_FC_STRIDE * 32;              // [32] doubles     swap phase: log u of the trial on pair c, handed to the lane of rung c
+  static constexpr int W_POOL = W_LUS + 8 * 32;                             // [2 NPAIR][32] doubles  round 1: normals of lane l at [j][l]; round 2 (aliased): [64] arguments / logarithms
+  static constexpr int W_ITEMS = W_POOL + 8 * 2 * NPAIR * 32;               // [32 NPAIR] bytes  Box-Muller work list: owner lane << 3 | pair
+  static constexpr int W_BYTES = (W_ITEMS + 32 * NPAIR + 15) & ~15;
+  __host__ __device__ static size_t bytes(int threads) { return (size_t)OFF_WARP + (size_t)(threads / 32) * W_BYTES; }
 };
 
 // ---- history ring access: x-records of PTG_HX(D) doubles (whole 32-byte sectors), (lpost, llike) pairs in their own ring
+// Ring traffic never re-uses a line soon (a record is read ~1.7 times in its life, thousands of iterations apart): it is marked
+// evict-first in L2 so that it does not push out what IS re-used every iteration (the step loop's local-memory lines, the tables).
 struct __align__(32) FRec4 { double a, b, c, d; };
+__device__ __forceinline__ uint64_t fring_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
 template <int D>
 __device__ __forceinline__ void fload_rec(const double *__restrict__ p, double v[D]) {
   constexpr int HX = PTG_HX(D);
+#ifndef PTG_F_NO_EVICT_FIRST
+  const uint64_t pol = fring_policy();
+#endif
 #pragma unroll
   for (int k = 0; k < HX; k += 4) {
     double a, b, c, d;
     // random records with no reuse: one 256-bit load per sector, not allocated in L1
+#if defined(PTG_F_PREFETCH_L1)
+    asm volatile("ld.global.L1::evict_first.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p + k), "l"(pol) : "memory");
+#elif !defined(PTG_F_NO_EVICT_FIRST)
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p + k), "l"(pol) : "memory");
+#else
     asm volatile("ld.global.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p + k) : "memory");
+#endif
     v[k] = a;
     if (k + 1 < D) v[k + 1] = b;
     if (k + 2 < D) v[k + 2] = c;
@@ -90,12 +96,27 @@ __device__ __forceinline__ void fload_rec(const double *__restrict__ p, double v
 template <int D>
 __device__ __forceinline__ void fstore_rec(double *__restrict__ p, const double v[D]) {
   constexpr int HX = PTG_HX(D);
+#ifndef PTG_F_NO_EVICT_FIRST
+  const uint64_t pol = fring_policy();
+#endif
 #pragma unroll
   for (int k = 0; k < HX; k += 4) {
-    FRec4 r;
-    r.a = v[k]; r.b = (k + 1 < D) ? v[k + 1] : 0.0; r.c = (k + 2 < D) ? v[k + 2] : 0.0; r.d = (k + 3 < D) ? v[k + 3] : 0.0;
+    const double b = (k + 1 < D) ? v[k + 1] : 0.0, c = (k + 2 < D) ? v[k + 2] : 0.0, d = (k + 3 < D) ? v[k + 3] : 0.0;
+#ifndef PTG_F_NO_EVICT_FIRST
+    asm volatile("st.global.L2::cache_hint.v4.f64 [%0], {%1,%2,%3,%4}, %5;" :: "l"(p + k), "d"(v[k]), "d"(b), "d"(c), "d"(d), "l"(pol) : "memory");
+#else
+    FRec4 r; r.a = v[k]; r.b = b; r.c = c; r.d = d;
     *reinterpret_cast<FRec4 *>(p + k) = r;
+#endif
   }
+}
+__device__ __forceinline__ void fstore_lp(double *__restrict__ p, double lpost, double llike) {
+#ifndef PTG_F_NO_EVICT_FIRST
+  const uint64_t pol = fring_policy();
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" :: "l"(p), "d"(lpost), "d"(llike), "l"(pol) : "memory");
+#else
+  *reinterpret_cast<double2 *>(p) = make_double2(lpost, llike);
+#endif
 }
 
 // MH_chain::add_state (chain.cc:916-949) of the chain's current state
@@ -107,26 +128,26 @@ __device__ __forceinline__ void fappend(const PtgModel &m, const PtgState &s, FC
 #pragma unroll
     for (int k = 0; k < D; k++) s.map_x[(long long)k * m.n_chains + chain] = ch.x[k];
   }
-  if (ch.since_save == 0) {
-    fstore_rec<D>(hbase + (long long)ch.slot * PTG_HX(D), ch.x);
-    const long long rec = chain * m.hist_cap + ch.slot;
-    *reinterpret_cast<double2 *>(s.hist_lp + 2 * rec) = make_double2(lpost, ch.llike);
+  if (cnt[FC_SSAVE] == 0) {
+    fstore_rec<D>(hbase + (long long)cnt[FC_SLOT] * PTG_HX(D), ch.x);
+    const long long rec = chain * m.hist_cap + cnt[FC_SLOT];
+    fstore_lp(s.hist_lp + 2 * rec, lpost, ch.llike);
     if (RECORD_FULL_POSSIBLE && m.record_full) {
       s.hist_acc[rec] = (s.naccept[chain] + cnt[FC_NACCEPT]) / (double)(s.ntries[chain] + n_mh_so_far);
       s.hist_beta[rec] = ch.beta;
       s.hist_type[rec] = cnt[FC_LAST_TYPE];
     }
-    if (ch.hfill < m.hist_cap) ch.hfill++;
-    ch.slot = (ch.slot + 1 == m.hist_cap) ? 0 : ch.slot + 1;
+    if (cnt[FC_HFILL] < m.hist_cap) cnt[FC_HFILL]++;
+    cnt[FC_SLOT] = (cnt[FC_SLOT] + 1 == m.hist_cap) ? 0 : cnt[FC_SLOT] + 1;
   }
-  ch.since_save = (ch.since_save + 1 == m.save_every) ? 0 : ch.since_save + 1;
+  cnt[FC_SSAVE] = (cnt[FC_SSAVE] + 1 == m.save_every) ? 0 : cnt[FC_SSAVE] + 1;
 }
 
 // element `index` of the eligible window (newest min(nsize,cap) samples): once the ring is full the oldest sits at `slot`
 template <int D>
-__device__ __forceinline__ int fslot(const PtgModel &m, const FChain<D> &ch, int index) {
+__device__ __forceinline__ int fslot(const PtgModel &m, const int *cnt, int index) {
   int p = index;
-  if (ch.hfill == m.hist_cap) { p = ch.slot + index; if (p >= m.hist_cap) p -= m.hist_cap; }
+  if (cnt[FC_HFILL] == m.hist_cap) { p = cnt[FC_SLOT] + index; if (p >= m.hist_cap) p -= m.hist_cap; }
   return p;
 }
 
@@ -333,16 +354,18 @@ __global__ void __launch_bounds__(MAXT, 1) ptg_fstep_kernel(const __grid_constan
 #define FS(expr, val) (SL ? (val) : (expr))
   constexpr int NPAIR = (D + 1) / 2;
   const int R = m.n_rungs, NP = m.n_props;
-  FShared<D> sh;
-  sh.carve(smem_raw, blockDim.x, R, NP);
-  for (int i = threadIdx.x; i < R * NP; i += blockDim.x) sh.bins[i] = m.bins[i];
+  typedef FShared<D> SH;
+  double *const sbins = reinterpret_cast<double *>(smem_raw + SH::OFF_BINS);      // [R][NP]
+  FProp *const sprop = reinterpret_cast<FProp *>(smem_raw + SH::OFF_PROP);
+  double *const spar = reinterpret_cast<double *>(smem_raw + SH::OFF_SPAR);
+  for (int i = threadIdx.x; i < R * NP; i += blockDim.x) sbins[i] = m.bins[i];
   for (int i = threadIdx.x; i < NP; i += blockDim.x) {
     const PtgProp &p = m.props[i];
     FProp q;
     q.snooker = p.snooker; q.g1frac = p.g1frac; q.gamma_std = p.gamma_std; q.reduce_gamma = p.reduce_gamma; q.ignore_frac = p.ignore_frac;
     q.unlikely_alpha = p.unlikely_alpha; q.one_d_frac = p.one_d_frac; q.kind = p.kind; q.has_transform = p.has_transform;
     q.sigma_off = p.sigma_off; q.trans_off = p.trans_off;
-    sh.prop[i] = q;
+    sprop[i] = q;
   }
   bool sines_pow2 = true; // every width of the sines surface is a power of two: x / w == x * (1 / w) exactly
   if (LK == PTG_LIKE_SINES) {
@@ -358,19 +381,19 @@ __global__ void __launch_bounds__(MAXT, 1) ptg_fstep_kernel(const __grid_constan
       const int i = threadIdx.x;
       const int k = (int)__ldg(P + 2 + i);
       const double mn = __ldg(P + 2 + D + i), w = __ldg(P + 2 + 2 * D + i) - mn;
-      sh.spar[4 * i] = mn; sh.spar[4 * i + 1] = sines_pow2 ? 1.0 / w : w; sh.spar[4 * i + 2] = k * PTG_PI; sh.spar[4 * i + 3] = (double)k;
+      spar[4 * i] = mn; spar[4 * i + 1] = sines_pow2 ? 1.0 / w : w; spar[4 * i + 2] = k * PTG_PI; spar[4 * i + 3] = (double)k;
     }
   }
   __syncthreads();
-  const FProp *sprop = sh.prop;
-  int *cnt = sh.cnt + threadIdx.x * PTG_FC_STRIDE;          // this thread's row
-  double *mapp = sh.map + 3 * threadIdx.x;                  // [0] running MAP, [1] current lpost, [2] current lprior
+  const int lane = threadIdx.x & 31;
+  unsigned char *const wblock = smem_raw + SH::OFF_WARP + (threadIdx.x >> 5) * SH::W_BYTES;     // this warp's block
+  double *const mapp = reinterpret_cast<double *>(wblock + SH::W_MAP) + 3 * lane;               // [0] running MAP, [1] current lpost, [2] current lprior
+  int *const cnt = reinterpret_cast<int *>(wblock + SH::W_CNT) + PTG_FC_STRIDE * lane;          // this thread's row
 #define LPOST (mapp[1])
 #define LPRIOR (mapp[2])
-  const int lane = threadIdx.x & 31;
-  double *wpool = sh.pool + (size_t)(threadIdx.x >> 5) * (2 * NPAIR * 32); // this warp's slots
-  double *wlus = sh.lus + (threadIdx.x & ~31);
-  unsigned char *witems = sh.items + (size_t)(threadIdx.x >> 5) * (32 * NPAIR);
+  double *const wlus = reinterpret_cast<double *>(wblock + SH::W_LUS);
+  double *const wpool = reinterpret_cast<double *>(wblock + SH::W_POOL);
+  unsigned char *const witems = wblock + SH::W_ITEMS;
 
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int gpw = 32 / W, g = lane / W, rung = lane - g * W;
@@ -387,20 +410,21 @@ __global__ void __launch_bounds__(MAXT, 1) ptg_fstep_kernel(const __grid_constan
 #define ladder_stream ((uint64_t)gl * PTG_STREAM_STRIDE + PTG_STREAM_LADDER)
 #define hbase (s.hist + chain * ((long long)m.hist_cap * PTG_HX(D)))
 #define step ((uint64_t)(step0 + it))
-  const double *bins = sh.bins + (rung < R ? rung : 0) * NP;
+  const double *bins = sbins + (rung < R ? rung : 0) * NP;
 
   FChain<D> ch;
-  int st_di = 1;
+#define st_di (cnt[FC_DI])
 #pragma unroll
   for (int k = 0; k < FC_COUNT; k++) cnt[k] = 0;
+  st_di = 1;
   if (active) {
 #pragma unroll
     for (int k = 0; k < D; k++) ch.x[k] = s.cur_x[(long long)k * m.n_chains + chain];
     LPOST = s.lpost[chain]; ch.llike = s.llike[chain]; LPRIOR = s.lprior[chain]; ch.beta = s.beta[chain];
     const long long nsize = s.nsize[chain];
-    ch.slot = (int)(nsize % m.hist_cap);
-    ch.hfill = (int)(nsize > m.hist_cap ? (long long)m.hist_cap : nsize);
-    ch.since_save = (int)(s.nhist[chain] % m.save_every);
+    cnt[FC_SLOT] = (int)(nsize % m.hist_cap);
+    cnt[FC_HFILL] = (int)(nsize > m.hist_cap ? (long long)m.hist_cap : nsize);
+    cnt[FC_SSAVE] = (int)(s.nhist[chain] % m.save_every);
     cnt[FC_LAST_TYPE] = s.last_type[chain];
     st_di = (s.directions[chain] + 1) | (s.instances[chain] << 2);
     mapp[0] = s.map_lpost[chain];
@@ -408,10 +432,10 @@ __global__ void __launch_bounds__(MAXT, 1) ptg_fstep_kernel(const __grid_constan
 #pragma unroll
     for (int k = 0; k < D; k++) ch.x[k] = 0;
     ch.llike = 0; ch.beta = 1;
-    ch.slot = 0; ch.hfill = 0; ch.since_save = 0;
+    cnt[FC_SLOT] = 0; cnt[FC_HFILL] = 0; cnt[FC_SSAVE] = 0;
     mapp[0] = 0; LPOST = 0; LPRIOR = 0;
   }
-  const int since_save0 = ch.since_save;
+  cnt[FC_SS0] = cnt[FC_SSAVE]; // nhist % save_every at the start of the launch
   int err = 0;
 
   // ================================================================= rung-sharded ladders: pending cross-GPU boundary swap
@@ -630,7 +654,7 @@ __global__ void __launch_bounds__(MAXT, 1) ptg_fstep_kernel(const __grid_constan
     int member = 0;
     if (FS(m.wrap_in_set, 1)) {
       const double x = (NP > 1) ? ptg_u32_to_unit(wA[0]) : 0.0;
-      if (ch.hfill >= D * 10 || !do_mh) { // every member ready (differential_evolution::is_ready, proposal_distribution.hh:407)
+      if (cnt[FC_HFILL] >= D * 10 || !do_mh) { // every member ready (differential_evolution::is_ready, proposal_distribution.hh:407)
         member = NP - 1;
         for (int i = NP - 2; i >= 0; i--) if (x < bins[i]) member = i;
       } else {
@@ -652,7 +676,7 @@ __global__ void __launch_bounds__(MAXT, 1) ptg_fstep_kernel(const __grid_constan
     bool snooker = false;
     int i1 = 0, i2 = 0, iz = 0, az = 0;
     if (is_de) {
-      const int hsize = ch.hfill;
+      const int hsize = cnt[FC_HFILL];
       int start = 0;
       if ((hsize - D * 100) * (1 - p.ignore_frac) > D * 10) start = (int)((hsize - D * 100) * p.ignore_frac);
       snooker = p.snooker > ptg_u32_to_unit(wA[1]);
@@ -665,18 +689,30 @@ __global__ void __launch_bounds__(MAXT, 1) ptg_fstep_kernel(const __grid_constan
       } else {
         const double mapl = mapp[0];
         const double *lpb = s.hist_lp + 2 * (chain * (long long)m.hist_cap);
-        if (snooker) { const int2 r = fde_index_slow<D>(m, ch.hfill, ch.slot, lpb, mapl, m.seed, my_stream, step, p.ignore_frac, p.unlikely_alpha, wB[1], 0, 0); iz = r.x; az = r.y; }
-        i1 = fde_index_slow<D>(m, ch.hfill, ch.slot, lpb, mapl, m.seed, my_stream, step, p.ignore_frac, p.unlikely_alpha, wA[3], 1, 0).x;
-        i2 = fde_index_slow<D>(m, ch.hfill, ch.slot, lpb, mapl, m.seed, my_stream, step, p.ignore_frac, p.unlikely_alpha, wB[0], 2, 0).x;
+        if (snooker) { const int2 r = fde_index_slow<D>(m, cnt[FC_HFILL], cnt[FC_SLOT], lpb, mapl, m.seed, my_stream, step, p.ignore_frac, p.unlikely_alpha, wB[1], 0, 0); iz = r.x; az = r.y; }
+        i1 = fde_index_slow<D>(m, cnt[FC_HFILL], cnt[FC_SLOT], lpb, mapl, m.seed, my_stream, step, p.ignore_frac, p.unlikely_alpha, wA[3], 1, 0).x;
+        i2 = fde_index_slow<D>(m, cnt[FC_HFILL], cnt[FC_SLOT], lpb, mapl, m.seed, my_stream, step, p.ignore_frac, p.unlikely_alpha, wB[0], 2, 0).x;
       }
-      i1 = fslot<D>(m, ch, i1); i2 = fslot<D>(m, ch, i2); // physical slots from here on
-#ifndef PTG_F_NO_PREFETCH
+      i1 = fslot<D>(m, cnt, i1); i2 = fslot<D>(m, cnt, i2); // physical slots from here on
+#if defined(PTG_F_PREFETCH_L1)
+      asm volatile("prefetch.global.L1 [%0];" :: "l"(hbase + (long long)i1 * PTG_HX(D)));
+      asm volatile("prefetch.global.L1 [%0];" :: "l"(hbase + (long long)i2 * PTG_HX(D)));
+      if (snooker) asm volatile("prefetch.global.L1 [%0];" :: "l"(hbase + (long long)fslot<D>(m, cnt, iz) * PTG_HX(D)));
+#elif !defined(PTG_F_NO_PREFETCH)
       asm volatile("prefetch.global.L2 [%0];" :: "l"(hbase + (long long)i1 * PTG_HX(D)));
       asm volatile("prefetch.global.L2 [%0];" :: "l"(hbase + (long long)i2 * PTG_HX(D)));
-      if (snooker) asm volatile("prefetch.global.L2 [%0];" :: "l"(hbase + (long long)fslot<D>(m, ch, iz) * PTG_HX(D)));
+      if (snooker) asm volatile("prefetch.global.L2 [%0];" :: "l"(hbase + (long long)fslot<D>(m, cnt, iz) * PTG_HX(D)));
 #endif
     }
 
+#ifndef PTG_F_NO_STASH
+    // values that are only needed again after pool round 1 wait in the thread's shared-memory row, not in registers (the round is the
+    // register-hungriest stretch of the iteration: Philox + log + sincospi)
+    {
+      volatile int *vk = cnt;
+      vk[FC_K0] = i1; vk[FC_K1] = i2; vk[FC_K2] = iz; vk[FC_K3] = (int)wA[2]; vk[FC_K4] = (int)wB[2]; vk[FC_K5] = (int)wB[3];
+    }
+#endif
     // ---- pool round 1: Box-Muller pairs of the Gaussian-member lanes + the next iteration's swap-trial draws
     // A Gaussian lane needs all NPAIR pairs, or -- for a single-axis step (proposal_distribution.hh:197-205) -- only the pair of its axis.
     const bool is_gauss = (kind == PTG_PROP_GAUSS);
@@ -737,6 +773,12 @@ __global__ void __launch_bounds__(MAXT, 1) ptg_fstep_kernel(const __grid_constan
       __syncwarp();
     }
 
+#ifndef PTG_F_NO_STASH
+    {
+      volatile int *vk = cnt;
+      i1 = vk[FC_K0]; i2 = vk[FC_K1]; iz = vk[FC_K2]; wA[2] = (uint32_t)vk[FC_K3]; wB[2] = (uint32_t)vk[FC_K4]; wB[3] = (uint32_t)vk[FC_K5];
+    }
+#endif
     // ---- Gaussian members: x' = x + M (z o sigma)  (proposal_distribution.hh:194-218)
 #pragma unroll
     for (int i = 0; i < D; i++) newx[i] = ch.x[i];
@@ -765,39 +807,51 @@ __global__ void __launch_bounds__(MAXT, 1) ptg_fstep_kernel(const __grid_constan
     double sn_a = 1, sn_b = 1; // arguments of the two snooker logarithms
     if (is_de) {
       const double ug = ptg_u32_to_unit(wA[2]);
-      double a[D], b[D];
-      fload_rec<D>(hbase + (long long)i1 * PTG_HX(D), a);
-      fload_rec<D>(hbase + (long long)i2 * PTG_HX(D), b);
+      // gamma of draw_standard (proposal_distribution.cc:495-499) or draw_snooker (:541-543); both proposals use the two products
+      // s1 * gamma and s2 * (-gamma), formed as soon as each record arrives
+      double gamma = p.gamma_std;
+      if (ug < p.g1frac) gamma = 1;
+      if (snooker) gamma = (1.2 + ug) / p.reduce_gamma;
+      double pa[D], pb[D];
+      {
+        double a[D];
+        fload_rec<D>(hbase + (long long)i1 * PTG_HX(D), a);
+#pragma unroll
+        for (int i = 0; i < D; i++) pa[i] = a[i] * gamma;
+      }
+      {
+        double b[D];
+        fload_rec<D>(hbase + (long long)i2 * PTG_HX(D), b);
+#pragma unroll
+        for (int i = 0; i < D; i++) pb[i] = b[i] * (-gamma);
+      }
       if (!snooker) {
         // draw_standard: prop = (s + gamma s1) + (-gamma s2); the jitter drawn by the reference is discarded (H8-1)
-        double gamma = p.gamma_std;
-        if (ug < p.g1frac) gamma = 1;
 #pragma unroll
         for (int i = 0; i < D; i++) {
-          const double t = ch.x[i] + a[i] * gamma;
-          newx[i] = t + b[i] * (-gamma);
+          const double t = ch.x[i] + pa[i];
+          newx[i] = t + pb[i];
         }
       } else {
         // draw_snooker (proposal_distribution.cc:538-591)
-        const double gamma = (1.2 + ug) / p.reduce_gamma;
         double smznorm2 = 0, minusz[D], smz[D];
         int isafe = 0;
         while (true) {
           double zz[D];
-          fload_rec<D>(hbase + (long long)fslot<D>(m, ch, iz) * PTG_HX(D), zz);
+          fload_rec<D>(hbase + (long long)fslot<D>(m, cnt, iz) * PTG_HX(D), zz);
           smznorm2 = 0;
 #pragma unroll
           for (int i = 0; i < D; i++) { minusz[i] = zz[i] * (-1); smz[i] = ch.x[i] + minusz[i]; }
 #pragma unroll
           for (int i = 0; i < D; i++) smznorm2 += smz[i] * smz[i];
           if (smznorm2 != 0 || ++isafe > 1000) break;
-          const int2 r = fde_index_slow<D>(m, ch.hfill, ch.slot, s.hist_lp + 2 * (chain * (long long)m.hist_cap), mapp[0], m.seed, my_stream, step, p.ignore_frac, p.unlikely_alpha, wB[1], 0, az);
+          const int2 r = fde_index_slow<D>(m, cnt[FC_HFILL], cnt[FC_SLOT], s.hist_lp + 2 * (chain * (long long)m.hist_cap), mapp[0], m.seed, my_stream, step, p.ignore_frac, p.unlikely_alpha, wB[1], 0, az);
           iz = r.x; az = r.y;
         }
         double dot = 0;
 #pragma unroll
         for (int i = 0; i < D; i++) {
-          const double ds12 = a[i] * gamma + b[i] * (-gamma);
+          const double ds12 = pa[i] + pb[i];
           dot += ds12 * smz[i];
         }
         const double fac = dot / smznorm2;
@@ -877,7 +931,7 @@ __global__ void __launch_bounds__(MAXT, 1) ptg_fstep_kernel(const __grid_constan
     // finite oldlprior, so with an all-uniform prior (every current state inside the box) the second clause never opens the gate
     const bool gate = valid && ((newlprior > -1e200) || FS(newlprior - (cur_lpost - ch.beta * ch.llike) > m.dprior_min, false));
     if (gate && do_mh) {
-      if constexpr (LK == PTG_LIKE_SINES) newlike = flike_sines_staged<D>(sh.spar, sines_pow2, m.lparams, newx);
+      if constexpr (LK == PTG_LIKE_SINES) newlike = flike_sines_staged<D>(spar, sines_pow2, m.lparams, newx);
       else newlike = flike<D, LK>(m, newx);
       newlpost = newlike * ch.beta + newlprior;
     } else code |= PTG_TRACE_NOLIKE;
@@ -927,6 +981,7 @@ __global__ void __launch_bounds__(MAXT, 1) ptg_fstep_kernel(const __grid_constan
     // appends of this launch: one per iteration + the extra ones (second trial of a step, boundary exchanges);
     // saves = appends k in [0, dnhist) with (since_save0 + k) % save_every == 0
     const int dnhist = n_steps + cnt[FC_XAPP], se = m.save_every;
+    const int since_save0 = cnt[FC_SS0];
     const int dnsize = (since_save0 + dnhist + se - 1) / se - (since_save0 + se - 1) / se;
     s.nhist[chain] += dnhist; s.nsize[chain] += dnsize; s.ntries[chain] += n_steps - cnt[FC_NSWAPPED]; s.naccept[chain] += cnt[FC_NACCEPT];
     s.last_type[chain] = cnt[FC_LAST_TYPE];
@@ -937,6 +992,7 @@ __global__ void __launch_bounds__(MAXT, 1) ptg_fstep_kernel(const __grid_constan
     if (err) atomicMax(s.err, err);
   }
 #undef FS
+#undef st_di
 #undef LPOST
 #undef LPRIOR
 }

@@ -61,7 +61,7 @@ static cudaError_t launch_fstep_t(const PtgModel &m, const PtgState &s, long lon
   const int threads = ptg_fstep_threads(warps);
   const int wpb = threads / 32;
   const int blocks = (int)((warps + wpb - 1) / wpb);
-  const size_t smem = FShared<D>::bytes(threads, m.n_rungs, m.n_props);
+  const size_t smem = FShared<D>::bytes(threads);
 #define GO(X, L, T) return launch_fstep_k<D, X, L, T>(m, s, step0, n_steps, W, xc, blocks, threads, smem, st)
   const bool small = threads <= 448; // at most 14 warps per SM: the 144-register instantiations
   if (xc.on && xc.every > 0) GO(2, -1, 896);
