@@ -44,11 +44,13 @@ WORKLOADS = {
                      desc="sines.hh sin^4 surface d=3, 4096 ladders x 32 rungs, default proposal mix (80% DE / 20% 6-scale Gaussian), swap_rate 0.1"),
     # configs[1] / B: polynomial chi^2, d=5, N=1000, DE only
     "b_poly": dict(model="poly", dim=5, rungs=16, ladders=1024, pt_steps=20, hist=1024, f_de=1.0, f_sn=0.1,
-                   flops=dict(per_chain_step=1000 * 26.0, peak_key="fp64_dmul_dadd_tflops", what="1000 points x (Horner 2(d-1) + residual 3 + division 15)"),
+                   flops=dict(per_chain_step=1000 * 12.0, peak_key="fp64_dfma_tflops", what="1000 points x (Horner on FMA 2(d-1) + residual 2 + weighted accumulate 2)"),
+                   limiter="fp64 pipe + L1 loads of the data block (warp-per-chain production functor, ptg_wide_mma.cuh)",
                    desc="5-coefficient polynomial chi^2 over 1000 points, 1024 ladders x 16 rungs, DE proposals"),
     # C2: 3-sinusoid chi^2 over 1e4 samples, d=9
     "c2_sinusoid": dict(model="sinusoid", dim=9, rungs=32, ladders=4096, pt_steps=1, hist=512, f_de=0.8, f_sn=0.1,
-                        flops=dict(per_chain_step=1e4 * 89.0, peak_key="fp64_dmul_dadd_tflops", what="1e4 samples x (3 sin at 24 flop + 17), SURVEY.md 8(d) convention"),
+                        flops=dict(per_chain_step=1e4 * 28.0, peak_key="fp64_dfma_tflops", what="1e4 samples x (3 components x (rotation 6 + amplitude 2) + residual 4): sin / cos advance by rotations on the uniform grid, re-anchored every 64 samples"),
+                        limiter="fp64 pipe (rotation recurrences of the sinusoid functor, ptg_wide_mma.cuh)",
                         desc="3-sinusoid chi^2 fit to 1e4 samples d=9, 4096 ladders x 32 rungs, default proposal mix"),
     # configs[3] / D: correlated Gaussian d=100, full covariance; "65536 chains x 24 rungs" read as 65 544 chains in total
     # (2731 ladders x 24 rungs; the 1.57 M-chain reading leaves < 100 history slots per chain in 180 GB, SURVEY.md 8d, and the

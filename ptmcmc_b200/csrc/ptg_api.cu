@@ -346,6 +346,15 @@ extern "C" int ptg_set_likelihood(ptg_handle *h, int32_t kind, const double *par
     int64_t N = n_data / 3; double nsum = 0;
     for (int64_t i = 0; i < N; i++) nsum += log(data[2 * N + i]);
     m.like_nsum = nsum;
+    // uniform abscissae (a sampled time series): the production sinusoid functor advances sin / cos by a rotation instead of calling
+    // libm at every sample (ptg_wide_mma.cuh)
+    m.like_uniform_t = 0; m.like_t0 = data[0]; m.like_dt = 0;
+    if (N >= 2) {
+      const double dt = (data[N - 1] - data[0]) / (double)(N - 1);
+      double worst = 0, scale = fabs(data[0]) > fabs(data[N - 1]) ? fabs(data[0]) : fabs(data[N - 1]);
+      for (int64_t i = 0; i < N; i++) { const double e = fabs(data[i] - (data[0] + (double)i * dt)); if (e > worst) worst = e; }
+      if (dt != 0 && worst <= 1e-13 * (scale > fabs(dt) ? scale : fabs(dt))) { m.like_uniform_t = 1; m.like_dt = dt; }
+    }
   }
   h->have_like = true;
   h->model_dirty = true;
@@ -688,7 +697,11 @@ static bool routes_warp_per_chain(const ptg_handle *h) {
   const bool data_like = m.like_kind == PTG_LIKE_POLY_CHI2 || m.like_kind == PTG_LIKE_SINUSOID_CHI2;
   bool has_prior_draw = false;
   for (const HostProp &hp : h->props) if (hp.p.kind == PTG_PROP_PRIOR_DRAW) has_prior_draw = true;
-  return !h->wide && data_like && !has_prior_draw && h->cfg.rng_mode == PTG_RNG_PHILOX && h->kernel_choice == PTG_KERNEL_AUTO && m.n_rungs <= 32 &&
+  // Since round 2 the thread-per-chain production kernel carries fused data functors (ptg_fast.cuh: ~220 fp64 instructions per chain-step
+  // for config B against the ~1000 instructions of per-chain machinery a whole warp spends here), so the warp-per-chain route is taken only
+  // on request (PTG_DATA_WARP_PER_CHAIN=1, experiments).
+  static const bool want = [] { const char *e = getenv("PTG_DATA_WARP_PER_CHAIN"); return e && atoi(e) != 0; }();
+  return want && !h->wide && data_like && !has_prior_draw && h->cfg.rng_mode == PTG_RNG_PHILOX && h->kernel_choice == PTG_KERNEL_AUTO && m.n_rungs <= 32 &&
          m.dim <= (m.like_kind == PTG_LIKE_POLY_CHI2 ? 16 : 18);
 }
 // The production kernel has streamlined instantiations (ptg_fast.cuh, LK >= 0) for the common production configuration; returns the
@@ -696,6 +709,9 @@ static bool routes_warp_per_chain(const ptg_handle *h) {
 static int fstep_streamlined_kind(const ptg_handle *h) {
   const PtgModel &m = h->m;
   if (h->kernel_choice == PTG_KERNEL_FAST_GENERAL) return -1;
+  // data chi-squared likelihoods: the production functors (fused multiply-adds, rotation recurrences) under automatic selection only;
+  // pinning PTG_KERNEL_FAST keeps the reference's unfused arithmetic (bit-identical with the tape-capable kernels)
+  if (m.like_kind == PTG_LIKE_POLY_CHI2 || m.like_kind == PTG_LIKE_SINUSOID_CHI2) return h->kernel_choice == PTG_KERNEL_AUTO ? m.like_kind : -1;
   if (m.like_kind != PTG_LIKE_SINES && m.like_kind != PTG_LIKE_GAUSS_ISO) return -1;
   if (m.swap_mode != PTG_SWAP_REFERENCE || m.evolve_rate > 0 || !m.wrap_in_set || m.record_full || m.trace_steps > 0) return -1;
   if (m.any_bound || !m.all_uniform_prior || !m.zero_valid) return -1;

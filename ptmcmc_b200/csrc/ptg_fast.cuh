@@ -240,10 +240,105 @@ __device__ __noinline__ FVec<D> ftransform(const double *__restrict__ M, FVec<D>
   return t;
 }
 
-// likelihood of the streamlined instantiations: the one functor, no switch (same expressions as like_eval, ptg_device.cuh)
+// ---- data chi-squared functors of the PRODUCTION instantiations (Philox runs under automatic kernel selection; bayesian.hh:595-622).
+// One thread evaluates its chain's whole data sum with explicit fused multiply-adds and four independent partial sums; the data block is
+// read with warp-uniform (broadcast) loads, 1/S_i is precomputed (ptg_api.cu).  The tape-capable kernels and the general instantiation
+// keep the reference's unfused arithmetic (like_eval_kind); these agree with it to ~1e-15 relative (1e-12 gate in the tests).
+//   polynomial (poly_example.cc:85-106): Horner's rule, D + 2 fp64 instructions per point
+template <int D>
+__device__ __forceinline__ double flike_poly_fused(const PtgModel &m, const double x[D]) {
+  const long long N = m.n_ldata / 3;
+  const double *__restrict__ xs = m.ldata, *__restrict__ ys = m.ldata + N, *__restrict__ iS = m.ldata + 3 * N;
+  // eight points per trip: all 24 loads are issued before the eight independent Horner chains start (a chain that runs alone on its
+  // scheduler -- config B puts one warp on each -- has nothing else to cover load and fp64 latency with)
+  double p4[4] = {0, 0, 0, 0};
+  long long i = 0;
+  for (; i + 8 <= N; i += 8) {
+    double xi[8], yi[8], wi[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) { xi[u] = __ldg(xs + i + u); yi[u] = __ldg(ys + i + u); wi[u] = __ldg(iS + i + u); }
+    double y[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) y[u] = x[D - 1];
+#pragma unroll
+    for (int j = D - 2; j >= 0; j--) {
+#pragma unroll
+      for (int u = 0; u < 8; u++) y[u] = fma(y[u], xi[u], x[j]);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) { const double dd = y[u] - yi[u]; p4[u & 3] = fma(dd * dd, wi[u], p4[u & 3]); }
+  }
+  for (; i < N; i++) {
+    const double xi = __ldg(xs + i);
+    double y = x[D - 1];
+#pragma unroll
+    for (int j = D - 2; j >= 0; j--) y = fma(y, xi, x[j]);
+    const double dd = y - __ldg(ys + i);
+    p4[0] = fma(dd * dd, __ldg(iS + i), p4[0]);
+  }
+  double sum = ((p4[0] + p4[1]) + (p4[2] + p4[3])) + m.like_nsum;
+  sum /= -2;
+  double result = sum - __ldg(m.lparams);
+  if (!isfinite(result)) result = -CUDART_INF;
+  return result;
+}
+//   sum of sinusoids y(t) = sum_k A_k sin(2 pi f_k t + phi_k): on a uniform time grid sin / cos of every component
+//   advance by one rotation per sample (4 fused multiply-adds) and are re-anchored with sincos of the reference's own phase expression
+//   every 128 samples (drift < 1e-13); an irregular grid evaluates sin at every sample
+template <int D>
+__device__ __forceinline__ double flike_sinusoid_fused(const PtgModel &m, const double x[D]) {
+  constexpr int NS = D / 3;
+  const long long N = m.n_ldata / 3;
+  const double *__restrict__ xs = m.ldata, *__restrict__ ys = m.ldata + N, *__restrict__ iS = m.ldata + 3 * N;
+  double part = 0;
+  if (m.like_uniform_t) {
+    double sd[NS > 0 ? NS : 1], cd[NS > 0 ? NS : 1];
+#pragma unroll
+    for (int k = 0; k < NS; k++) sincos(2 * PTG_PI * x[3 * k + 1] * m.like_dt, &sd[k], &cd[k]);
+    for (long long base = 0; base < N; base += 128) {
+      double sn[NS > 0 ? NS : 1], cs[NS > 0 ? NS : 1];
+      const double tb = __ldg(xs + base);
+#pragma unroll
+      for (int k = 0; k < NS; k++) sincos(2 * PTG_PI * x[3 * k + 1] * tb + x[3 * k + 2], &sn[k], &cs[k]);
+      const int nq = (int)((N - base) < 128 ? (N - base) : 128);
+#pragma unroll 2
+      for (int q = 0; q < nq; q++) {
+        double y = 0;
+#pragma unroll
+        for (int k = 0; k < NS; k++) y = fma(x[3 * k], sn[k], y);
+        const double dd = y - __ldg(ys + base + q);
+        part = fma(dd * dd, __ldg(iS + base + q), part);
+#pragma unroll
+        for (int k = 0; k < NS; k++) {
+          const double ns = fma(sn[k], cd[k], cs[k] * sd[k]);
+          const double nc = fma(cs[k], cd[k], -(sn[k] * sd[k]));
+          sn[k] = ns; cs[k] = nc;
+        }
+      }
+    }
+  } else {
+    for (long long i = 0; i < N; i++) {
+      const double ti = __ldg(xs + i);
+      double y = 0;
+#pragma unroll
+      for (int k = 0; k < NS; k++) y = fma(x[3 * k], sin(2 * PTG_PI * x[3 * k + 1] * ti + x[3 * k + 2]), y);
+      const double dd = y - __ldg(ys + i);
+      part = fma(dd * dd, __ldg(iS + i), part);
+    }
+  }
+  double sum = part + m.like_nsum;
+  sum /= -2;
+  double result = sum - __ldg(m.lparams);
+  if (!isfinite(result)) result = -CUDART_INF;
+  return result;
+}
+
+// likelihood of the specialised instantiations: the one functor, no switch
 template <int D, int LK>
 __device__ __forceinline__ double flike(const PtgModel &m, const double x[D]) {
   if constexpr (LK < 0) return like_eval<D>(m, x);
+  else if constexpr (LK == PTG_LIKE_POLY_CHI2) return flike_poly_fused<D>(m, x);
+  else if constexpr (LK == PTG_LIKE_SINUSOID_CHI2) return flike_sinusoid_fused<D>(m, x);
   else return like_eval_kind<D, LK>(m, x);
 }
 
@@ -350,7 +445,9 @@ __device__ __forceinline__ int fx_swap(const PtgModel &m, const PtgState &s, con
 template <int D, int XCHG, int LK, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) ptg_fstep_kernel(const __grid_constant__ PtgModel m, PtgState s, long long step0, int n_steps, int W, const __grid_constant__ PtgXchg xc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr bool SL = (LK >= 0);                 // streamlined: the FS(run-time expression, folded value) flags below are constants
+  // streamlined: the FS(run-time expression, folded value) flags below are constants.  The data chi-squared kinds only swap the functor
+  // (their evaluation dwarfs every flag test) and keep all features at run time.
+  constexpr bool SL = (LK >= 0) && LK != PTG_LIKE_POLY_CHI2 && LK != PTG_LIKE_SINUSOID_CHI2;
 #define FS(expr, val) (SL ? (val) : (expr))
   constexpr int NPAIR = (D + 1) / 2;
   const int R = m.n_rungs, NP = m.n_props;

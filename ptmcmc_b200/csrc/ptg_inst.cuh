@@ -58,7 +58,8 @@ static cudaError_t launch_fstep_t(const PtgModel &m, const PtgState &s, long lon
   // CTA size: the largest of 28 / 14 / 4 warps that still puts a CTA on (nearly) every SM.  The kernel is compiled for 72
   // registers (launch bound 896 x 1), so 896 resident threads per SM in every geometry; one 28-warp CTA per SM measured
   // 5 % faster than seven 4-warp CTAs on the 4096 x 32 workload.
-  const int threads = ptg_fstep_threads(warps);
+  int threads = ptg_fstep_threads(warps);
+  if ((lk == PTG_LIKE_POLY_CHI2 || lk == PTG_LIKE_SINUSOID_CHI2) && threads > 448) threads = 448; // the data-likelihood instantiations are compiled for <= 448 threads
   const int wpb = threads / 32;
   const int blocks = (int)((warps + wpb - 1) / wpb);
   const size_t smem = FShared<D>::bytes(threads);
@@ -68,6 +69,8 @@ static cudaError_t launch_fstep_t(const PtgModel &m, const PtgState &s, long lon
   if (xc.on) { if (lk == PTG_LIKE_SINES) { if (small) GO(1, PTG_LIKE_SINES, 448); GO(1, PTG_LIKE_SINES, 896); } GO(1, -1, 896); }
   if (lk == PTG_LIKE_SINES) { if (small) GO(0, PTG_LIKE_SINES, 448); GO(0, PTG_LIKE_SINES, 896); }
   if (lk == PTG_LIKE_GAUSS_ISO) { if (small) GO(0, PTG_LIKE_GAUSS_ISO, 448); GO(0, PTG_LIKE_GAUSS_ISO, 896); }
+  if constexpr (D >= 2) { if (lk == PTG_LIKE_POLY_CHI2) GO(0, PTG_LIKE_POLY_CHI2, 448); }       // fp64-bound: at most 14 warps per SM, the full register file
+  if constexpr (D % 3 == 0) { if (lk == PTG_LIKE_SINUSOID_CHI2) GO(0, PTG_LIKE_SINUSOID_CHI2, 448); }
   GO(0, -1, 896);
 #undef GO
 }

@@ -37,6 +37,8 @@ struct PtgModel {
   int64_t n_chains;
   double swap_rate, dprior_min, evolve_rate, evolve_lpost_cut;
   double like_nsum;
+  double like_t0, like_dt;    // data chi^2 likelihoods: abscissae are the uniform grid t0 + i dt (like_uniform_t), e.g. config C2's time samples
+  int32_t like_uniform_t, pad1;
   double uniform_lprior;      // log(prod 1/(b-a)) when every factor is uniform (evaluated once on the device)
   uint64_t seed;
   int64_t ladder_offset;

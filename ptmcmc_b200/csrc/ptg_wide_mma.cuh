@@ -183,8 +183,10 @@ __device__ __forceinline__ double xsum_tree(const double v[CPL]) {
 // DATA loop spread over the lanes of the chain's warp: lane l takes points l, l+32, ...; the partial sums meet in a shuffle
 // tree.  Used when the batch has too few chains to fill the GPU with one thread per chain (BASELINE config B: 16 384 chains).
 // dim <= 32 (CPL = 1): parameter j lives in lane j.
-// sum over this lane's points of (poly(x_i) - y_i)^2 / S_i for a polynomial with DD coefficients, the reference's Horner-free
-// evaluation order `y += xn*c_j; xn *= x_i` (poly_example.cc:97-101); four independent partial sums per lane; 1/S_i precomputed
+// sum over this lane's points of (poly(x_i) - y_i)^2 / S_i for a polynomial with DD coefficients; four independent partial sums per
+// lane; 1/S_i precomputed.  This is the PRODUCTION (Philox-only) functor: Horner's rule on explicit fused multiply-adds -- DD + 2 fp64
+// instructions per point instead of the 3 DD + 4 of the reference's unfused `y += xn*c_j; xn *= x_i` (poly_example.cc:97-101), which
+// the tape-capable kernels keep.  Values agree with the reference's order to ~1e-15 relative (tests: 1e-12 gate on stored samples).
 template <int DD>
 __device__ __forceinline__ double xpoly_partial(const double *__restrict__ xs, const double *__restrict__ ys, const double *__restrict__ iS, long long N, const double *cj, int lane) {
   double p4[4] = {0, 0, 0, 0};
@@ -194,15 +196,50 @@ __device__ __forceinline__ double xpoly_partial(const double *__restrict__ xs, c
       const long long i = i0 + 32 * u;
       if (i < N) {
         const double xi = __ldg(xs + i);
-        double y = 0, xn = 1;
+        double y = cj[DD - 1];
 #pragma unroll
-        for (int j = 0; j < DD; j++) { y += xn * cj[j]; xn *= xi; }
+        for (int j = DD - 2; j >= 0; j--) y = fma(y, xi, cj[j]);
         const double dd = y - __ldg(ys + i);
-        p4[u] += dd * dd * __ldg(iS + i);
+        p4[u] = fma(dd * dd, __ldg(iS + i), p4[u]);
       }
     }
   }
   return (p4[0] + p4[1]) + (p4[2] + p4[3]);
+}
+
+// sum over this lane's points of (sum_k A_k sin(2 pi f_k t_i + phi_k) - y_i)^2 / S_i on a UNIFORM time grid t_i = t0 + i dt: the lane's
+// points are 32 dt apart, so sin / cos of every component advance by a fixed rotation (4 fused multiply-adds) instead of a libm call;
+// they are re-anchored with sincos of the reference's own phase expression every 64 points, which bounds the drift to ~1e-14.
+template <int NS>
+__device__ __forceinline__ double xsinusoid_partial_uniform(const double *__restrict__ xs, const double *__restrict__ ys, const double *__restrict__ iS, long long N,
+                                                            double dt, const double *cj, int lane) {
+  double sd[NS], cd[NS];
+#pragma unroll
+  for (int k = 0; k < NS; k++) sincos(2 * PTG_PI * cj[3 * k + 1] * (32 * dt), &sd[k], &cd[k]);
+  double part = 0;
+  for (long long base = lane; base < N; base += 32 * 64) {
+    double sn[NS], cs[NS];
+    const double tb = __ldg(xs + base);
+#pragma unroll
+    for (int k = 0; k < NS; k++) sincos(2 * PTG_PI * cj[3 * k + 1] * tb + cj[3 * k + 2], &sn[k], &cs[k]);
+#pragma unroll 4
+    for (int q = 0; q < 64; q++) {
+      const long long i = base + 32 * q;
+      if (i >= N) break;
+      double y = 0;
+#pragma unroll
+      for (int k = 0; k < NS; k++) y = fma(cj[3 * k], sn[k], y);
+      const double dd = y - __ldg(ys + i);
+      part = fma(dd * dd, __ldg(iS + i), part);
+#pragma unroll
+      for (int k = 0; k < NS; k++) {
+        const double ns = fma(sn[k], cd[k], cs[k] * sd[k]);
+        const double nc = fma(cs[k], cd[k], -(sn[k] * sd[k]));
+        sn[k] = ns; cs[k] = nc;
+      }
+    }
+  }
+  return part;
 }
 
 __device__ __forceinline__ double xlike_data_parallel(const PtgModel &m, double xmine, int lane) {
@@ -225,13 +262,21 @@ __device__ __forceinline__ double xlike_data_parallel(const PtgModel &m, double 
     double cj[18];
 #pragma unroll
     for (int j = 0; j < 18; j++) cj[j] = __shfl_sync(0xffffffffu, xmine, j);
+    const double *__restrict__ iS = m.ldata + 3 * N;
+    if (m.like_uniform_t) {
+      switch (D / 3) {
+#define X(NS) case NS: part = xsinusoid_partial_uniform<NS>(xs, ys, iS, N, m.like_dt, cj, lane); break;
+        X(1) X(2) X(3) X(4) X(5) X(6)
+#undef X
+      }
+    } else
     for (long long i = lane; i < N; i += 32) {
       const double ti = __ldg(xs + i);
       double y = 0;
 #pragma unroll
       for (int k = 0; k + 2 < 18; k += 3) if (k + 2 < D) y += cj[k] * sin(2 * PTG_PI * cj[k + 1] * ti + cj[k + 2]);
       const double dd = y - __ldg(ys + i);
-      part += dd * dd * __ldg(m.ldata + 3 * N + i);
+      part += dd * dd * __ldg(iS + i);
     }
   }
 #pragma unroll

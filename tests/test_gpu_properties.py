@@ -188,6 +188,38 @@ def test_chi2_workload_is_invariant_to_batch_size(engine_cls):
     assert hb["x"].tobytes() == hp["x"].tobytes() and hb["llike"].tobytes() == hp["llike"].tobytes()
 
 
+@pytest.mark.parametrize("name", ["b_poly_N1000", "c2_sinusoid_N10000_uniform_grid", "c2_sinusoid_irregular_grid"])
+def test_production_chi2_functors_match_the_reference_arithmetic(name, engine_cls, oracle_cls):
+    """BASELINE configs B / C2 under automatic kernel selection run the warp-per-chain production functors (Horner on fused multiply-adds;
+    sin / cos advanced by rotations on a uniform time grid, ptg_wide_mma.cuh).  Every log-likelihood the chains STORED must equal the
+    reference's unfused arithmetic (the oracle's functor) at the stored position to 1e-12 relative -- BASELINE's bar for log-likelihoods"""
+    from tests.models import sinusoid_data
+    if name.startswith("b_poly"):
+        spec = Spec("poly", 5, 16, centers=np.zeros(5), halfwidths=np.full(5, 10.0), prop="de", Tmax=1e6, extra=poly_data())
+    else:
+        spec = sinusoid_spec(8, n=10000)
+        if "irregular" in name:
+            t = np.sort(np.random.default_rng(5).uniform(0, 10.0, 3000))
+            spec.extra.update(data_x=t, data_y=np.sin(2 * np.pi * 1.3 * t) + np.random.default_rng(6).normal(size=3000), data_dy=np.ones(3000))
+    L = 24
+    e = engine_cls(spec.config(n_ladders=L, rng_mode=K.RNG_PHILOX, hist_capacity=spec.de_ni * spec.dim + 400, record_level=K.RECORD_BASIC))
+    spec.setup(e); e.init_from_prior(); e.step(150); e.synchronize()
+    o = oracle_cls(spec.config(n_ladders=1)); spec.setup(o)
+    cnt = e.get_counters()
+    R = spec.rungs
+    worst = 0.0
+    for l, r in ((0, 0), (7, 3), (L - 1, R - 1)):
+        n = int(cnt["nsize"][l * R + r])
+        h = e.get_history(l, r, n - 120, 120, full=False)       # samples produced by the step kernel (not the start-up draws)
+        want = o.eval_loglike(h["x"])
+        fin = np.isfinite(want)
+        assert (np.isfinite(h["llike"]) == fin).all()
+        rel = np.abs(h["llike"][fin] - want[fin]) / np.abs(want[fin])
+        worst = max(worst, float(rel.max()))
+    print("%s: max relative deviation of stored log-likelihoods from the reference arithmetic: %.3g" % (name, worst))
+    assert worst < 1e-12
+
+
 def test_async_host_blocks_return_every_cold_sample(engine_cls):
     """ptg_step_host_begin / _wait: two blocks in flight, every cold sample of each block lands in its own host buffer"""
     spec = Spec("sines", 3, 8)
