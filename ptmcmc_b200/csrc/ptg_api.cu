@@ -504,10 +504,9 @@ static int upload_model(ptg_handle *h) {
   if (!h->have_prior || !h->have_like || !h->have_props) return fail(PTG_EINVAL, "set prior, likelihood and proposals before initialising");
   const int d = m.dim;
   if (h->wide) {
-    if (m.like_kind != PTG_LIKE_FLAT && m.like_kind != PTG_LIKE_GAUSS_ISO && m.like_kind != PTG_LIKE_GAUSS_FULLCOV)
-      return fail(PTG_EINVAL, "dim > 16: likelihood functors flat, gaussian and full-covariance gaussian are available");
-    for (const HostProp &hp : h->props)
-      if (hp.p.kind == PTG_PROP_PRIOR_DRAW) return fail(PTG_EINVAL, "dim > 16: the prior-draw proposal member is not available");
+    if (m.like_kind != PTG_LIKE_FLAT && m.like_kind != PTG_LIKE_GAUSS_ISO && m.like_kind != PTG_LIKE_GAUSS_FULLCOV && m.like_kind != PTG_LIKE_POLY_CHI2 &&
+        m.like_kind != PTG_LIKE_SINUSOID_CHI2)
+      return fail(PTG_EINVAL, "dim > 16: likelihood functors flat, gaussian, full-covariance gaussian and the data chi^2 models are available");
   }
   // proposals
   h->wide_trans_off = -1;
@@ -775,7 +774,10 @@ extern "C" int ptg_step(ptg_handle *h, int64_t n_steps) {
     if (warp_per_chain) e = ptg_launch_xmstep(m, h->s, h->istep, chunk, -1, h->stream);
     else if (h->wide) {
       // Philox runs take the DMMA-batched kernel; tape replay (and PTG_KERNEL_WARP) the exact-summation-order kernel
-      if (h->cfg.rng_mode == PTG_RNG_PHILOX && h->kernel_choice != PTG_KERNEL_WARP) e = ptg_launch_xmstep(m, h->s, h->istep, chunk, h->wide_trans_off, h->stream);
+      // (data chi^2 likelihoods and the prior-draw member exist in the exact-order kernel only)
+      bool exact_only = m.like_kind == PTG_LIKE_POLY_CHI2 || m.like_kind == PTG_LIKE_SINUSOID_CHI2;
+      for (const HostProp &hp : h->props) if (hp.p.kind == PTG_PROP_PRIOR_DRAW) exact_only = true;
+      if (h->cfg.rng_mode == PTG_RNG_PHILOX && h->kernel_choice != PTG_KERNEL_WARP && !exact_only) e = ptg_launch_xmstep(m, h->s, h->istep, chunk, h->wide_trans_off, h->stream);
       else e = ptg_launch_xstep(h->cfg.rng_mode, m, h->s, h->istep, chunk, h->stream);
     }
     else switch (m.dim) {

@@ -160,6 +160,36 @@ __device__ __forceinline__ double xlike(const PtgModel &m, const double x[CPL], 
     __syncwarp();
     const double r2 = xsum_ordered(rowA, D);
     result = __ldg(P) - r2 / __ldg(P + 1);
+  } else if (m.like_kind == PTG_LIKE_POLY_CHI2 || m.like_kind == PTG_LIKE_SINUSOID_CHI2) {
+    // chi^2 over data (bayesian.hh:595-622) in the reference's summation order: the lanes evaluate 32 consecutive points' terms in
+    // parallel (each term in the reference's own operation order), then every lane adds the 32 terms up in index order
+#pragma unroll
+    for (int k = 0; k < CPL; k++) { const int c = CPL * lane + k; if (c < D) rowA[c] = x[k]; }
+    __syncwarp();
+    const long long N = m.n_ldata / 3;
+    const double *__restrict__ xs = m.ldata, *__restrict__ ys = m.ldata + N, *__restrict__ S = m.ldata + 2 * N;
+    const bool poly = m.like_kind == PTG_LIKE_POLY_CHI2;
+    double sum = 0;
+    for (long long base = 0; base < N; base += 32) {
+      const long long i = base + lane;
+      double term = 0;
+      if (i < N) {
+        const double xi = __ldg(xs + i);
+        double y = 0;
+        if (poly) { double xn = 1; for (int j = 0; j < D; j++) { y += xn * rowA[j]; xn *= xi; } } // poly_example.cc:97-101
+        else for (int k = 0; k + 2 < D; k += 3) y += rowA[k] * sin(2 * PTG_PI * rowA[k + 1] * xi + rowA[k + 2]);
+        const double dd = y - __ldg(ys + i);
+        term = dd * dd / __ldg(S + i);
+      }
+      rowB[lane] = term;
+      __syncwarp();
+      const int nq = (int)((N - base) < 32 ? (N - base) : 32);
+      for (int q = 0; q < nq; q++) sum += rowB[q];
+      __syncwarp();
+    }
+    sum += m.like_nsum;
+    sum /= -2;
+    result = sum - __ldg(P);
   } else { // PTG_LIKE_GAUSS_FULLCOV, cython/exampleGaussian.py:103-109: y_i = sum_j C_ij x_j (j in order), q = sum_i x_i y_i (i in order)
     const double *__restrict__ C = m.ldata;
 #pragma unroll
@@ -398,6 +428,11 @@ __device__ __forceinline__ MhOut xmh_step(const PtgModel &m, const PtgState &s, 
       prop_lh = (log(pmz2) - log(smznorm2)) * (D - 1) / 2.0;
       type = 1;
     }
+  } else if (p.kind == PTG_PROP_PRIOR_DRAW) { // draw_from_dist::draw (proposal_distribution.hh:124-129)
+    valid = xprior_draw<CPL, MODE>(m, rs, PTG_BLK_PRIOR, newx, lane);
+    const double lp_old = xprior<CPL>(m, ch.x, true, rowA, lane);
+    prop_lh = lp_old - xprior<CPL>(m, newx, valid, rowA, lane);
+    type = 0;
   } else { // PTG_PROP_GAUSS (gaussian_prop::draw, proposal_distribution.hh:194-218)
     double off[CPL];
     xnormals<CPL, MODE>(m, rs, off, lane);

@@ -148,4 +148,30 @@ def wide_cases():
         ("W_gauss_d24_gaussprior_de", Spec("gauss", 24, 4, centers=np.zeros(24), halfwidths=np.full(24, 2.0), prior="gaussian", prop="de",
                                            Tmax=100, extra=dict(sigma=1.0, de_unlikely_alpha=0.3), de_ni=12), 200, 1),
         ("W_D_fullcov_d100_R24_cov1d", d1, 60, 1),
+        # the data chi^2 likelihoods and the prior-draw member above 16 dimensions (exact-summation-order kernel)
+        ("W_poly_d18", Spec("poly", 18, 4, centers=np.zeros(18), halfwidths=np.full(18, 5.0), prop="de", Tmax=1e4, de_ni=12, seed=0.35,
+                            extra=wide_poly_data()), 120, 1),
+        ("W_sinusoid_d18", wide_sinusoid_spec(4), 100, 1),
+        ("W_prior_draw_d20_mixed", Spec("gauss", 20, 4, centers=np.linspace(-1, 1, 20), halfwidths=np.full(20, 2.0), prior="mixed", prop="prior",
+                                        prior_types=[1, 2] * 10, Tmax=100, de_ni=12, seed=0.71, extra=dict(sigma=1.2)), 200, 1),
     ]
+
+
+def wide_poly_data(n=203, d=18, seed=11):
+    """a degree-17 polynomial on [-1, 1] (203 points: a ragged last group of the 32-point rounds)"""
+    rng = np.random.default_rng(seed)
+    xs = np.linspace(-1, 1, n)
+    truth = rng.uniform(-3, 3, d)
+    ys = sum(truth[j] * xs ** j for j in range(d)) + rng.normal(size=n)
+    return dict(data_x=xs, data_y=ys, data_dy=np.full(n, 0.8))
+
+
+def wide_sinusoid_spec(rungs, n=150, dt=0.02):
+    """six sinusoids (d = 18) on a short series"""
+    rng = np.random.default_rng(13)
+    t = np.arange(n) * dt
+    A, f, ph = rng.uniform(0.3, 1.5, 6), rng.uniform(0.5, 8, 6), rng.uniform(0, 2 * np.pi, 6)
+    y = sum(A[k] * np.sin(2 * np.pi * f[k] * t + ph[k]) for k in range(6)) + rng.normal(size=n)
+    c = np.array([1, 5, np.pi] * 6, dtype=float)
+    return Spec("sinusoid", 18, rungs, centers=c, halfwidths=c.copy(), bound="oow" * 6, de_ni=12, seed=0.19,
+                extra=dict(data_x=t, data_y=y, data_dy=np.ones(n)))
