@@ -48,7 +48,10 @@ extern "C" {
 /* boundary types: states.hh:35-38 */
 enum { PTG_BOUND_OPEN = 0, PTG_BOUND_LIMIT = 1, PTG_BOUND_REFLECT = 2, PTG_BOUND_WRAP = 3 };
 /* 1-D prior factor types: mixed_dist_product, probability_function.hh:151-155 */
-enum { PTG_PRIOR_UNIFORM = 1, PTG_PRIOR_GAUSSIAN = 2, PTG_PRIOR_POLAR = 3, PTG_PRIOR_COPOLAR = 4, PTG_PRIOR_LOG = 5 };
+enum { PTG_PRIOR_UNIFORM = 1, PTG_PRIOR_GAUSSIAN = 2, PTG_PRIOR_POLAR = 3, PTG_PRIOR_COPOLAR = 4, PTG_PRIOR_LOG = 5,
+       /* a Gaussian factor of gaussian_dist_product(..., wrap_probability = true) (probability_function.cc:57-78): on a dimension whose
+        * boundary wraps, the pdf sums the images x +- k (xmax - xmin) until a pair of images adds less than 1e-12 (at most 100 pairs) */
+       PTG_PRIOR_GAUSSIAN_WRAPPED = 6 };
 /* device likelihood functors */
 enum {
   PTG_LIKE_FLAT = 0,          /* log L = 0                                  (example.cc:22-72 "constant") */
@@ -144,6 +147,21 @@ int ptg_register_evaluate_log(ptg_handle *h, ptg_batch_loglike_fn fn, void *user
  * single proposal bare, as ptmcmc drivers do when they pass e.g. a differential_evolution directly to
  * set_proposal (testMH.cpp:91-160): no selection draw, type() not multiplied by 10. */
 int ptg_set_proposals(ptg_handle *h, int32_t n, const ptg_proposal *props, double Tpow, int32_t wrap_in_set);
+/* Options of the proposal objects beyond their constructors (call after ptg_set_proposals, before initialising):
+ *   adapt_rate  != 0: the adaptive shares of proposal_distribution_set (proposal_distribution.cc:132-166; ptmcmc's prop_adapt_rate with
+ *               prop_adapt_more): every chain owns its copy of the shares; two accepts or two rejects in a row of member i scale
+ *               shares[i] by 1 - adapt_rate / 4, and from the (10 n)-th decision on reset_bins renormalises after every decision.
+ *               Needs a set (wrap_in_set = 1).
+ *   de_mixing   != 0: differential_evolution::support_mixing(true) on a BARE differential-evolution proposal (wrap_in_set = 0) of a
+ *               ladder: every history draw first weighs the rungs by 10 + 10 log-likelihood samples of each (draw_from_chain,
+ *               proposal_distribution.cc:594-741) and then draws from the chosen rung's history.  Inside a set the reference never
+ *               mixes (proposal_distribution_set does not override support_mixing(), chain.cc:1375), so the flag is refused there.
+ *               Needs unlikely_alpha = 0, dim <= 16, n_rungs <= 32.
+ *   de_Tmix     temperature_mixing_factor (mix_temperatures_more, proposal_distribution.hh:403; ptmcmc's de_Tmix).
+ * Both run in the tape-capable warp kernel (PTG_KERNEL_WARP) in either RNG mode. */
+int ptg_set_proposal_options(ptg_handle *h, double adapt_rate, int32_t de_mixing, double de_Tmix);
+/* the current shares of every chain's proposal set, shares[n_chains][n_props] (proposal_distribution_set::report(1)) */
+int ptg_get_proposal_shares(ptg_handle *h, double *shares);
 /* explicit inverse temperatures instead of the geometric ladder; [n_ladders*n_rungs] or NULL */
 int ptg_set_betas(ptg_handle *h, const double *betas);
 

@@ -40,6 +40,8 @@
 #define PTG_BLK_NORMAL 0x100  /* + j/2 : Box-Muller pair -> normals j, j+1 ; (w0,w1)=u_a (w2,w3)=u_b      (u52) */
 #define PTG_BLK_RETRY 0x200   /* + which*0x100 + a : DE index attempt a>=1 (w0) and unlikely-alpha test (w1) (u32) */
 #define PTG_BLK_PRIOR 0x600   /* + i : prior draw of dimension i; (w0,w1)=u (w2,w3)=u_b for Gaussian dims  (u52) */
+#define PTG_BLK_MIX 0x10000   /* + which*0x1000 + k/4, word k%4 : k-th uniform of the temperature-mixing history draw `which`
+                                 (draw_from_chain with support_mixing: 20 n_rungs + 2 uniforms, in the reference's order)   (u32) */
 /* blocks of a ladder's stream within one PT step: trial j -> w0 u_try, w1 u_pair (u32), (w2,w3) u_swap (u52) */
 #define PTG_BLK_SWAP_EVENODD 0x100 /* + lower rung : (w0,w1) u_try, (w2,w3) u_swap                           (u52) */
 /* initialisation (domain 1): block = attempt*0x100 + i, same word use as PTG_BLK_PRIOR */

@@ -59,6 +59,9 @@ typedef struct {
   int64_t hcap;
   stream_t rng;
   double *bin_max;
+  /* adaptive shares (proposal_distribution.hh:313-318): this rung's clone of the set owns them */
+  double *shares; int *last_accepted; int adapt_count;
+  int64_t frozen;   /* history_freeze (chain.cc:1552, chain.hh:86): the size other chains see during the MH phase of a PT step */
 } chain_t;
 
 struct pto_handle {
@@ -72,6 +75,7 @@ struct pto_handle {
   prior1d_t prior[PTG_MAX_DIM];
   int like_kind; double *lparams; int n_lparams; double *ldata; int64_t n_ldata; double like_nsum;
   int nprops; prop_t props[PTG_MAX_PROPOSALS]; double Tpow; int wrap_in_set;
+  double adapt_rate; int de_mixing; double de_Tmix; double hot_norm[PTG_MAX_PROPOSALS];
   double *betas0; /* optional explicit */
   chain_t *chains;
   stream_t *lstreams;
@@ -192,7 +196,8 @@ static double pdf1d(const prior1d_t *p, double x) {
     if (x < p->a) return 0;
     if (x > p->b) return 0;
     return 1 / (p->b - p->a);
-  case PTG_PRIOR_GAUSSIAN: {
+  case PTG_PRIOR_GAUSSIAN:
+  case PTG_PRIOR_GAUSSIAN_WRAPPED: {
     double xnorm = (x - p->a) / p->b;
     return exp(-xnorm * xnorm / 2) / sqrt(2 * M_PI) / p->b;
   }
@@ -226,7 +231,24 @@ static double invcdf1d(const prior1d_t *p, double u) {
 static double prior_eval_log(const pto_handle *h, const double *x, int valid) {
   if (!valid) return log(0.0);
   double result = 1;
-  for (int i = 0; i < h->d; i++) result *= pdf1d(&h->prior[i], x[i]);
+  for (int i = 0; i < h->d; i++) {
+    double resulti = pdf1d(&h->prior[i], x[i]);
+    if (h->prior[i].kind == PTG_PRIOR_GAUSSIAN_WRAPPED && h->lower[i] == PTG_BOUND_WRAP && h->upper[i] == PTG_BOUND_WRAP) {
+      /* gaussian_dist_product::evaluate with wrap_probability (probability_function.cc:57-78): add the images of a wrapped dimension */
+      const double tol = 1e-12;
+      double xplus = x[i], xminus = x[i], delta = 1;
+      double width = h->xmax[i] - h->xmin[i];
+      int count = 0;
+      while (delta > tol && count < 100) {
+        xplus += width;
+        xminus -= width;
+        delta = pdf1d(&h->prior[i], xminus) + pdf1d(&h->prior[i], xplus);
+        resulti += delta;
+        count++;
+      }
+    }
+    result *= resulti;
+  }
   return log(result);
 }
 /* drawSample (probability_function.cc:37-47,147-154,264-279) + ProbabilityDist::draw (ProbabilityDist.cxx:33-59)
@@ -234,7 +256,7 @@ static double prior_eval_log(const pto_handle *h, const double *x, int valid) {
 static int prior_draw(pto_handle *h, stream_t *s, int domain, uint64_t step, uint32_t blk0, double *x) {
   for (int i = 0; i < h->d; i++) {
     const prior1d_t *p = &h->prior[i];
-    if (p->kind == PTG_PRIOR_GAUSSIAN) {
+    if (p->kind == PTG_PRIOR_GAUSSIAN || p->kind == PTG_PRIOR_GAUSSIAN_WRAPPED) {
       double z;
       if (is_philox(s)) {
         double z1; philox_normal_pair(h, s, domain, step, blk0 + i, &z, &z1);
@@ -385,7 +407,7 @@ static void add_state(pto_handle *h, chain_t *c, const double *x, double llike, 
 }
 
 /* ---------------------------------------------------------------------------------------------- proposals */
-typedef struct { int type; double log_hastings; int valid; } draw_result_t;
+typedef struct { int type; double log_hastings; int valid; int member; } draw_result_t;
 
 /* differential_evolution::draw_i_from_chain (proposal_distribution.cc:744-778); `size` is the frozen chain
  * size (chain.hh:86); with a ring of capacity C only the newest min(size,C) samples are eligible. */
@@ -412,6 +434,94 @@ static int64_t de_draw_index(pto_handle *h, chain_t *c, const prop_t *p, uint64_
   }
 }
 
+
+/* ---- temperature mixing: differential_evolution::draw_from_chain with support_mixing (proposal_distribution.cc:594-741) ----
+ * Reached when a BARE differential_evolution with support_mixing(true) is handed to parallel_tempering_chains::set_proposal
+ * (chain.cc:1375-1379: set_chain(this), so ch = the ladder and multiplicity() = Ntemps).  unlikely_alpha = 0 is required, so
+ * draw_i_from_chain consumes exactly one uniform.  Sizes are the FROZEN sizes (history_freeze, chain.cc:1552). */
+static double mix_u(pto_handle *h, chain_t *caller, uint64_t step, int which, int *k) {
+  const int kk = (*k)++;
+  return draw_u32(h, &caller->rng, PTG_DOMAIN_STEP, step, PTG_BLK_MIX + (uint32_t)which * 0x1000u + (uint32_t)(kk >> 2), kk & 3);
+}
+/* draw_i_from_chain(caller, c) (proposal_distribution.cc:744-778): window index into c's frozen history */
+static int mix_draw_i(pto_handle *h, chain_t *caller, const chain_t *c, const prop_t *p, uint64_t step, int which, int *k) {
+  int64_t W = c->frozen;
+  if (h->cfg.hist_capacity > 0 && W > h->cfg.hist_capacity) W = h->cfg.hist_capacity;
+  int size = (int)W, start = 0, mins = h->d * 10, minc = h->d * 100;
+  if ((size - minc) * (1 - p->ignore_frac) > mins) start = (int)((size - minc) * p->ignore_frac);
+  double xrnd = mix_u(h, caller, step, which, k);
+  return (int)(start + (size - start) * xrnd);
+}
+static int64_t win_base(const pto_handle *h, int64_t nsz) {
+  return (h->cfg.hist_capacity > 0 && nsz > h->cfg.hist_capacity) ? nsz - h->cfg.hist_capacity : 0;
+}
+/* MH_chain::getLogLike(index, true) (chain.cc:1078-1085): beyond the chain's own size it is the current value */
+static double mix_llike_at(const pto_handle *h, const chain_t *c, int64_t nsz, int index) {
+  int64_t base = win_base(h, nsz);
+  if (index < 0 || index >= nsz - base) return c->llike;
+  return c->hllike[base + index];
+}
+static const double *de_draw_state_mixed(pto_handle *h, chain_t *caller, const prop_t *p, uint64_t step, int which, int *kcount) {
+  const int R = h->R;
+  chain_t *lad = h->chains + ((size_t)(caller - h->chains) / R) * R;
+  enum { Nmean = 10, Nmedian = 10 };
+  const double pmix = h->de_Tmix;
+  double k[PTG_MAX_RUNGS + 1], l0[Nmean], l[Nmedian];
+  int kd = *kcount, index, guard = 0; /* the uniform counter runs on across the snooker's redraws of z */
+  double beta = caller->beta;
+  k[0] = 0;
+  int ithis = 0;
+  for (int i = 0; i < R; i++) {
+    chain_t *ci = &lad[i];
+    double l0max = -1e100, l0min = 1e100;
+    for (int j = 0; j < Nmean; j++) {
+      index = mix_draw_i(h, caller, ci, p, step, which, &kd);
+      double dl = mix_llike_at(h, caller, caller->nsize, index);
+      if (isfinite(dl)) {
+        if (dl > l0max) l0max = dl;
+        if (dl < l0min) l0min = dl;
+        l0[j] = dl;
+      } else { j--; if (++guard > 100000) { h->tape_err = 1; *kcount = kd; return caller->x; } }
+    }
+    double alpha = ci->beta, amb = alpha - beta;
+    amb = -amb;
+    if (amb == 0) ithis = i;
+    double sum = 0;
+    double l0scale = amb < 0 ? l0min : l0max;
+    for (int ii = 0; ii < Nmean; ii++) sum += exp((l0[ii] - l0scale) * amb);
+    double ll0 = log(sum / Nmean) + l0scale * amb;
+    for (int j = 0; j < Nmedian; j++) {
+      index = mix_draw_i(h, caller, ci, p, step, which, &kd);
+      l[j] = mix_llike_at(h, ci, ci->frozen, index);
+    }
+    for (int a = 1; a < Nmedian; a++) { /* sort(l.begin(), l.end()) */
+      double v = l[a]; int b = a - 1;
+      while (b >= 0 && l[b] > v) { l[b + 1] = l[b]; b--; }
+      l[b + 1] = v;
+    }
+    double ll = l[(int)Nmedian / 2];
+    double lk = ll0 - ll * amb;
+    lk = -lk;
+    lk /= pmix;
+    if (lk > 0) lk = 0;
+    k[i + 1] = k[i] + exp(lk);
+  }
+  int ipick = ithis;
+  double xrnd = mix_u(h, caller, step, which, &kd) * k[R];
+  for (int i = 0; i < R; i++)
+    if (xrnd <= k[i + 1]) { ipick = i; break; }
+  chain_t *ci = &lad[ipick];
+  index = mix_draw_i(h, caller, ci, p, step, which, &kd);
+  *kcount = kd;
+  return ci->hx + (size_t)(win_base(h, ci->frozen) + index) * h->d;
+}
+static int de_mixing_on(const pto_handle *h) { return h->de_mixing && !h->wrap_in_set && h->R > 1; }
+/* draw_from_chain: the state a DE proposal reads for `which` (0 = z, 1 = s1, 2 = s2) */
+static const double *de_draw_state(pto_handle *h, chain_t *c, const prop_t *p, uint64_t step, int which, int *attempt) {
+  if (de_mixing_on(h)) return de_draw_state_mixed(h, c, p, step, which, attempt);
+  return c->hx + (size_t)de_draw_index(h, c, p, step, which, attempt) * h->d;
+}
+
 /* differential_evolution::draw_standard (proposal_distribution.cc:489-535) */
 static void de_draw_standard(pto_handle *h, chain_t *c, const prop_t *p, uint64_t step, double *prop, draw_result_t *r) {
   const int d = h->d;
@@ -419,9 +529,8 @@ static void de_draw_standard(pto_handle *h, chain_t *c, const prop_t *p, uint64_
   double xgamma = draw_u32(h, &c->rng, PTG_DOMAIN_STEP, step, PTG_BLK_A, 2);
   if (xgamma < p->g1frac) gamma = 1;
   int a1 = 0, a2 = 0;
-  int64_t i1 = de_draw_index(h, c, p, step, 1, &a1);
-  int64_t i2 = de_draw_index(h, c, p, step, 2, &a2);
-  const double *s1 = c->hx + (size_t)i1 * d, *s2 = c->hx + (size_t)i2 * d;
+  const double *s1 = de_draw_state(h, c, p, step, 1, &a1);
+  const double *s2 = de_draw_state(h, c, p, step, 2, &a2);
   if (!is_philox(&c->rng)) { /* edist.drawSample: d normals drawn and discarded (H8-1, :518-526) */
     double zz[PTG_MAX_DIM]; draw_normals(h, &c->rng, step, d, zz);
   }
@@ -441,8 +550,7 @@ static void de_draw_snooker(pto_handle *h, chain_t *c, const prop_t *p, uint64_t
   double smznorm2 = 0, minusz[PTG_MAX_DIM], smz[PTG_MAX_DIM];
   int az = 0, isafe = 0;
   while (smznorm2 == 0) {
-    int64_t iz = de_draw_index(h, c, p, step, 0, &az);
-    const double *z = c->hx + (size_t)iz * d;
+    const double *z = de_draw_state(h, c, p, step, 0, &az);
     for (int i = 0; i < d; i++) { minusz[i] = z[i] * (-1); smz[i] = c->x[i] + minusz[i]; }
     smznorm2 = 0;
     for (int i = 0; i < d; i++) smznorm2 += smz[i] * smz[i];
@@ -450,9 +558,8 @@ static void de_draw_snooker(pto_handle *h, chain_t *c, const prop_t *p, uint64_t
     if (isafe > 1000) break;
   }
   int a1 = 0, a2 = 0;
-  int64_t i1 = de_draw_index(h, c, p, step, 1, &a1);
-  int64_t i2 = de_draw_index(h, c, p, step, 2, &a2);
-  const double *s1 = c->hx + (size_t)i1 * d, *s2 = c->hx + (size_t)i2 * d;
+  const double *s1 = de_draw_state(h, c, p, step, 1, &a1);
+  const double *s2 = de_draw_state(h, c, p, step, 2, &a2);
   double dot = 0;
   for (int i = 0; i < d; i++) {
     double ds12 = s1[i] * gamma + s2[i] * (-gamma);
@@ -552,6 +659,7 @@ static int set_draw(pto_handle *h, chain_t *c, uint64_t step, double *prop, draw
       if (prop_ready(h, c, &h->props[i]) && x < c->bin_max[i]) {
         member_draw(h, c, &h->props[i], step, prop, r);
         r->type = i + 10 * r->type;
+        r->member = i;
         return 0;
       }
     }
@@ -563,7 +671,7 @@ static int set_draw(pto_handle *h, chain_t *c, uint64_t step, double *prop, draw
 
 /* proposal_distribution_set::reset_bins (proposal_distribution.cc:37-59): called once by the constructor
  * (no chain: Tfac=0) and once by set_chain on each rung's clone (proposal_distribution.hh:336) */
-static void compute_bins(pto_handle *h, double beta, double *bin_max) {
+static void compute_bins(pto_handle *h, double beta, double *bin_max, double *shares_out) {
   int n = h->nprops;
   double shares[PTG_MAX_PROPOSALS], hot[PTG_MAX_PROPOSALS];
   for (int i = 0; i < n; i++) { shares[i] = h->props[i].share; hot[i] = h->props[i].hot_share; }
@@ -588,6 +696,34 @@ static void compute_bins(pto_handle *h, double beta, double *bin_max) {
     double back = bin_max[n - 1];
     for (int i = 0; i < n; i++) bin_max[i] /= back;
   }
+  for (int i = 0; i < n; i++) { if (shares_out) shares_out[i] = shares[i]; h->hot_norm[i] = hot[i]; }
+}
+
+/* proposal_distribution_set::reset_bins on a rung's own clone (proposal_distribution.cc:37-59): normalises the shares IN PLACE */
+static void chain_reset_bins(pto_handle *h, chain_t *c) {
+  int n = h->nprops;
+  double Tfac = 0;
+  if (h->Tpow > 0) Tfac = 1 - pow(c->beta, h->Tpow);
+  double sum = 0;
+  for (int i = 0; i < n; i++) sum += c->shares[i];
+  double last = 0;
+  for (int i = 0; i < n; i++) {
+    c->shares[i] /= sum;
+    c->bin_max[i] = last + c->shares[i];
+    if (h->Tpow > 0) c->bin_max[i] += (h->hot_norm[i] - c->shares[i]) * Tfac;
+    last = c->bin_max[i];
+  }
+  double back = c->bin_max[n - 1];
+  for (int i = 0; i < n; i++) c->bin_max[i] /= back;
+}
+/* proposal_distribution_set::accept / reject (proposal_distribution.cc:132-166).  adapt_count is never reset, so from the
+ * adapt_every-th decision on the bins are rebuilt after every decision. */
+static void set_adapt(pto_handle *h, chain_t *c, int member, int accepted) {
+  if (!h->wrap_in_set || h->adapt_rate == 0) return;
+  if (c->last_accepted[member] == accepted) c->shares[member] *= 1 - h->adapt_rate * 0.25;
+  c->last_accepted[member] = accepted;
+  c->adapt_count++;
+  if (c->adapt_count >= 10 * h->nprops) chain_reset_bins(h, c);
 }
 
 /* ---------------------------------------------------------------------------------------------- MH step */
@@ -595,7 +731,7 @@ static void compute_bins(pto_handle *h, double beta, double *bin_max) {
 static int mh_step(pto_handle *h, chain_t *c, uint64_t step, double *lhr_out, int *code_out) {
   const int d = h->d;
   double newx[PTG_MAX_DIM];
-  draw_result_t r; r.type = 0; r.log_hastings = 0; r.valid = 1;
+  draw_result_t r; r.type = 0; r.log_hastings = 0; r.valid = 1; r.member = 0;
   double oldlprior = c->lpost - c->beta * c->llike;
   if (set_draw(h, c, step, newx, &r) != 0) return fail(PTG_EINVAL, "proposal set: no member ready");
   int valid = r.valid;
@@ -622,9 +758,13 @@ static int mh_step(pto_handle *h, chain_t *c, uint64_t step, double *lhr_out, in
   if (accept) {
     c->naccept++;
     c->last_type = r.type;
+    set_adapt(h, c, r.member, 1);
     add_state(h, c, newx, newlike, newlpost);
     code |= PTG_TRACE_ACCEPT;
-  } else add_state(h, c, c->x, c->llike, c->lpost);
+  } else {
+    set_adapt(h, c, r.member, 0);
+    add_state(h, c, c->x, c->llike, c->lpost);
+  }
   code |= (r.type & PTG_TRACE_TYPE_MASK);
   *lhr_out = lhr; *code_out = code;
   return 0;
@@ -728,6 +868,7 @@ static int pt_step_ladder(pto_handle *h, int l) {
     h->swap_count[(size_t)l * (R - 1) + i]++;
   }
   /* standard step for the rungs not touched by a swap trial (chain.cc:1544-1559) */
+  for (int i = 0; i < R; i++) ch[i].frozen = ch[i].nsize; /* history_freeze: nothing below changes another chain's visible size */
   for (int i = 0; i < R; i++) {
     int skip = 0;
     for (int j = 0; j < ntrial; j++) if (i == iswaps[j] || i == iswaps[j] + 1) skip = 1;
@@ -792,7 +933,7 @@ int pto_destroy(pto_handle *h) {
   for (int64_t i = 0; i < h->nchains; i++) {
     chain_t *c = &h->chains[i];
     free(c->x); free(c->map_x); free(c->hx); free(c->hlpost); free(c->hllike); free(c->hacc); free(c->hbeta); free(c->htype);
-    free(c->rng.urec); free(c->rng.zrec); free(c->bin_max);
+    free(c->rng.urec); free(c->rng.zrec); free(c->bin_max); free(c->shares); free(c->last_accepted);
   }
   for (int l = 0; l < h->L; l++) { free(h->lstreams[l].urec); free(h->lstreams[l].zrec); }
   for (int i = 0; i < h->nprops; i++) { free(h->props[i].sigmas); free(h->props[i].transform); }
@@ -828,7 +969,7 @@ int pto_set_prior(pto_handle *h, const int32_t *type, const double *a, const dou
     } else if (p->kind == PTG_PRIOR_LOG) {
       if (a[i] <= 0 || b[i] <= a[i]) return fail(PTG_EINVAL, "log prior needs 0<xmin<xmax");
       p->la = log(a[i]); p->lb = log(b[i]);
-    } else if (p->kind != PTG_PRIOR_UNIFORM && p->kind != PTG_PRIOR_GAUSSIAN) return fail(PTG_EINVAL, "bad prior type");
+    } else if (p->kind != PTG_PRIOR_UNIFORM && p->kind != PTG_PRIOR_GAUSSIAN && p->kind != PTG_PRIOR_GAUSSIAN_WRAPPED) return fail(PTG_EINVAL, "bad prior type");
   }
   h->have_prior = 1;
   return 0;
@@ -855,6 +996,7 @@ int pto_set_proposals(pto_handle *h, int32_t n, const ptg_proposal *props, doubl
   if (n < 1 || n > PTG_MAX_PROPOSALS) return fail(PTG_EINVAL, "bad proposal count");
   if (!wrap_in_set && n != 1) return fail(PTG_EINVAL, "a bare proposal must be single");
   h->nprops = n; h->Tpow = Tpow; h->wrap_in_set = wrap_in_set;
+  h->adapt_rate = 0; h->de_mixing = 0; h->de_Tmix = 1;
   for (int i = 0; i < n; i++) {
     prop_t *p = &h->props[i]; const ptg_proposal *q = &props[i];
     p->kind = q->kind; p->share = q->share; p->hot_share = q->hot_share;
@@ -870,6 +1012,21 @@ int pto_set_proposals(pto_handle *h, int32_t n, const ptg_proposal *props, doubl
   return 0;
 }
 
+int pto_set_proposal_options(pto_handle *h, double adapt_rate, int32_t de_mixing, double de_Tmix) {
+  if (!h->have_props) return fail(PTG_EINVAL, "set the proposals first");
+  if (adapt_rate != 0 && !h->wrap_in_set) return fail(PTG_EINVAL, "adaptive shares need a proposal set");
+  if (de_mixing) {
+    if (h->wrap_in_set || h->props[0].kind != PTG_PROP_DE) return fail(PTG_EINVAL, "temperature mixing needs a bare differential-evolution proposal");
+    if (h->props[0].unlikely_alpha != 0) return fail(PTG_EINVAL, "temperature mixing needs unlikely_alpha = 0");
+  }
+  h->adapt_rate = adapt_rate; h->de_mixing = de_mixing; h->de_Tmix = de_Tmix;
+  return 0;
+}
+int pto_get_proposal_shares(pto_handle *h, double *shares) {
+  for (int64_t i = 0; i < h->nchains; i++)
+    for (int k = 0; k < h->nprops; k++) shares[i * h->nprops + k] = h->chains[i].shares ? h->chains[i].shares[k] : h->props[k].share;
+  return 0;
+}
 int pto_set_betas(pto_handle *h, const double *betas) {
   if (!betas) return 0;
   for (int64_t i = 0; i < h->nchains; i++) h->chains[i].beta = betas[i];
@@ -940,9 +1097,13 @@ static int finish_init(pto_handle *h) {
   for (int64_t i = 0; i < h->nchains; i++) {
     chain_t *c = &h->chains[i];
     c->nhist = 0;
-    free(c->bin_max);
+    free(c->bin_max); free(c->shares); free(c->last_accepted);
     c->bin_max = (double *)calloc(PTG_MAX_PROPOSALS, sizeof(double));
-    compute_bins(h, c->beta, c->bin_max); /* set_proposal after initialize (ptmcmc.cc:514-522) */
+    c->shares = (double *)calloc(PTG_MAX_PROPOSALS, sizeof(double));
+    c->last_accepted = (int *)calloc(PTG_MAX_PROPOSALS, sizeof(int));
+    for (int k = 0; k < PTG_MAX_PROPOSALS; k++) c->last_accepted[k] = 1; /* last_accepted.resize(Nsize,true) (proposal_distribution.cc:88) */
+    c->adapt_count = 0;
+    compute_bins(h, c->beta, c->bin_max, c->shares); /* set_proposal after initialize (ptmcmc.cc:514-522) */
   }
   for (int l = 0; l < h->L; l++)
     for (int r = 0; r < h->R; r++) { /* chain.cc:1345-1358 */

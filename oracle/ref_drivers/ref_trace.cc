@@ -233,6 +233,8 @@ int main(int argc, char **argv) {
     prior = new uniform_dist_product(&space, lo, hi);
   } else if (prior_kind == "gaussian") {
     prior = new gaussian_dist_product(&space, centers, halfw);
+  } else if (prior_kind == "gaussian_wrap") { // wrap_probability: images of wrapped dimensions are summed (probability_function.cc:57-78)
+    prior = new gaussian_dist_product(&space, centers, halfw, true);
   } else { // mixed: types file of doubles (1 uniform, 2 gaussian)
     valarray<int> types(d);
     vector<double> pt = kv.count("types") ? readvec(kv["types"]) : vector<double>(d, 1.0);
@@ -272,7 +274,8 @@ int main(int argc, char **argv) {
     int Ng = 6; double gshare = D("gauss_draw_frac", 0.2), g1d = D("gauss_1d_frac", 0.5);
     vector<proposal_distribution *> set(1 + Ng); vector<double> shares(1 + Ng), hot(1 + Ng);
     differential_evolution *de = new differential_evolution(0.1, D("de_g1_frac", 0.3), D("de_eps", 1e-4), 0.0, D("de_unlikely_alpha", 0));
-    de->reduce_gamma(D("de_reduce_gamma", 4)); de->mix_temperatures_more(300);
+    de->reduce_gamma(D("de_reduce_gamma", 4)); de->mix_temperatures_more(D("de_Tmix", 300));
+    if (I("de_mixing", 0)) de->support_mixing(true); // as ptmcmc.cc:84 does; inert inside a set (chain.cc:1375 asks the SET, which says no)
     set[0] = de; shares[0] = 1 - gshare;
     double sum = (pow(2, Ng + 1) - 2), stepfac = 2, fac = pow(2.0 / stepfac, 4.0), sharefac = 1;
     for (int i = 1; i < 1 + Ng; i++) {
@@ -280,11 +283,12 @@ int main(int argc, char **argv) {
       set[i] = new gaussian_prop(scales / 100.0 / fac, g1d, false);
       sharefac *= 2; shares[i] = sharefac / sum * gshare;
     }
-    cprop = new proposal_distribution_set(set, shares, 0, 0, hot);
+    cprop = new proposal_distribution_set(set, shares, D("adapt_rate", 0), 0, hot);
   } else if (prop == "de") {
     differential_evolution *de = new differential_evolution(D("de_snooker", 0.1), D("de_g1_frac", 0.3), D("de_eps", 1e-4),
                                                             D("de_ignore_frac", 0.0), D("de_unlikely_alpha", 0));
     de->reduce_gamma(D("de_reduce_gamma", 4));
+    if (I("de_mixing", 0)) { de->support_mixing(true); de->mix_temperatures_more(D("de_Tmix", 1)); }
     cprop = de;
   } else if (prop == "gauss") {
     cprop = new gaussian_prop(scales / D("gauss_div", 10.0), D("gauss_1d_frac", 0.5), false);
@@ -323,7 +327,7 @@ int main(int argc, char **argv) {
     // thermal weighting of the prior draws as ptmcmc_sampler::select_proposal sets it up (ptmcmc.cc:95-101): hot share 1 for the prior draw
     double Tpow = D("Tpow", 0);
     if (Tpow > 0) { hot[0] = D("hot_de", 0.0); hot[1] = D("hot_prior", 1.0); }
-    cprop = new proposal_distribution_set(set, shares, 0, Tpow, hot);
+    cprop = new proposal_distribution_set(set, shares, D("adapt_rate", 0), Tpow, hot);
   } else { cerr << "unknown prop " << prop << endl; return 2; }
 
   // ---- chain: exactly ptmcmc_sampler::initialize (ptmcmc.cc:508-522) ------------------------------

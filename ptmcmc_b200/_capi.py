@@ -15,7 +15,7 @@ MAX_RUNGS = 64
 
 # enums (include/ptmcmc_b200.h)
 BOUND_OPEN, BOUND_LIMIT, BOUND_REFLECT, BOUND_WRAP = 0, 1, 2, 3
-PRIOR_UNIFORM, PRIOR_GAUSSIAN, PRIOR_POLAR, PRIOR_COPOLAR, PRIOR_LOG = 1, 2, 3, 4, 5
+PRIOR_UNIFORM, PRIOR_GAUSSIAN, PRIOR_POLAR, PRIOR_COPOLAR, PRIOR_LOG, PRIOR_GAUSSIAN_WRAPPED = 1, 2, 3, 4, 5, 6
 LIKE_FLAT, LIKE_GAUSS_ISO, LIKE_SINES, LIKE_POLY_CHI2, LIKE_SINUSOID_CHI2, LIKE_GAUSS_FULLCOV, LIKE_HOST_CALLBACK, LIKE_SHELL2D, LIKE_SHELLS = 0, 1, 2, 3, 4, 5, 6, 7, 8
 PROP_DE, PROP_GAUSS, PROP_PRIOR_DRAW = 1, 2, 3
 SWAP_REFERENCE, SWAP_EVEN_ODD = 0, 1
@@ -81,6 +81,7 @@ class CApi:
         self._call("create", C.byref(cfg), C.byref(self.h))
         self.n_chains = cfg.n_ladders * cfg.n_rungs
         self.dim = cfg.dim
+        self.n_props = 0
 
     def _fn(self, name):
         return getattr(self.lib, self.prefix + name)
@@ -123,6 +124,7 @@ class CApi:
     def set_proposals(self, props, Tpow=0.0, wrap_in_set=True):
         """props: list of dicts(kind=..., share=..., [DE fields] / [sigmas, one_d_frac, transform])"""
         arr = (Proposal * len(props))()
+        self.n_props = len(props)
         for i, p in enumerate(props):
             q = arr[i]
             q.kind = p["kind"]; q.share = p.get("share", 1.0); q.hot_share = p.get("hot_share", 0.0)
@@ -135,6 +137,15 @@ class CApi:
                 if p.get("transform") is not None:
                     t = _f64(p["transform"]); self._keep.append(t); q.transform = _dp(t)
         self._call("set_proposals", self.h, C.c_int32(len(props)), arr, C.c_double(Tpow), C.c_int32(1 if wrap_in_set else 0))
+
+    def set_proposal_options(self, adapt_rate=0.0, de_mixing=False, de_Tmix=1.0):
+        """adaptive shares of the set (proposal_distribution.cc:132-166) / temperature mixing of a bare DE proposal (:594-741)"""
+        self._call("set_proposal_options", self.h, C.c_double(adapt_rate), C.c_int32(1 if de_mixing else 0), C.c_double(de_Tmix))
+
+    def get_proposal_shares(self):
+        sh = np.empty((self.n_chains, max(self.n_props, 1)))
+        self._call("get_proposal_shares", self.h, _dp(sh))
+        return sh
 
     def set_betas(self, betas):
         b = _f64(betas); self._call("set_betas", self.h, _dp(b))

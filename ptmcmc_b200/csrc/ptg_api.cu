@@ -40,12 +40,14 @@ struct ptg_handle {
   bool model_dirty;                // a set_* call changed the model since the last upload
   std::vector<HostProp> props;
   double Tpow;
+  double adapt_rate; int de_mixing; double de_Tmix;   // ptg_set_proposal_options
   std::vector<double> lparams, ldata, betas;
   std::vector<int32_t> lower, upper; std::vector<double> xmin, xmax; std::vector<PtgPrior1D> prior; // every dimension (dim may exceed 16)
   int wide_trans_off;              // offset of the (first) eigen-rotation matrix in prop_data, -1 = none
   bool wide;                       // dim > 16: warp-per-chain kernels (ptg_wide.cuh)
   std::vector<void *> allocs;       // every device allocation (freed in destroy)
   double *d_lparams, *d_ldata, *d_prop_data, *d_bins;
+  double *d_xscratch;              // pipelined wide kernel: one published-state row per chain
   double *d_tape_u, *d_tape_z; long long *d_u_end, *d_z_end;
   long long istep;
   double *d_scratch; size_t scratch_bytes;
@@ -305,7 +307,7 @@ extern "C" int ptg_set_prior(ptg_handle *h, const int32_t *type, const double *a
     } else if (p.kind == PTG_PRIOR_LOG) {
       if (a[i] <= 0 || b[i] <= a[i]) return fail(PTG_EINVAL, "log prior needs 0 < xmin < xmax");
       p.la = log(a[i]); p.lb = log(b[i]);
-    } else if (p.kind != PTG_PRIOR_UNIFORM && p.kind != PTG_PRIOR_GAUSSIAN) return fail(PTG_EINVAL, "bad prior type %d", p.kind);
+    } else if (p.kind != PTG_PRIOR_UNIFORM && p.kind != PTG_PRIOR_GAUSSIAN && p.kind != PTG_PRIOR_GAUSSIAN_WRAPPED) return fail(PTG_EINVAL, "bad prior type %d", p.kind);
   }
   for (int i = 0; i < m.dim && i < PTG_TPC_MAX_DIM; i++) m.prior[i] = h->prior[i];
   m.all_uniform_prior = all_uniform ? 1 : 0;
@@ -418,8 +420,49 @@ extern "C" int ptg_set_proposals(ptg_handle *h, int32_t n, const ptg_proposal *p
     h->props.push_back(hp);
   }
   h->Tpow = Tpow; h->m.wrap_in_set = wrap_in_set ? 1 : 0; h->m.n_props = n;
+  h->adapt_rate = 0; h->de_mixing = 0; h->de_Tmix = 1;
   h->have_props = true;
   h->model_dirty = true;
+  return 0;
+}
+
+// proposal_distribution_set's adapt_rate (proposal_distribution.cc:61,132-166) and differential_evolution::support_mixing /
+// mix_temperatures_more (proposal_distribution.hh:403,412)
+extern "C" int ptg_set_proposal_options(ptg_handle *h, double adapt_rate, int32_t de_mixing, double de_Tmix) {
+  if (!h) return fail(PTG_EINVAL, "null handle");
+  if (!h->have_props) return fail(PTG_EINVAL, "set the proposals first");
+  if (h->inited) return fail(PTG_EINVAL, "proposal options must be set before initialising");
+  if (adapt_rate != 0 || de_mixing) {
+    if (h->wide) return fail(PTG_EINVAL, "adaptive shares / temperature mixing run in the thread-per-chain warp kernel: dim <= 16");
+    if (h->m.n_rungs > 32 || h->m.maxswaps > 32) return fail(PTG_EINVAL, "adaptive shares / temperature mixing need n_rungs <= 32 and at most 32 swap trials per step");
+    if (h->m.like_kind == PTG_LIKE_HOST_CALLBACK) return fail(PTG_EINVAL, "adaptive shares / temperature mixing are not available with a host-callback likelihood");
+  }
+  if (adapt_rate != 0 && !h->m.wrap_in_set) return fail(PTG_EINVAL, "adaptive shares need a proposal set (wrap_in_set = 1)");
+  if (de_mixing) {
+    if (h->m.wrap_in_set || h->props[0].p.kind != PTG_PROP_DE)
+      return fail(PTG_EINVAL, "temperature mixing needs a bare differential-evolution proposal: inside a set the reference never mixes (chain.cc:1375)");
+    if (h->props[0].p.unlikely_alpha != 0) return fail(PTG_EINVAL, "temperature mixing needs unlikely_alpha = 0");
+    if (!(de_Tmix > 0)) return fail(PTG_EINVAL, "de_Tmix must be positive");
+  }
+  h->adapt_rate = adapt_rate; h->de_mixing = de_mixing ? 1 : 0; h->de_Tmix = de_Tmix;
+  h->model_dirty = true;
+  return 0;
+}
+
+static void compute_bins(const ptg_handle *h, double beta, double *bin_max, double *shares_out, double *hot_out);
+extern "C" int ptg_get_proposal_shares(ptg_handle *h, double *shares) {
+  if (!h || !shares) return fail(PTG_EINVAL, "null argument");
+  if (!h->model_uploaded) return fail(PTG_EINVAL, "not initialised");
+  const PtgModel &m = h->m;
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  if (h->s.ad_shares) {
+    CUDA_TRY(cudaMemcpyAsync(shares, h->s.ad_shares, (size_t)m.n_chains * m.n_props * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+  } else {
+    std::vector<double> bins(m.n_props), sh(m.n_props);
+    compute_bins(h, 1.0, bins.data(), sh.data(), nullptr);
+    for (int64_t c = 0; c < m.n_chains; c++) for (int k = 0; k < m.n_props; k++) shares[c * m.n_props + k] = sh[k];
+  }
   return 0;
 }
 
@@ -472,7 +515,7 @@ extern "C" int ptg_inject_tape_marks(ptg_handle *h, int64_t n_steps, const int64
 
 // proposal_distribution_set::reset_bins (proposal_distribution.cc:37-59): run once by the constructor (no chain yet,
 // Tfac = 0) and once more by set_chain on each rung's clone (proposal_distribution.hh:336)
-static void compute_bins(const ptg_handle *h, double beta, double *bin_max) {
+static void compute_bins(const ptg_handle *h, double beta, double *bin_max, double *shares_out, double *hot_out) {
   const int n = (int)h->props.size();
   double shares[PTG_MAX_PROPOSALS], hot[PTG_MAX_PROPOSALS];
   for (int i = 0; i < n; i++) { shares[i] = h->props[i].p.share; hot[i] = h->props[i].p.hot_share; }
@@ -497,6 +540,7 @@ static void compute_bins(const ptg_handle *h, double beta, double *bin_max) {
     double back = bin_max[n - 1];
     for (int i = 0; i < n; i++) bin_max[i] /= back;
   }
+  for (int i = 0; i < n; i++) { if (shares_out) shares_out[i] = shares[i]; if (hot_out) hot_out[i] = hot[i]; }
 }
 
 static int upload_model(ptg_handle *h) {
@@ -508,6 +552,8 @@ static int upload_model(ptg_handle *h) {
         m.like_kind != PTG_LIKE_SINUSOID_CHI2)
       return fail(PTG_EINVAL, "dim > 16: likelihood functors flat, gaussian, full-covariance gaussian and the data chi^2 models are available");
   }
+  if ((h->adapt_rate != 0 || h->de_mixing) && m.like_kind == PTG_LIKE_HOST_CALLBACK)
+    return fail(PTG_EINVAL, "adaptive shares / temperature mixing are not available with a host-callback likelihood");
   // proposals
   h->wide_trans_off = -1;
   std::vector<double> pdata;
@@ -528,9 +574,28 @@ static int upload_model(ptg_handle *h) {
     }
   }
   if (pdata.empty()) pdata.push_back(0.0);
+  m.adapt_rate = h->adapt_rate; m.de_mixing = h->de_mixing; m.de_Tmix = h->de_Tmix; m.Tpow = h->Tpow;
+  if (m.adapt_rate != 0) {
+    // adaptive shares: every chain's clone of the set starts from the normalised shares and the bins of its own rung's temperature
+    // (constructor + set_chain, proposal_distribution.cc:61-93, .hh:336), all members "last accepted" (:88), adapt_count 0
+    const size_t nc = (size_t)m.n_chains, np = (size_t)m.n_props;
+    std::vector<double> sh(nc * np), bn(nc * np);
+    for (size_t c = 0; c < nc; c++) compute_bins(h, h->betas[c], &bn[c * np], &sh[c * np], m.hot_norm);
+    int rc2 = 0;
+    if (!h->s.ad_shares) {
+      rc2 |= dev_alloc(h, &h->s.ad_shares, nc * np, false); rc2 |= dev_alloc(h, &h->s.ad_bins, nc * np, false);
+      rc2 |= dev_alloc(h, &h->s.ad_last, nc, false); rc2 |= dev_alloc(h, &h->s.ad_count, nc);
+    }
+    if (rc2) return PTG_ENOMEM;
+    CUDA_TRY(cudaMemcpyAsync(h->s.ad_shares, sh.data(), sh.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->s.ad_bins, bn.data(), bn.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->s.ad_last, 0xff, nc * sizeof(int32_t), h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->s.ad_count, 0, nc * sizeof(int32_t), h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+  }
   // bins per rung, from ladder 0's initial inverse temperatures
   std::vector<double> bins((size_t)m.n_rungs * m.n_props);
-  for (int r = 0; r < m.n_rungs; r++) compute_bins(h, h->betas[r], &bins[(size_t)r * m.n_props]);
+  for (int r = 0; r < m.n_rungs; r++) compute_bins(h, h->betas[r], &bins[(size_t)r * m.n_props], nullptr, m.hot_norm);
   if (h->Tpow > 0)
     for (int l = 1; l < m.n_ladders; l++)
       for (int r = 0; r < m.n_rungs; r++)
@@ -721,12 +786,18 @@ static int fstep_streamlined_kind(const ptg_handle *h) {
   }
   return m.like_kind;
 }
+// ptg_wide.cu: the pipelined full-covariance kernel (ptg_wide_pipe.cuh)
+int ptg_xpstep_fits(const PtgModel &m, int trans_off);
+size_t ptg_xpstep_scratch_doubles(const PtgModel &m);
+cudaError_t ptg_launch_xpstep(const PtgModel &m, const PtgState &s, long long step0, int n_steps, int trans_off, double *scratch, cudaStream_t st);
 static int pick_kernel(const ptg_handle *h, int *W) {
   *W = warp_kernel_width(h);
   int k = PTG_KERNEL_SHARED;
   if (*W) k = (h->cfg.rng_mode == PTG_RNG_PHILOX) ? PTG_KERNEL_FAST : PTG_KERNEL_WARP;
   if (h->kernel_choice == PTG_KERNEL_SHARED) k = PTG_KERNEL_SHARED;
   if (h->kernel_choice == PTG_KERNEL_WARP && *W) k = PTG_KERNEL_WARP;
+  // adaptive shares and temperature mixing exist in the tape-capable warp kernel (either RNG mode); ptg_set_proposal_options made sure it applies
+  if ((h->m.adapt_rate != 0 || h->m.de_mixing) && *W) k = PTG_KERNEL_WARP;
   return k;
 }
 
@@ -777,7 +848,14 @@ extern "C" int ptg_step(ptg_handle *h, int64_t n_steps) {
       // (data chi^2 likelihoods and the prior-draw member exist in the exact-order kernel only)
       bool exact_only = m.like_kind == PTG_LIKE_POLY_CHI2 || m.like_kind == PTG_LIKE_SINUSOID_CHI2;
       for (const HostProp &hp : h->props) if (hp.p.kind == PTG_PROP_PRIOR_DRAW) exact_only = true;
-      if (h->cfg.rng_mode == PTG_RNG_PHILOX && h->kernel_choice != PTG_KERNEL_WARP && !exact_only) e = ptg_launch_xmstep(m, h->s, h->istep, chunk, h->wide_trans_off, h->stream);
+      if (h->cfg.rng_mode == PTG_RNG_PHILOX && h->kernel_choice != PTG_KERNEL_WARP && !exact_only) {
+        // full-covariance Gaussian with one rotation matrix (BASELINE config D): the pipelined kernel with both matrices resident in shared
+        // memory; PTG_KERNEL_SHARED pins the round-1 L1-streamed DMMA kernel (bit-identical chains, tests)
+        if (h->kernel_choice != PTG_KERNEL_SHARED && ptg_xpstep_fits(m, h->wide_trans_off)) {
+          if (!h->d_xscratch) { int rc = dev_alloc(h, &h->d_xscratch, ptg_xpstep_scratch_doubles(m)); if (rc) return rc; }
+          e = ptg_launch_xpstep(m, h->s, h->istep, chunk, h->wide_trans_off, h->d_xscratch, h->stream);
+        } else e = ptg_launch_xmstep(m, h->s, h->istep, chunk, h->wide_trans_off, h->stream);
+      }
       else e = ptg_launch_xstep(h->cfg.rng_mode, m, h->s, h->istep, chunk, h->stream);
     }
     else switch (m.dim) {
@@ -1473,6 +1551,10 @@ static std::vector<CkArr> ck_arrays(ptg_handle *h) {
       {s.swap_count, n * 8}, {s.swap_accept, n * 8}, {s.directions, n * 4}, {s.ups, n * 4}, {s.downs, n * 4}, {s.instances, n * 4},
       {s.u_pos, (n + m.n_ladders) * 8}, {s.z_pos, (n + m.n_ladders) * 8}};
   if (m.record_full) { v.push_back({s.hist_acc, n * cap * 8}); v.push_back({s.hist_beta, n * cap * 8}); v.push_back({s.hist_type, n * cap * 4}); }
+  if (s.ad_shares) { // the adapted shares of every chain's proposal set (proposal_distribution_set::checkpoint, proposal_distribution.cc:168-200)
+    const size_t np = (size_t)m.n_props;
+    v.push_back({s.ad_shares, n * np * 8}); v.push_back({s.ad_bins, n * np * 8}); v.push_back({s.ad_last, n * 4}); v.push_back({s.ad_count, n * 4});
+  }
   return v;
 }
 static const uint64_t CK_MAGIC = 0x70746763686b3032ull; // "ptgchk02"

@@ -120,7 +120,8 @@ __device__ __forceinline__ double pdf1d(const PtgPrior1D &p, double x) {
     if (x < p.a) return 0;
     if (x > p.b) return 0;
     return 1 / (p.b - p.a);
-  case PTG_PRIOR_GAUSSIAN: {
+  case PTG_PRIOR_GAUSSIAN:
+  case PTG_PRIOR_GAUSSIAN_WRAPPED: {
     double xnorm = (x - p.a) / p.b;
     return exp(-xnorm * xnorm / 2) / sqrt(2 * PTG_PI) / p.b;
   }
@@ -138,6 +139,28 @@ __device__ __forceinline__ double pdf1d(const PtgPrior1D &p, double x) {
     return 1 / (p.lb - p.la) / x;
   }
   return 0;
+}
+// one factor of the prior product: pdf1d, plus the images of a wrapped dimension for a wrapped Gaussian factor
+// (gaussian_dist_product::evaluate with wrap_probability, probability_function.cc:57-78).  The image sum is a rare path kept out of line
+// (one copy per translation unit instead of one per dimension of every unrolled prior product).
+static __device__ __noinline__ double prior_wrap_images(double x0, double sigma, double x, double width, double resulti) {
+  const double tol = 1e-12;
+  double xplus = x, xminus = x, delta = 1;
+  int count = 0;
+  while (delta > tol && count < 100) {
+    xplus += width;
+    xminus -= width;
+    const double xm = (xminus - x0) / sigma, xp = (xplus - x0) / sigma;
+    delta = exp(-xm * xm / 2) / sqrt(2 * PTG_PI) / sigma + exp(-xp * xp / 2) / sqrt(2 * PTG_PI) / sigma;
+    resulti += delta;
+    count++;
+  }
+  return resulti;
+}
+__device__ __forceinline__ double prior_factor(const PtgPrior1D &p, double x, int lt, int ut, double xmin, double xmax) {
+  double resulti = pdf1d(p, x);
+  if (p.kind == PTG_PRIOR_GAUSSIAN_WRAPPED && lt == PTG_BOUND_WRAP && ut == PTG_BOUND_WRAP) resulti = prior_wrap_images(p.a, p.b, x, xmax - xmin, resulti);
+  return resulti;
 }
 __device__ __forceinline__ double invcdf1d(const PtgPrior1D &p, double u) {
   switch (p.kind) {
@@ -160,7 +183,7 @@ __device__ __forceinline__ double prior_eval_log(const PtgModel &m, const double
   }
   double result = 1;
 #pragma unroll
-  for (int i = 0; i < D; i++) result *= pdf1d(m.prior[i], x[i]);
+  for (int i = 0; i < D; i++) result *= prior_factor(m.prior[i], x[i], m.lower[i], m.upper[i], m.xmin[i], m.xmax[i]);
   return log(result);
 }
 // drawSample (probability_function.cc:37-47,147-154,264-279), returns validity after state(space,v) enforcement
@@ -169,7 +192,7 @@ __device__ __forceinline__ bool prior_draw(const PtgModel &m, Stream<MODE> &rs, 
 #pragma unroll
   for (int i = 0; i < D; i++) {
     uint32_t w[4]; rs.fetch(blk0 + i, w);
-    if (m.prior[i].kind == PTG_PRIOR_GAUSSIAN) {
+    if (m.prior[i].kind == PTG_PRIOR_GAUSSIAN || m.prior[i].kind == PTG_PRIOR_GAUSSIAN_WRAPPED) {
       double z;
       if constexpr (MODE == PTG_RNG_PHILOX) { double z1; box_muller(w, z, z1); }
       else z = rs.next_z();
@@ -180,6 +203,39 @@ __device__ __forceinline__ bool prior_draw(const PtgModel &m, Stream<MODE> &rs, 
     }
   }
   return space_enforce<D>(m, x);
+}
+
+// ------------------------------------------------------------------------------------------------- adaptive shares
+// proposal_distribution_set::accept / reject (proposal_distribution.cc:132-166) on this chain's clone of the set: two accepts or two
+// rejects in a row of `member` scale its share by 1 - adapt_rate / 4; adapt_count is never reset in the reference, so from the
+// adapt_every-th (10 n) decision on reset_bins (:37-59) runs after every decision: shares normalised in place, bins rebuilt with the
+// chain's CURRENT temperature when Tpow > 0.
+__device__ __forceinline__ void set_adapt(const PtgModel &m, const PtgState &s, long long chain, int member, bool accepted, double beta) {
+  const int n = m.n_props;
+  double *sh = s.ad_shares + chain * n, *bn = s.ad_bins + chain * n;
+  int last = s.ad_last[chain];
+  if ((((last >> member) & 1) != 0) == accepted) sh[member] *= 1 - m.adapt_rate * 0.25;
+  last = accepted ? (last | (1 << member)) : (last & ~(1 << member));
+  s.ad_last[chain] = last;
+  const int cnt = s.ad_count[chain] + 1;
+  s.ad_count[chain] = cnt;
+  if (cnt >= 10 * n) {
+    double Tfac = 0;
+    if (m.Tpow > 0) Tfac = 1 - pow(beta, m.Tpow);
+    double sum = 0;
+    for (int i = 0; i < n; i++) sum += sh[i];
+    double lastb = 0;
+    for (int i = 0; i < n; i++) {
+      const double v = sh[i] / sum;
+      sh[i] = v;
+      double b = lastb + v;
+      if (m.Tpow > 0) b += (m.hot_norm[i] - v) * Tfac;
+      bn[i] = b;
+      lastb = b;
+    }
+    const double back = bn[n - 1];
+    for (int i = 0; i < n; i++) bn[i] /= back;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------- likelihoods

@@ -38,7 +38,9 @@ struct PtgModel {
   double swap_rate, dprior_min, evolve_rate, evolve_lpost_cut;
   double like_nsum;
   double like_t0, like_dt;    // data chi^2 likelihoods: abscissae are the uniform grid t0 + i dt (like_uniform_t), e.g. config C2's time samples
-  int32_t like_uniform_t, pad1;
+  int32_t like_uniform_t, de_mixing; // de_mixing: temperature mixing of a bare DE proposal's history draws (proposal_distribution.cc:594-741)
+  double adapt_rate, de_Tmix, Tpow;  // adaptive shares of the set (proposal_distribution.cc:132-166); reset_bins' thermal exponent
+  double hot_norm[PTG_MAX_PROPOSALS]; // normalised hot shares (constructor, proposal_distribution.cc:72-79)
   double uniform_lprior;      // log(prod 1/(b-a)) when every factor is uniform (evaluated once on the device)
   uint64_t seed;
   int64_t ladder_offset;
@@ -85,6 +87,9 @@ struct PtgState {
   double *pend_lprior, *pend_lh, *pend_like; // [n_chains]
   int32_t *pend_type, *pend_flags;      // flags: bit0 valid, bit1 gate (likelihood wanted), bit2 MH step pending
   uint32_t *pend_w;                     // [n_chains][2] acceptance-draw words
+  // adaptive shares: every chain's clone of the proposal set owns shares, bins, last_accepted (bit per member) and adapt_count
+  double *ad_shares, *ad_bins;          // [n_chains][n_props]
+  int32_t *ad_last, *ad_count;          // [n_chains]
   int32_t *err;       // device error flag (PTG_ETAPE, PTG_ESTUCK)
 };
 // Rung-sharded ladders, exchange fused into the production step kernel over NVLink peer memory (ptg_fast.cuh).

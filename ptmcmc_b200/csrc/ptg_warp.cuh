@@ -232,6 +232,89 @@ __device__ __forceinline__ int wde_index(const PtgModel &m, const PtgState &s, c
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------- temperature mixing
+// differential_evolution::draw_from_chain with support_mixing (proposal_distribution.cc:594-741): a bare DE proposal on a ladder weighs
+// the rungs by Nmean = 10 log-likelihoods of the CALLER's history (at indices drawn against rung i's size) and the median of Nmedian = 10
+// of rung i's own, picks a rung and draws the state from its history.  Sizes are the frozen sizes (history_freeze, chain.cc:1552): the
+// ladder's lanes published (window size, ring offset, beta) of their rung to `mx` before the MH phase.  unlikely_alpha = 0 (checked on
+// the host), so draw_i_from_chain (:744-778) is one uniform: the k-th of history draw `which` has the Philox address
+// PTG_BLK_MIX + which * 0x1000 + k / 4, word k % 4; tape runs consume the chain's tape in the same order.
+struct WMix { int size[32], off[32]; double beta[32]; };   // per warp
+template <int D, int MODE>
+__device__ __noinline__ const double *wde_state_mixed(const PtgModel &m, const PtgState &s, const WLane &w, const Chain<D> &ch, const PtgProp &p,
+                                                     Stream<MODE> &rs, int which, int &kcount, const WMix &mx) {
+  const int R = w.R, g0 = w.lane - w.rung;          // lane of rung 0 of this ladder
+  const long long chain0 = ch.chain - w.rung;
+  uint32_t q0 = 0, q1 = 0, q2 = 0, q3 = 0; int blk = -1;
+  auto nextu = [&]() -> double {
+    const int kk = kcount++;
+    if constexpr (MODE == PTG_RNG_PHILOX) {
+      if ((kk >> 2) != blk) { uint32_t q[4]; blk = kk >> 2; rs.fetch(PTG_BLK_MIX + (uint32_t)which * 0x1000u + (uint32_t)blk, q); q0 = q[0]; q1 = q[1]; q2 = q[2]; q3 = q[3]; }
+      const int wd = kk & 3;
+      return ptg_u32_to_unit(wd == 0 ? q0 : (wd == 1 ? q1 : (wd == 2 ? q2 : q3)));
+    } else return rs.next_u();
+  };
+  auto draw_i = [&](int j) -> int {
+    const int size = mx.size[g0 + j];
+    int start = 0;
+    const int mins = D * 10, minc = D * 100;
+    if ((size - minc) * (1 - p.ignore_frac) > mins) start = (int)((size - minc) * p.ignore_frac);
+    return (int)(start + (size - start) * nextu());
+  };
+  auto llike_at = [&](int j, int index, double current) -> double { // MH_chain::getLogLike(index, true), chain.cc:1078-1085
+    if (index < 0 || index >= mx.size[g0 + j]) return current;
+    int pp = mx.off[g0 + j] + index; if (pp >= m.hist_cap) pp -= m.hist_cap;
+    return s.hist_lp[2 * ((chain0 + j) * m.hist_cap + pp) + 1];
+  };
+  constexpr int Nmean = 10, Nmedian = 10;
+  const double pmix = m.de_Tmix, beta = ch.beta;
+  double ksum = 0, kthis_lo = 0; // running k[i]; the pick needs k[] again, so the weights are kept
+  double kw[32];
+  int ithis = 0, guard = 0;
+  for (int i = 0; i < R; i++) {
+    double l0[Nmean], l[Nmedian];
+    double l0max = -1e100, l0min = 1e100;
+    for (int j = 0; j < Nmean; j++) {
+      const int index = draw_i(i);
+      const double dl = llike_at(w.rung, index, ch.llike);
+      if (isfinite(dl)) {
+        if (dl > l0max) l0max = dl;
+        if (dl < l0min) l0min = dl;
+        l0[j] = dl;
+      } else { j--; if (++guard > 100000) { rs.err = 3; break; } }
+    }
+    const double alpha = mx.beta[g0 + i];
+    double amb = alpha - beta;
+    amb = -amb;
+    if (amb == 0) ithis = i;
+    double sum = 0;
+    const double l0scale = amb < 0 ? l0min : l0max;
+    for (int ii = 0; ii < Nmean; ii++) sum += exp((l0[ii] - l0scale) * amb);
+    const double ll0 = log(sum / Nmean) + l0scale * amb;
+    for (int j = 0; j < Nmedian; j++) { const int index = draw_i(i); l[j] = llike_at(i, index, 0.0); }
+    for (int a = 1; a < Nmedian; a++) { // sort(l.begin(), l.end())
+      const double v = l[a]; int b = a - 1;
+      while (b >= 0 && l[b] > v) { l[b + 1] = l[b]; b--; }
+      l[b + 1] = v;
+    }
+    const double ll = l[Nmedian / 2];
+    double lk = ll0 - ll * amb;
+    lk = -lk;
+    lk /= pmix;
+    if (lk > 0) lk = 0;
+    ksum = ksum + exp(lk);
+    kw[i] = ksum;
+  }
+  (void)kthis_lo;
+  int ipick = ithis;
+  const double xrnd = nextu() * ksum;
+  for (int i = 0; i < R; i++) if (xrnd <= kw[i]) { ipick = i; break; }
+  const int index = draw_i(ipick);
+  int pp = mx.off[g0 + ipick] + index; if (pp >= m.hist_cap) pp -= m.hist_cap;
+  return s.hist + ((chain0 + ipick) * m.hist_cap + pp) * PTG_HX(D);
+}
+
 // ------------------------------------------------------------------------------------------------- cooperative normals
 // PHILOX: standard normals z[0..D) for every lane with `need`; each (owner lane, Box-Muller pair) is one work item
 // evaluated by some lane of the warp from the OWNER's stream address, so the values equal per-lane draw_normals().
@@ -275,7 +358,7 @@ __device__ __forceinline__ void wcoop_normals(uint64_t seed, uint64_t step, uint
 // Called by ALL lanes of the warp; lanes with do_mh == false take part in the cooperative work only.
 template <int D, int MODE>
 __device__ __forceinline__ MhOut wmh_step(const PtgModel &m, const PtgState &s, const WLane &w, Chain<D> &ch, Stream<MODE> &rs,
-                                          const double *__restrict__ bins, bool do_mh, uint64_t stream_base) {
+                                          const double *__restrict__ bins, bool do_mh, uint64_t stream_base, const WMix &mx) {
   double newx[D];
 #pragma unroll
   for (int i = 0; i < D; i++) newx[i] = ch.x[i];
@@ -290,6 +373,9 @@ __device__ __forceinline__ MhOut wmh_step(const PtgModel &m, const PtgState &s, 
 
   // ---- member selection: first ready member with u < bin_max (proposal_distribution.cc:105-112)
   int member = 0;
+  const bool adaptive = m.adapt_rate != 0 && m.wrap_in_set != 0;   // this chain's own, adapting bins
+  if (adaptive && do_mh) bins = s.ad_bins + ch.chain * m.n_props;
+  const bool mixing = m.de_mixing != 0 && w.R > 1;
   if (m.wrap_in_set && do_mh) {
     member = -1;
     for (int count = 0; count <= 100 && member < 0; count++) {
@@ -320,9 +406,13 @@ __device__ __forceinline__ MhOut wmh_step(const PtgModel &m, const PtgState &s, 
       double gamma = p.gamma_std;
       if (ug < p.g1frac) gamma = 1;
       int a1 = 0, a2 = 0;
-      const int i1 = wde_index<D, MODE>(m, s, ch, p, rs, wA[3], 1, hsize, a1);
-      const int i2 = wde_index<D, MODE>(m, s, ch, p, rs, wB[0], 2, hsize, a2);
-      const double *s1 = hist_elem<D>(m, s, ch, i1), *s2 = hist_elem<D>(m, s, ch, i2);
+      const double *s1, *s2;
+      if (mixing) { s1 = wde_state_mixed<D, MODE>(m, s, w, ch, p, rs, 1, a1, mx); s2 = wde_state_mixed<D, MODE>(m, s, w, ch, p, rs, 2, a2, mx); }
+      else {
+        const int i1 = wde_index<D, MODE>(m, s, ch, p, rs, wA[3], 1, hsize, a1);
+        const int i2 = wde_index<D, MODE>(m, s, ch, p, rs, wB[0], 2, hsize, a2);
+        s1 = hist_elem<D>(m, s, ch, i1); s2 = hist_elem<D>(m, s, ch, i2);
+      }
       if constexpr (MODE == PTG_RNG_TAPE) { // the d normals of the discarded jitter are still consumed (H8-1)
         for (int j = 0; j < D; j++) (void)rs.next_z();
       }
@@ -341,8 +431,9 @@ __device__ __forceinline__ MhOut wmh_step(const PtgModel &m, const PtgState &s, 
       double smznorm2 = 0, minusz[D], smz[D];
       int az = 0, isafe = 0;
       while (smznorm2 == 0) {
-        const int iz = wde_index<D, MODE>(m, s, ch, p, rs, wB[1], 0, hsize, az);
-        const double *zz = hist_elem<D>(m, s, ch, iz);
+        const double *zz;
+        if (mixing) zz = wde_state_mixed<D, MODE>(m, s, w, ch, p, rs, 0, az, mx);
+        else { const int iz = wde_index<D, MODE>(m, s, ch, p, rs, wB[1], 0, hsize, az); zz = hist_elem<D>(m, s, ch, iz); }
         smznorm2 = 0;
 #pragma unroll
         for (int i = 0; i < D; i++) { minusz[i] = zz[i] * (-1); smz[i] = ch.x[i] + minusz[i]; }
@@ -351,9 +442,13 @@ __device__ __forceinline__ MhOut wmh_step(const PtgModel &m, const PtgState &s, 
         if (++isafe > 1000) break;
       }
       int a1 = 0, a2 = 0;
-      const int i1 = wde_index<D, MODE>(m, s, ch, p, rs, wA[3], 1, hsize, a1);
-      const int i2 = wde_index<D, MODE>(m, s, ch, p, rs, wB[0], 2, hsize, a2);
-      const double *s1 = hist_elem<D>(m, s, ch, i1), *s2 = hist_elem<D>(m, s, ch, i2);
+      const double *s1, *s2;
+      if (mixing) { s1 = wde_state_mixed<D, MODE>(m, s, w, ch, p, rs, 1, a1, mx); s2 = wde_state_mixed<D, MODE>(m, s, w, ch, p, rs, 2, a2, mx); }
+      else {
+        const int i1 = wde_index<D, MODE>(m, s, ch, p, rs, wA[3], 1, hsize, a1);
+        const int i2 = wde_index<D, MODE>(m, s, ch, p, rs, wB[0], 2, hsize, a2);
+        s1 = hist_elem<D>(m, s, ch, i1); s2 = hist_elem<D>(m, s, ch, i2);
+      }
       double dot = 0;
 #pragma unroll
       for (int i = 0; i < D; i++) {
@@ -445,6 +540,7 @@ __device__ __forceinline__ MhOut wmh_step(const PtgModel &m, const PtgState &s, 
   }
   if (do_mh) {
     ch.ntries++;
+    if (adaptive) set_adapt(m, s, ch.chain, member, accept, ch.beta);
     if (accept) {
       ch.naccept++;
       ch.last_type = type;
@@ -469,9 +565,11 @@ template <int D, int MODE>
 __global__ void __launch_bounds__(128, PTG_WSTEP_MINB) ptg_wstep_kernel(const __grid_constant__ PtgModel m, PtgState s, long long step0, int n_steps, int W) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *sbins = reinterpret_cast<double *>(smem_raw); // [R][n_props]
+  __shared__ WMix smix[4];
   const int R = m.n_rungs;
   for (int i = threadIdx.x; i < R * m.n_props; i += blockDim.x) sbins[i] = m.bins[i];
   __syncthreads();
+  WMix &mx = smix[threadIdx.x >> 5];
 
   WLane w;
   w.W = W; w.R = R; w.lane = threadIdx.x & 31;
@@ -526,7 +624,13 @@ __global__ void __launch_bounds__(128, PTG_WSTEP_MINB) ptg_wstep_kernel(const __
     __syncwarp();
     rs.step = step;
     const bool do_mh = w.active && napp == 0;
-    MhOut o = wmh_step<D, MODE>(m, s, w, ch, rs, bins, do_mh, stream_base);
+    if (m.de_mixing) { // history_freeze (chain.cc:1552): what the other rungs of the ladder see of this chain during the MH phase
+      const bool wrapped = ch.nsize > m.hist_cap;
+      mx.size[w.lane] = (int)(wrapped ? (long long)m.hist_cap : ch.nsize); mx.off[w.lane] = wrapped ? ch.slot : 0; mx.beta[w.lane] = ch.beta;
+      __syncwarp();
+    }
+    MhOut o = wmh_step<D, MODE>(m, s, w, ch, rs, bins, do_mh, stream_base, mx);
+    if (m.de_mixing) __syncwarp();
     if (w.active && (long long)step < m.trace_steps) {
       s.trace_lhr[step * m.n_chains + chain] = do_mh ? o.lhr : 0.0;
       s.trace_code[step * m.n_chains + chain] = do_mh ? o.code : PTG_TRACE_SWAPPED;

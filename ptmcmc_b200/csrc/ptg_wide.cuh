@@ -46,7 +46,7 @@ struct XShared {
     iswap = i; i += PTG_SWAP_SLOTS;
   }
 };
-static inline size_t ptg_xshared_bytes(int R, int DP, int NP) {
+static __host__ __device__ inline size_t ptg_xshared_bytes(int R, int DP, int NP) {
   size_t b = sizeof(double) * ((size_t)(3 * ((R + 7) & ~7) + 2) * DP + (size_t)R * 11 + 3 * PTG_SWAP_SLOTS + (size_t)R * NP) + sizeof(long long) * 2 * (size_t)R +
              sizeof(int) * ((size_t)R * 8 + PTG_SWAP_SLOTS);
   return (b + 15) & ~(size_t)15;
@@ -140,7 +140,7 @@ __device__ __forceinline__ double xprior(const PtgModel &m, const double x[CPL],
   }
   __syncwarp();
 #pragma unroll
-  for (int k = 0; k < CPL; k++) { const int c = CPL * lane + k; if (c < D) row[c] = pdf1d(m.prior_w[c], x[k]); }
+  for (int k = 0; k < CPL; k++) { const int c = CPL * lane + k; if (c < D) row[c] = prior_factor(m.prior_w[c], x[k], m.lower_w[c], m.upper_w[c], m.xmin_w[c], m.xmax_w[c]); }
   __syncwarp();
   double result = 1;
   for (int j = 0; j < D; j++) result *= row[j];
@@ -275,7 +275,7 @@ __device__ __forceinline__ bool xprior_draw(const PtgModel &m, Stream<MODE> &rs,
       if (c < D) {
         uint32_t w[4]; rs.fetch(blk0 + c, w);
         const PtgPrior1D p = m.prior_w[c];
-        if (p.kind == PTG_PRIOR_GAUSSIAN) { double z0, z1; box_muller(w, z0, z1); x[k] = z0 * p.b + p.a; }
+        if (p.kind == PTG_PRIOR_GAUSSIAN || p.kind == PTG_PRIOR_GAUSSIAN_WRAPPED) { double z0, z1; box_muller(w, z0, z1); x[k] = z0 * p.b + p.a; }
         else x[k] = invcdf1d(p, ptg_u52_to_unit(w[0], w[1]));
       }
     }
@@ -285,7 +285,7 @@ __device__ __forceinline__ bool xprior_draw(const PtgModel &m, Stream<MODE> &rs,
 #pragma unroll
     for (int kk = 0; kk < CPL; kk++) x[kk] = 0;
     for (int i = 0; i < D; i++) {
-      const bool g = m.prior_w[i].kind == PTG_PRIOR_GAUSSIAN;
+      const bool g = m.prior_w[i].kind == PTG_PRIOR_GAUSSIAN || m.prior_w[i].kind == PTG_PRIOR_GAUSSIAN_WRAPPED;
       const int owner = i / CPL, k = i - owner * CPL;
       if (owner == lane) {
         const PtgPrior1D p = m.prior_w[i];

@@ -1,0 +1,367 @@
+// ptg_wide_pipe.cuh -- the PIPELINED warp-per-chain production kernel for the full-covariance Gaussian workload (BASELINE config D:
+// d = 100, eigen-rotated Gaussian proposal + differential evolution; Philox draws).  Same arithmetic as ptg_xmstep_kernel
+// (ptg_wide_mma.cuh) -- chains are bit-identical between the two -- restructured around what the round-1 profile showed: the FP64
+// tensor pipe ran 10 % of the time because every DMMA operand came through L1 / L2 behind a dependent load, seven CTA barriers
+// separated the phases, and the ladder's swap phase ran on warp 0 while 23 warps waited.
+//
+//  * Both dim x dim matrices (rotation M and Cinv) are RESIDENT IN SHARED MEMORY for the whole launch, rows padded to a stride of
+//    DS = 8 (mod 16) doubles so that the 128-bit fragment loads of the eight row groups of an MMA are bank-conflict free.
+//  * One CTA = one ladder = n_rungs chain warps + ONE LADDER WARP.  The ladder warp runs the swap phase (chain.cc:1410-1538) on
+//    shuffles while the chain warps run the rotation contraction; nobody waits for it.
+//  * Everything of a proposal that does not depend on the swap outcome (Philox blocks, member selection, the Gaussian offsets z o sigma,
+//    the DE history indices -- their records are only PREFETCHED into L2 here) is done BEFORE the swap barrier; a rung that turns out to
+//    have been in a swap trial discards it (as the reference skips its MH step, chain.cc:1553-1558).
+//  * The rotation contracts only the rows of Gaussian-proposal chains (row indirection, 8-row tiles), the quadratic form only gated rows.
+//  * Four barriers per PT iteration instead of seven; the current states that swapped rungs exchange travel through a small global
+//    scratch row per chain (L2 resident) instead of a third shared-memory row buffer, which is what lets both matrices fit.
+//
+//    S1  publish scalars + x (scratch); prep: draws, member, offsets -> OFF rows, prefetch DE records            | ladder warp: swap draws
+//    -- barrier (all) --
+//    S2  T = OFF M^T on DMMA (Gaussian rows)                                                                       | ladder warp: swap phase
+//    -- barrier (all) --
+//    S3  swapped rungs append / take over states; MH rungs: proposal, enforce, prior, gate -> NEWX rows
+//    -- barrier (chain warps) --
+//    S4  Y = NEWX Cinv^T on DMMA (gated rows)
+//    -- barrier (chain warps) --
+//    S5  quadratic form, Metropolis test, append
+#pragma once
+#include "ptg_wide_mma.cuh"
+
+struct XPShared {
+  double *Ms, *Cs;            // [D][DS] each, resident matrices (row n of the matrix = output component n)
+  double *bufA, *bufB;        // [RP + 2][DS]: OFF / NEWX rows ; T / Y rows.  Row RP of bufA = zeros (padding rows of an MMA tile), row RP of bufB = dump
+  double *plo, *phi;          // [32 CPL] prior box edges (all-uniform prior)
+  int *kindflag;              // [R]: 1 = row of the rotation (set in S1), 2 = row of the quadratic form (set in S3)
+};
+
+static inline int ptg_xp_stride(int D) { int ds = (D + 7) & ~7; while ((ds & 15) != 8) ds += 8; return ds; }
+static inline size_t ptg_xp_shared_bytes(int R, int D, int NP, int CPL) {
+  const int DS = ptg_xp_stride(D), RP = (R + 7) & ~7;
+  size_t b = ptg_xshared_bytes(R, 0, NP);                                   // the ladder scalars / swap outcome block of XShared (no row buffers)
+  b += sizeof(double) * ((size_t)2 * D * DS + (size_t)2 * (RP + 2) * DS + 2 * (size_t)32 * CPL);
+  b += sizeof(int) * ((size_t)R + 8);
+  return (b + 15) & ~(size_t)15;
+}
+
+// Out[row][n] = sum_k In[row][k] * Bs[n][k] for the rows whose bit is set in `mask` (8-row MMA tiles; padding rows read the zero row
+// `pad_row` of In and write the dump row `pad_row` of Out); Bs in shared memory with row stride DS.  k is consumed in the same permuted
+// order as xcta_dmma (D % 4 == 0: lane t takes elements (2t, 2t+1) of each group of 8 for two consecutive MMAs), so every output row
+// is bit-identical with the L1-streamed version.  Called by the `nwarps` chain warps.
+__device__ __forceinline__ void xp_dmma(const double *In, const double *Bs, double *Out, unsigned mask, int D, int DS, int pad_row, int warp, int nwarps, int lane) {
+  const int cnt = __popc(mask);
+  const int mt_n = (cnt + 7) >> 3, nt_n = (D + 7) >> 3;
+  const int g = lane >> 2, t = lane & 3;
+  const int K8 = D & ~7;
+  for (int tile = warp; tile < mt_n * nt_n; tile += nwarps) {
+    const int mt = tile / nt_n, nt = tile - mt * nt_n;
+    const int ridx = mt * 8 + g;
+    const int row = (ridx < cnt) ? (int)__fns(mask, 0, ridx + 1) : pad_row;
+    const double *arow = In + (size_t)row * DS;
+    int n = nt * 8 + g;
+    if (n >= D) n = D - 1;
+    const double *brow = Bs + (size_t)n * DS;
+    double c0 = 0, c1 = 0;
+#pragma unroll 4
+    for (int k0 = 0; k0 < K8; k0 += 8) {
+      const double2 a2 = *reinterpret_cast<const double2 *>(arow + k0 + 2 * t);
+      const double2 b2 = *reinterpret_cast<const double2 *>(brow + k0 + 2 * t);
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a2.x), "d"(b2.x));
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a2.y), "d"(b2.y));
+    }
+    for (int k0 = K8; k0 < D; k0 += 4) { // tail: columns >= D of both operands are zero in shared memory
+      const int k = k0 + t;
+      const double a = arow[k], b = brow[k];
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+    }
+    double *orow = Out + (size_t)row * DS + nt * 8 + 2 * t; // accumulator fragment: lane g*4+t holds C[g][2t..2t+1]
+    orow[0] = c0; orow[1] = c1;
+  }
+}
+
+__device__ __forceinline__ void xp_bar_chains(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
+
+template <int CPL, int MAXT>
+__global__ void __launch_bounds__(MAXT) ptg_xpstep_kernel(const __grid_constant__ PtgModel m, PtgState s, long long step0, int n_steps, int trans_off, double *xscratch) {
+  constexpr int MODE = PTG_RNG_PHILOX;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int R = m.n_rungs, D = m.dim, NP = m.n_props, RP = (R + 7) & ~7;
+  const int DS = ((D + 7) & ~7) + ((((D + 7) & ~7) & 15) == 8 ? 0 : 8);
+  XShared L;
+  L.carve(smem_raw, R, 0, NP);
+  XPShared P;
+  {
+    double *d = reinterpret_cast<double *>(smem_raw + ptg_xshared_bytes(R, 0, NP));
+    P.Ms = d; d += (size_t)D * DS; P.Cs = d; d += (size_t)D * DS;
+    P.bufA = d; d += (size_t)(RP + 2) * DS; P.bufB = d; d += (size_t)(RP + 2) * DS;
+    P.plo = d; d += 32 * CPL; P.phi = d; d += 32 * CPL;
+    P.kindflag = reinterpret_cast<int *>(d);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool is_ladder_warp = (warp == R);
+  const int rung = is_ladder_warp ? 0 : warp;
+  const int nchain_threads = 32 * R;
+  const long long ladder = blockIdx.x;
+  const long long chain = ladder * R + rung;
+  // ---- one-time staging: matrices, zero / padding rows, box edges, bins
+  {
+    const double *__restrict__ Mg = m.prop_data + trans_off, *__restrict__ Cg = m.ldata;
+    for (int i = threadIdx.x; i < D * DS; i += blockDim.x) {
+      const int r = i / DS, c = i - r * DS;
+      P.Ms[i] = (c < D) ? __ldg(Mg + (size_t)r * D + c) : 0.0;
+      P.Cs[i] = (c < D) ? __ldg(Cg + (size_t)r * D + c) : 0.0;
+    }
+    for (int i = threadIdx.x; i < (RP + 2) * DS; i += blockDim.x) { P.bufA[i] = 0; P.bufB[i] = 0; }
+    for (int c = threadIdx.x; c < 32 * CPL; c += blockDim.x) {
+      P.plo[c] = (c < D && m.all_uniform_prior) ? m.prior_w[c].a : -CUDART_INF;
+      P.phi[c] = (c < D && m.all_uniform_prior) ? m.prior_w[c].b : CUDART_INF;
+    }
+    for (int i = threadIdx.x; i < R * NP; i += blockDim.x) L.sbins[i] = m.bins[i];
+  }
+  double *rowA = P.bufA + (size_t)rung * DS, *rowB = P.bufB + (size_t)rung * DS;
+  double *myscratch = xscratch + ((size_t)blockIdx.x * R + rung) * (size_t)(32 * CPL);
+  const double *ladscratch = xscratch + (size_t)blockIdx.x * R * (size_t)(32 * CPL);
+
+  XChain<CPL> ch;
+  ch.chain = chain;
+  Stream<MODE> rs;
+  if (!is_ladder_warp) {
+#pragma unroll
+    for (int k = 0; k < CPL; k++) { const int c = CPL * lane + k; ch.x[k] = (c < D) ? s.cur_x[(long long)c * m.n_chains + chain] : 0.0; }
+    ch.lpost = s.lpost[chain]; ch.llike = s.llike[chain]; ch.lprior = s.lprior[chain]; ch.beta = s.beta[chain]; ch.map_lpost = s.map_lpost[chain];
+    ch.nhist = s.nhist[chain]; ch.nsize = s.nsize[chain]; ch.ntries = s.ntries[chain]; ch.naccept = s.naccept[chain]; ch.last_type = s.last_type[chain];
+    ch.slot = (int)(ch.nsize % m.hist_cap); ch.since_save = (int)(ch.nhist % m.save_every);
+    stream_open<MODE>(m, s, rs, chain, (uint64_t)(m.ladder_offset + ladder) * PTG_STREAM_STRIDE + (uint64_t)rung, PTG_DOMAIN_STEP);
+    if (lane == 0) {
+      L.dir[rung] = s.directions[chain]; L.ups[rung] = s.ups[chain]; L.downs[rung] = s.downs[chain]; L.inst[rung] = s.instances[chain];
+      L.scount[rung] = 0; L.saccept[rung] = 0;
+    }
+  } else stream_blank<MODE>(m, rs);
+  const int maxswaps = m.maxswaps;
+  const double swap_thresh = (R - 1) * m.swap_rate / maxswaps;
+  double ptry = 2 * m.swap_rate; if (ptry > 1) ptry = 1;
+  const double *bins = L.sbins + (size_t)rung * NP;
+  const uint64_t ladder_stream = (uint64_t)(m.ladder_offset + ladder) * PTG_STREAM_STRIDE + PTG_STREAM_LADDER;
+  __syncthreads();
+
+  for (int it = 0; it < n_steps; it++) {
+    const uint64_t step = (uint64_t)(step0 + it);
+    // ================================================================ S1: publish + everything that does not depend on the swap outcome
+    double off[CPL];
+    int type = 0, member = 0, kind = 0, i1 = 0, i2 = 0, iz = 0, az = 0;
+    bool snooker = false, need_t = false;
+    double gamma = 0;
+    uint32_t wB[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int k = 0; k < CPL; k++) off[k] = 0;
+    int hsize = 0;
+    if (!is_ladder_warp) {
+#pragma unroll
+      for (int k = 0; k < CPL; k++) myscratch[CPL * lane + k] = ch.x[k];      // states of swapped rungs travel through this row
+      if (lane == 0) {
+        L.sll[rung] = ch.llike; L.slpost[rung] = ch.lpost; L.slprior[rung] = ch.lprior; L.sbeta[rung] = ch.beta;
+        L.n_lpost[rung] = ch.lpost; L.n_beta[rung] = ch.beta; L.perm[rung] = rung; L.napp[rung] = 0;
+      }
+      rs.step = step;
+      hsize = (int)(ch.nsize > m.hist_cap ? (long long)m.hist_cap : ch.nsize);
+      uint32_t wA[4];
+      rs.fetch(PTG_BLK_A, wA); rs.fetch(PTG_BLK_B, wB);
+      if (m.wrap_in_set) {
+        member = -1;
+        const double x = (NP > 1) ? ptg_u32_to_unit(wA[0]) : 0.0;
+        for (int i = 0; i < NP; i++) {
+          const bool ready = (m.props[i].kind != PTG_PROP_DE) || hsize >= D * 10;
+          if (member < 0 && ready && x < bins[i]) member = i;
+        }
+        if (member < 0) { rs.err = 2; member = 0; }
+      }
+      const PtgProp &p = m.props[member];
+      kind = p.kind;
+      if (kind == PTG_PROP_DE) {
+        const double usnk = ptg_u32_to_unit(wA[1]), ug = ptg_u32_to_unit(wA[2]);
+        snooker = p.snooker > usnk;
+        int a1 = 0, a2 = 0;
+        if (!snooker) { gamma = p.gamma_std; if (ug < p.g1frac) gamma = 1; }
+        else {
+          gamma = (1.2 + ug) / p.reduce_gamma;
+          iz = xde_index<CPL, MODE>(m, s, ch, p, rs, wB[1], 0, hsize, az);
+        }
+        i1 = xde_index<CPL, MODE>(m, s, ch, p, rs, wA[3], 1, hsize, a1);
+        i2 = xde_index<CPL, MODE>(m, s, ch, p, rs, wB[0], 2, hsize, a2);
+        // pull the records towards the SM while the rotation runs: one 128-byte line per lane
+        const int nline = (D * 8 + 127) >> 7;
+        if (lane < nline) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(xhist<CPL>(m, s, ch, i1) + lane * 16));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(xhist<CPL>(m, s, ch, i2) + lane * 16));
+          if (snooker) asm volatile("prefetch.global.L2 [%0];" ::"l"(xhist<CPL>(m, s, ch, iz) + lane * 16));
+        }
+      } else if (kind == PTG_PROP_GAUSS) {
+        xnormals<CPL, MODE>(m, rs, off, lane);
+        const double *__restrict__ sig = m.prop_data + p.sigma_off;
+#pragma unroll
+        for (int k = 0; k < CPL; k++) { const int c = CPL * lane + k; off[k] = (c < D) ? off[k] * __ldg(sig + c) + 0.0 : 0.0; }
+        if (p.one_d_frac > 0 && ptg_u32_to_unit(wA[1]) < p.one_d_frac) {
+          const int ia = (int)(D * ptg_u32_to_unit(wA[2]));
+#pragma unroll
+          for (int k = 0; k < CPL; k++) if (CPL * lane + k != ia) off[k] = 0.0;
+          type = 1;
+        }
+        if (p.has_transform) {
+          if (p.trans_off == trans_off) need_t = true;                             // the batched DMMA rotation of S2
+          else xtransform<CPL>(m, m.prop_data + p.trans_off, off, rowB, lane);       // a second, different matrix: exact per-warp path
+        }
+      }
+      if (need_t) {
+#pragma unroll
+        for (int k = 0; k < CPL; k++) { const int c = CPL * lane + k; if (c < D) rowA[c] = off[k]; }
+      }
+      if (lane == 0) P.kindflag[rung] = need_t ? 1 : 0;
+    }
+    __syncthreads();
+    // ================================================================ S2: rotation on the tensor cores | swap phase on the ladder warp
+    if (is_ladder_warp) {
+      if (R > 1) xswap_warp(m, L, ladder_stream, step, lane, maxswaps, swap_thresh, ptry);
+    } else {
+      // rows of the rotation: every warp derives the same list from the flags (ballot over the rungs)
+      const unsigned mask = __ballot_sync(0xffffffffu, lane < R && P.kindflag[lane] == 1);
+      if (mask) xp_dmma(P.bufA, P.Ms, P.bufB, mask, D, DS, RP, warp, R, lane);
+    }
+    __syncthreads();
+    if (is_ladder_warp) { // the ladder warp sits out the chain-only barriers; it meets the chain warps again at the next iteration's first barrier
+      continue;
+    }
+    // ================================================================ S3: swap outcome; proposal, enforce, prior, gate
+    const int na = L.napp[rung];
+    ch.beta = L.n_beta[rung];
+    const bool mh = (na == 0);
+    double newx[CPL];
+    double prop_lh = 0;
+#pragma unroll
+    for (int k = 0; k < CPL; k++) newx[k] = ch.x[k];
+    if (!mh) {
+      // xswapped_rung with the published states in the global scratch rows
+      for (int k = 0; k < 2 && k < na; k++) {
+        const int src = L.app_src[2 * rung + k];
+        double xs[CPL];
+#pragma unroll
+        for (int q = 0; q < CPL; q++) xs[q] = ladscratch[(size_t)src * (32 * CPL) + CPL * lane + q];
+        xappend<CPL>(m, s, ch, xs, L.sll[src], L.app_lpost[2 * rung + k], L.app_beta[2 * rung + k], lane);
+      }
+      const int src = L.perm[rung];
+#pragma unroll
+      for (int q = 0; q < CPL; q++) ch.x[q] = ladscratch[(size_t)src * (32 * CPL) + CPL * lane + q];
+      ch.llike = L.sll[src]; ch.lprior = L.slprior[src]; ch.lpost = L.n_lpost[rung];
+    } else if (m.evolve_rate > 0) ch.lpost = L.n_lpost[rung];
+    const double oldlprior = ch.lpost - ch.beta * ch.llike;
+    bool valid = m.zero_valid != 0, gate = false;
+    double newlprior = -CUDART_INF;
+    if (mh) {
+      const PtgProp &p = m.props[member];
+      if (kind == PTG_PROP_DE) {
+        if (!snooker) {
+          double a[CPL], b[CPL];
+          xload_rec<CPL>(xhist<CPL>(m, s, ch, i1), a, lane, D);
+          xload_rec<CPL>(xhist<CPL>(m, s, ch, i2), b, lane, D);
+#pragma unroll
+          for (int k = 0; k < CPL; k++) { const double t = ch.x[k] + a[k] * gamma; newx[k] = t + b[k] * (-gamma); }
+        } else {
+          double smznorm2 = 0, minusz[CPL], smz[CPL], t[CPL];
+          int isafe = 0;
+          while (true) {
+            double zz[CPL];
+            xload_rec<CPL>(xhist<CPL>(m, s, ch, iz), zz, lane, D);
+#pragma unroll
+            for (int k = 0; k < CPL; k++) { minusz[k] = zz[k] * (-1); smz[k] = ch.x[k] + minusz[k]; t[k] = smz[k] * smz[k]; }
+            smznorm2 = xsum_tree<CPL>(t);
+            if (++isafe > 1000 || smznorm2 != 0) break;
+            iz = xde_index<CPL, MODE>(m, s, ch, p, rs, wB[1], 0, hsize, az);
+          }
+          double a[CPL], b[CPL];
+          xload_rec<CPL>(xhist<CPL>(m, s, ch, i1), a, lane, D);
+          xload_rec<CPL>(xhist<CPL>(m, s, ch, i2), b, lane, D);
+#pragma unroll
+          for (int k = 0; k < CPL; k++) { const double ds12 = a[k] * gamma + b[k] * (-gamma); t[k] = ds12 * smz[k]; }
+          const double fac = xsum_tree<CPL>(t) / smznorm2;
+#pragma unroll
+          for (int k = 0; k < CPL; k++) { newx[k] = ch.x[k] + smz[k] * fac; const double pmz = newx[k] + minusz[k]; t[k] = pmz * pmz; }
+          prop_lh = (log(xsum_tree<CPL>(t)) - log(smznorm2)) * (D - 1) / 2.0;
+          type = 1;
+        }
+      } else if (kind == PTG_PROP_GAUSS) {
+        if (need_t) {
+#pragma unroll
+          for (int k = 0; k < CPL; k++) { const int c = CPL * lane + k; off[k] = (c < D) ? rowB[c] : 0.0; }
+        }
+#pragma unroll
+        for (int k = 0; k < CPL; k++) newx[k] = ch.x[k] + off[k];
+      }
+      if (m.wrap_in_set) type = member + 10 * type;
+      if (valid) valid = xenforce<CPL>(m, newx, lane);
+      if (m.all_uniform_prior) {
+        bool in = valid;
+#pragma unroll
+        for (int k = 0; k < CPL; k++) in = in && !(newx[k] < P.plo[CPL * lane + k]) && !(newx[k] > P.phi[CPL * lane + k]);
+        newlprior = __all_sync(0xffffffffu, in) ? m.uniform_lprior : -CUDART_INF;
+      } else newlprior = xprior<CPL>(m, newx, valid, rowB, lane);
+      gate = valid && ((newlprior > -1e200) || (newlprior - oldlprior > m.dprior_min));
+    }
+    __syncwarp();
+    if (mh && gate) {
+#pragma unroll
+      for (int k = 0; k < CPL; k++) { const int c = CPL * lane + k; if (c < D) rowA[c] = newx[k]; }
+    }
+    if (lane == 0) P.kindflag[rung] = (mh && gate) ? 2 : 0;
+    xp_bar_chains(nchain_threads);
+    // ================================================================ S4: quadratic form rows Y = NEWX Cinv^T on the tensor cores
+    {
+      const unsigned mask = __ballot_sync(0xffffffffu, lane < R && P.kindflag[lane] == 2);
+      if (mask) xp_dmma(P.bufA, P.Cs, P.bufB, mask, D, DS, RP, warp, R, lane);
+    }
+    xp_bar_chains(nchain_threads);
+    // ================================================================ S5: quadratic form, Metropolis test, append
+    double newlike = -CUDART_INF, newlpost = -CUDART_INF;
+    if (mh && gate) {
+      double t[CPL];
+#pragma unroll
+      for (int k = 0; k < CPL; k++) { const int c = CPL * lane + k; t[k] = (c < D) ? newx[k] * rowB[c] : 0.0; }
+      newlike = __ldg(m.lparams) - 0.5 * xsum_tree<CPL>(t);
+      if (!isfinite(newlike)) newlike = -CUDART_INF;
+    }
+    double lhr = 0; int code = PTG_TRACE_SWAPPED;
+    if (mh) {
+      code = 0;
+      bool accept = true;
+      if (gate) newlpost = newlike * ch.beta + newlprior; else code |= PTG_TRACE_NOLIKE;
+      lhr = prop_lh;
+      if (isnan(lhr)) accept = false;
+      lhr += newlpost - ch.lpost;
+      if (!valid) { accept = false; code |= PTG_TRACE_INVALID; }
+      if (accept && lhr < 0) accept = (log(ptg_u52_to_unit(wB[2], wB[3])) < lhr);
+      ch.ntries++;
+      if (accept) {
+        ch.naccept++;
+        ch.last_type = type;
+#pragma unroll
+        for (int k = 0; k < CPL; k++) ch.x[k] = newx[k];
+        ch.llike = newlike; ch.lpost = newlpost; ch.lprior = newlprior;
+        code |= PTG_TRACE_ACCEPT;
+      }
+      xappend<CPL>(m, s, ch, ch.x, ch.llike, ch.lpost, ch.beta, lane);
+      code |= (type & PTG_TRACE_TYPE_MASK);
+    }
+    if (lane == 0 && (long long)step < m.trace_steps) {
+      s.trace_lhr[step * m.n_chains + chain] = lhr;
+      s.trace_code[step * m.n_chains + chain] = code;
+    }
+  }
+  __syncthreads();
+  if (is_ladder_warp) return;
+#pragma unroll
+  for (int k = 0; k < CPL; k++) { const int c = CPL * lane + k; if (c < D) s.cur_x[(long long)c * m.n_chains + chain] = ch.x[k]; }
+  if (lane == 0) {
+    s.lpost[chain] = ch.lpost; s.llike[chain] = ch.llike; s.lprior[chain] = ch.lprior; s.beta[chain] = ch.beta; s.map_lpost[chain] = ch.map_lpost;
+    s.nhist[chain] = ch.nhist; s.nsize[chain] = ch.nsize; s.ntries[chain] = ch.ntries; s.naccept[chain] = ch.naccept; s.last_type[chain] = ch.last_type;
+    stream_close<MODE>(s, rs, chain);
+    s.directions[chain] = L.dir[rung]; s.ups[chain] = L.ups[rung]; s.downs[chain] = L.downs[rung]; s.instances[chain] = L.inst[rung];
+    s.swap_count[chain] += L.scount[rung]; s.swap_accept[chain] += L.saccept[rung];
+  }
+}

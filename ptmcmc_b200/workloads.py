@@ -91,6 +91,8 @@ class Spec:
             api.set_prior([K.PRIOR_UNIFORM] * d, self.centers - self.halfwidths, self.centers + self.halfwidths)
         elif self.prior == "gaussian":
             api.set_prior([K.PRIOR_GAUSSIAN] * d, self.centers, self.halfwidths)
+        elif self.prior == "gaussian_wrap":   # gaussian_dist_product(..., wrap_probability = true)
+            api.set_prior([K.PRIOR_GAUSSIAN_WRAPPED] * d, self.centers, self.halfwidths)
         else:
             api.set_prior(*self.prior_ab())
         e = self.extra
@@ -150,6 +152,11 @@ class Spec:
             api.set_proposals([de2, dict(kind=K.PROP_PRIOR_DRAW, share=f, hot_share=e.get("hot_prior", 1.0) if Tpow > 0 else 0.0)], Tpow=Tpow)
         else:
             raise ValueError(self.prop)
+        if e.get("adapt_rate", 0) != 0 or e.get("de_mixing", 0):
+            bare = self.prop in ("de", "gauss", "cov")
+            # inside a set the reference never mixes (chain.cc:1375 asks the set, which does not support mixing): only a bare DE does
+            api.set_proposal_options(adapt_rate=e.get("adapt_rate", 0.0), de_mixing=bool(e.get("de_mixing", 0)) and bare,
+                                     de_Tmix=e.get("de_Tmix", 1.0 if bare else 300.0))
 
     # ---------------------------------------------------------------- reference side
     def ref_args(self, tmpdir, steps, out):

@@ -132,6 +132,20 @@ def parity_cases():
         ("shells_d3_pair", Spec("shells", 3, 6, centers=[0, 0, 0], halfwidths=[6, 6, 6], seed=0.43, Tmax=100, extra=dict(shell_spm=1.5)), 600, 1),
         ("shells_d2_logx", Spec("shells", 2, 6, centers=[np.exp(0.001) * np.sqrt(np.exp(5.998)), 0.0], halfwidths=[np.sqrt(np.exp(5.998)), 6.0], prior="mixed",
                                 prior_types=[5, 1], seed=0.59, Tmax=100, extra=dict(shell_logx=1)), 600, 1),
+        # adaptive shares of the set (proposal_distribution.cc:132-166): every rung's clone adapts its own shares; with Tpow > 0 the
+        # rebuilt bins follow the rung's CURRENT temperature (evolving here)
+        ("adaptive_shares_default", Spec("gauss", 2, 6, centers=[2, -3], halfwidths=[2, 3], seed=0.67, Tmax=100, extra=dict(adapt_rate=0.05)), 1200, 2),
+        ("adaptive_shares_Tpow_evolve", Spec("sines", 2, 6, prop="prior", seed=0.73, evolve_rate=0.01,
+                                             extra=dict(Tpow=1.5, prior_draw_frac=0.2, hot_de=0.4, hot_prior=0.6, adapt_rate=0.2)), 1000, 1),
+        # the wrapped Gaussian prior (probability_function.cc:57-78): images of the wrapped dimensions are added to the pdf
+        ("gaussian_wrap_prior", Spec("gauss", 3, 5, centers=[0.5, -1.0, 2.0], halfwidths=[0.8, 1.5, 0.6], prior="gaussian_wrap", bound="wow",
+                                     seed=0.79, Tmax=50, extra=dict(sigma=2.5)), 800, 2),
+        # temperature mixing of the history draws (proposal_distribution.cc:594-741): a bare differential_evolution with
+        # support_mixing(true) on the ladder; and the same flag inside the default set, where the reference never mixes (chain.cc:1375)
+        ("de_mixing_bare", Spec("gauss", 2, 5, centers=[2, -3], halfwidths=[2, 3], prop="de", seed=0.89, Tmax=100, de_ni=20,
+                                extra=dict(de_mixing=1, de_Tmix=3.0)), 400, 2),
+        ("de_mixing_sines_R8", Spec("sines", 2, 8, prop="de", seed=0.97, de_ni=15, swap_rate=0.3, extra=dict(de_mixing=1, de_Tmix=300.0, de_snooker=0.3)), 300, 1),
+        ("de_mixing_inert_in_set", Spec("gauss", 2, 4, centers=[2, -3], halfwidths=[2, 3], seed=0.93, Tmax=100, extra=dict(de_mixing=1, de_Tmix=300.0)), 400, 1),
     ] + wide_cases()
 
 

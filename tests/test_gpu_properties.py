@@ -435,3 +435,25 @@ def test_device_ess_recipe_matches_host_recipe(engine_cls):
         with pytest.raises(Exception):
             e.get_autocovar_windows(0, 1000, 50, [0, 1], 2)       # windows older than the chain
         e.close()
+
+
+@pytest.mark.parametrize("d,R,L,kw", [(100, 24, 5, {}), (100, 24, 3, dict(evolve_rate=0.01, swap_rate=0.3)), (40, 6, 7, {}), (20, 4, 9, dict(save_every=3)),
+                                       (64, 15, 3, {}), (100, 31, 2, dict(swap_rate=0.05))])
+def test_pipelined_fullcov_kernel_is_bit_identical(d, R, L, kw, engine_cls):
+    """the pipelined full-covariance kernel (ptg_wide_pipe.cuh: matrices resident in shared memory, ladder warp, rows of the contractions
+    picked by indirection) against the round-1 L1-streamed DMMA kernel (pinned with KERNEL_SHARED): same chains bit for bit"""
+    from tests.models import fullcov_spec
+    spec = fullcov_spec(d, R, Tmax=1e4, de_ni=11, prop="covde", **kw)
+    spec.extra["gauss_1d_frac"] = 0.2
+    runs = []
+    for kern in (K.KERNEL_AUTO, K.KERNEL_SHARED):
+        e = engine_cls(spec.config(n_ladders=L, rng_mode=K.RNG_PHILOX, hist_capacity=11 * d + 700, record_level=K.RECORD_FULL, trace_steps=300))
+        e.select_kernel(kern); spec.setup(e); e.init_from_prior(); e.step(120); e.step(180); e.synchronize()
+        cur, cnt = e.get_current(), e.get_counters()
+        n = int(cnt["nsize"][R - 1])
+        h = e.get_history(L - 1, R - 1, 0, int(cnt["nsize"][(L - 1) * R + R - 1]))
+        runs.append((cur["x"].tobytes(), cur["lpost"].tobytes(), cur["beta"].tobytes(), cnt["naccept"].tobytes(), cnt["nsize"].tobytes(), h["x"].tobytes(),
+                     h["lpost"].tobytes(), e.get_trace(0, 300)[1].tobytes(), e.get_swap_stats()["swap_accept"].tobytes()))
+        e.close()
+    for a, b in zip(*runs):
+        assert a == b
