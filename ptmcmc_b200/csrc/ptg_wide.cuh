@@ -32,7 +32,7 @@ struct XShared {
   double *n_lpost, *n_beta, *app_lpost, *app_beta, *split, *udraw, *sbins; // [R],[R],[2R],[2R],[R],[3*SLOTS],[R*NP]
   long long *scount, *saccept;                    // [R]
   int *perm, *napp, *app_src, *dir, *ups, *downs, *inst, *iswap; // [R],[R],[2R],[R]x4,[SLOTS]
-  __device__ void carve(unsigned char *base, int R, int DP, int NP) {
+  __host__ __device__ void carve(unsigned char *base, int R, int DP, int NP) {
     double *d = reinterpret_cast<double *>(base);
     const int RP = (R + 7) & ~7; // the DMMA kernel treats rowA / rowB as [RP][DP] matrices (8-row tiles)
     sx = d; d += (size_t)RP * DP; rowA = d; d += (size_t)RP * DP; rowB = d; d += (size_t)(RP + 2) * DP; // +2 rows: prior box edges (DMMA kernel)

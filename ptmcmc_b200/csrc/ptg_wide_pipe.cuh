@@ -6,8 +6,8 @@
 //
 //  * Both dim x dim matrices (rotation M and Cinv) are RESIDENT IN SHARED MEMORY for the whole launch, rows padded to a stride of
 //    DS = 8 (mod 16) doubles so that the 128-bit fragment loads of the eight row groups of an MMA are bank-conflict free.
-//  * One CTA = one ladder = n_rungs chain warps + ONE LADDER WARP.  The ladder warp runs the swap phase (chain.cc:1410-1538) on
-//    shuffles while the chain warps run the rotation contraction; nobody waits for it.
+//  * One CTA = one ladder, one warp per chain.  The hottest rung's warp runs the ladder's swap phase (chain.cc:1410-1538) on shuffles
+//    WHILE the other warps run the rotation contraction; nobody waits for it.
 //  * Everything of a proposal that does not depend on the swap outcome (Philox blocks, member selection, the Gaussian offsets z o sigma,
 //    the DE history indices -- their records are only PREFETCHED into L2 here) is done BEFORE the swap barrier; a rung that turns out to
 //    have been in a swap trial discards it (as the reference skips its MH step, chain.cc:1553-1558).
@@ -15,14 +15,17 @@
 //  * Four barriers per PT iteration instead of seven; the current states that swapped rungs exchange travel through a small global
 //    scratch row per chain (L2 resident) instead of a third shared-memory row buffer, which is what lets both matrices fit.
 //
-//    S1  publish scalars + x (scratch); prep: draws, member, offsets -> OFF rows, prefetch DE records            | ladder warp: swap draws
-//    -- barrier (all) --
-//    S2  T = OFF M^T on DMMA (Gaussian rows)                                                                       | ladder warp: swap phase
-//    -- barrier (all) --
+//  * Shared-memory addresses are constant-bank offsets (XPLayout, computed on the host); the two Philox blocks of a step are generated
+//    once per warp (even / odd lanes) instead of by all 32 lanes.
+//
+//    S1  publish scalars + x (scratch); prep: draws, member, offsets -> OFF rows, prefetch DE records
+//    -- barrier --
+//    S2  T = OFF M^T on DMMA (Gaussian rows) on warps 0 .. R-2                                       | warp R-1: the ladder's swap phase
+//    -- barrier --
 //    S3  swapped rungs append / take over states; MH rungs: proposal, enforce, prior, gate -> NEWX rows
-//    -- barrier (chain warps) --
+//    -- barrier --
 //    S4  Y = NEWX Cinv^T on DMMA (gated rows)
-//    -- barrier (chain warps) --
+//    -- barrier --
 //    S5  quadratic form, Metropolis test, append
 #pragma once
 #include "ptg_wide_mma.cuh"
@@ -34,6 +37,13 @@ struct XPShared {
   int *kindflag;              // [R]: 1 = row of the rotation (set in S1), 2 = row of the quadratic form (set in S3)
 };
 
+// Byte offsets of every shared-memory array from the start of dynamic shared memory, computed on the host and passed as a kernel parameter:
+// the addresses are then constant-bank offsets instead of integer arithmetic the compiler re-derives inside the loop under register pressure.
+struct XPLayout {
+  int DS, RP;
+  int Ms, Cs, bufA, bufB, plo, phi, kindflag;
+  int sll, slpost, slprior, sbeta, n_lpost, n_beta, app_lpost, app_beta, sbins, scount, saccept, perm, napp, app_src, dir, ups, downs, inst;
+};
 static inline int ptg_xp_stride(int D) { int ds = (D + 7) & ~7; while ((ds & 15) != 8) ds += 8; return ds; }
 static inline size_t ptg_xp_shared_bytes(int R, int D, int NP, int CPL) {
   const int DS = ptg_xp_stride(D), RP = (R + 7) & ~7;
@@ -41,6 +51,23 @@ static inline size_t ptg_xp_shared_bytes(int R, int D, int NP, int CPL) {
   b += sizeof(double) * ((size_t)2 * D * DS + (size_t)2 * (RP + 2) * DS + 2 * (size_t)32 * CPL);
   b += sizeof(int) * ((size_t)R + 8);
   return (b + 15) & ~(size_t)15;
+}
+
+static inline XPLayout ptg_xp_layout(int R, int D, int NP, int CPL) {
+  XPLayout y;
+  y.DS = ptg_xp_stride(D); y.RP = (R + 7) & ~7;
+  XShared L;
+  L.carve(nullptr, R, 0, NP);
+  auto off = [](const void *p) { return (int)(reinterpret_cast<const unsigned char *>(p) - reinterpret_cast<const unsigned char *>(0)); };
+  y.sll = off(L.sll); y.slpost = off(L.slpost); y.slprior = off(L.slprior); y.sbeta = off(L.sbeta); y.n_lpost = off(L.n_lpost); y.n_beta = off(L.n_beta);
+  y.app_lpost = off(L.app_lpost); y.app_beta = off(L.app_beta); y.sbins = off(L.sbins); y.scount = off(L.scount); y.saccept = off(L.saccept);
+  y.perm = off(L.perm); y.napp = off(L.napp); y.app_src = off(L.app_src); y.dir = off(L.dir); y.ups = off(L.ups); y.downs = off(L.downs); y.inst = off(L.inst);
+  int b = (int)ptg_xshared_bytes(R, 0, NP);
+  y.Ms = b; b += 8 * D * y.DS; y.Cs = b; b += 8 * D * y.DS;
+  y.bufA = b; b += 8 * (y.RP + 2) * y.DS; y.bufB = b; b += 8 * (y.RP + 2) * y.DS;
+  y.plo = b; b += 8 * 32 * CPL; y.phi = b; b += 8 * 32 * CPL;
+  y.kindflag = b;
+  return y;
 }
 
 // Out[row][n] = sum_k In[row][k] * Bs[n][k] for the rows whose bit is set in `mask` (8-row MMA tiles; padding rows read the zero row
@@ -78,28 +105,28 @@ __device__ __forceinline__ void xp_dmma(const double *In, const double *Bs, doub
   }
 }
 
-__device__ __forceinline__ void xp_bar_chains(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
-
 template <int CPL, int MAXT>
-__global__ void __launch_bounds__(MAXT) ptg_xpstep_kernel(const __grid_constant__ PtgModel m, PtgState s, long long step0, int n_steps, int trans_off, double *xscratch) {
+__global__ void __launch_bounds__(MAXT) ptg_xpstep_kernel(const __grid_constant__ PtgModel m, PtgState s, long long step0, int n_steps, int trans_off, double *xscratch,
+                                                          const __grid_constant__ XPLayout lay) {
   constexpr int MODE = PTG_RNG_PHILOX;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int R = m.n_rungs, D = m.dim, NP = m.n_props, RP = (R + 7) & ~7;
-  const int DS = ((D + 7) & ~7) + ((((D + 7) & ~7) & 15) == 8 ? 0 : 8);
+  const int R = m.n_rungs, D = m.dim, NP = m.n_props;
+#define XP_SM(T, member) reinterpret_cast<T *>(smem_raw + lay.member)
   XShared L;
-  L.carve(smem_raw, R, 0, NP);
+  L.sx = L.rowA = L.rowB = nullptr; L.split = L.udraw = nullptr; L.iswap = nullptr;
+  L.sll = XP_SM(double, sll); L.slpost = XP_SM(double, slpost); L.slprior = XP_SM(double, slprior); L.sbeta = XP_SM(double, sbeta);
+  L.n_lpost = XP_SM(double, n_lpost); L.n_beta = XP_SM(double, n_beta); L.app_lpost = XP_SM(double, app_lpost); L.app_beta = XP_SM(double, app_beta);
+  L.sbins = XP_SM(double, sbins); L.scount = XP_SM(long long, scount); L.saccept = XP_SM(long long, saccept);
+  L.perm = XP_SM(int, perm); L.napp = XP_SM(int, napp); L.app_src = XP_SM(int, app_src); L.dir = XP_SM(int, dir); L.ups = XP_SM(int, ups);
+  L.downs = XP_SM(int, downs); L.inst = XP_SM(int, inst);
   XPShared P;
-  {
-    double *d = reinterpret_cast<double *>(smem_raw + ptg_xshared_bytes(R, 0, NP));
-    P.Ms = d; d += (size_t)D * DS; P.Cs = d; d += (size_t)D * DS;
-    P.bufA = d; d += (size_t)(RP + 2) * DS; P.bufB = d; d += (size_t)(RP + 2) * DS;
-    P.plo = d; d += 32 * CPL; P.phi = d; d += 32 * CPL;
-    P.kindflag = reinterpret_cast<int *>(d);
-  }
+  P.Ms = XP_SM(double, Ms); P.Cs = XP_SM(double, Cs); P.bufA = XP_SM(double, bufA); P.bufB = XP_SM(double, bufB);
+  P.plo = XP_SM(double, plo); P.phi = XP_SM(double, phi); P.kindflag = XP_SM(int, kindflag);
+#undef XP_SM
+  const int DS = lay.DS, RP = lay.RP;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool is_ladder_warp = (warp == R);
-  const int rung = is_ladder_warp ? 0 : warp;
-  const int nchain_threads = 32 * R;
+  const int rung = warp;
+  const int swap_warp = R - 1;                    // this warp runs the ladder's swap phase while the others run the rotation
   const long long ladder = blockIdx.x;
   const long long chain = ladder * R + rung;
   // ---- one-time staging: matrices, zero / padding rows, box edges, bins
@@ -124,7 +151,7 @@ __global__ void __launch_bounds__(MAXT) ptg_xpstep_kernel(const __grid_constant_
   XChain<CPL> ch;
   ch.chain = chain;
   Stream<MODE> rs;
-  if (!is_ladder_warp) {
+  {
 #pragma unroll
     for (int k = 0; k < CPL; k++) { const int c = CPL * lane + k; ch.x[k] = (c < D) ? s.cur_x[(long long)c * m.n_chains + chain] : 0.0; }
     ch.lpost = s.lpost[chain]; ch.llike = s.llike[chain]; ch.lprior = s.lprior[chain]; ch.beta = s.beta[chain]; ch.map_lpost = s.map_lpost[chain];
@@ -135,7 +162,7 @@ __global__ void __launch_bounds__(MAXT) ptg_xpstep_kernel(const __grid_constant_
       L.dir[rung] = s.directions[chain]; L.ups[rung] = s.ups[chain]; L.downs[rung] = s.downs[chain]; L.inst[rung] = s.instances[chain];
       L.scount[rung] = 0; L.saccept[rung] = 0;
     }
-  } else stream_blank<MODE>(m, rs);
+  }
   const int maxswaps = m.maxswaps;
   const double swap_thresh = (R - 1) * m.swap_rate / maxswaps;
   double ptry = 2 * m.swap_rate; if (ptry > 1) ptry = 1;
@@ -154,7 +181,7 @@ __global__ void __launch_bounds__(MAXT) ptg_xpstep_kernel(const __grid_constant_
 #pragma unroll
     for (int k = 0; k < CPL; k++) off[k] = 0;
     int hsize = 0;
-    if (!is_ladder_warp) {
+    {
 #pragma unroll
       for (int k = 0; k < CPL; k++) myscratch[CPL * lane + k] = ch.x[k];      // states of swapped rungs travel through this row
       if (lane == 0) {
@@ -164,7 +191,12 @@ __global__ void __launch_bounds__(MAXT) ptg_xpstep_kernel(const __grid_constant_
       rs.step = step;
       hsize = (int)(ch.nsize > m.hist_cap ? (long long)m.hist_cap : ch.nsize);
       uint32_t wA[4];
-      rs.fetch(PTG_BLK_A, wA); rs.fetch(PTG_BLK_B, wB);
+      { // the two blocks of the step: even lanes generate A, odd lanes B, then everybody takes both (instead of 32 lanes generating both)
+        uint32_t q[4];
+        rs.fetch((lane & 1) ? PTG_BLK_B : PTG_BLK_A, q);
+#pragma unroll
+        for (int i = 0; i < 4; i++) { wA[i] = __shfl_sync(0xffffffffu, q[i], 0); wB[i] = __shfl_sync(0xffffffffu, q[i], 1); }
+      }
       if (m.wrap_in_set) {
         member = -1;
         const double x = (NP > 1) ? ptg_u32_to_unit(wA[0]) : 0.0;
@@ -218,17 +250,13 @@ __global__ void __launch_bounds__(MAXT) ptg_xpstep_kernel(const __grid_constant_
     }
     __syncthreads();
     // ================================================================ S2: rotation on the tensor cores | swap phase on the ladder warp
-    if (is_ladder_warp) {
-      if (R > 1) xswap_warp(m, L, ladder_stream, step, lane, maxswaps, swap_thresh, ptry);
-    } else {
+    if (R > 1 && warp == swap_warp) xswap_warp(m, L, ladder_stream, step, lane, maxswaps, swap_thresh, ptry);
+    else {
       // rows of the rotation: every warp derives the same list from the flags (ballot over the rungs)
       const unsigned mask = __ballot_sync(0xffffffffu, lane < R && P.kindflag[lane] == 1);
-      if (mask) xp_dmma(P.bufA, P.Ms, P.bufB, mask, D, DS, RP, warp, R, lane);
+      if (mask) xp_dmma(P.bufA, P.Ms, P.bufB, mask, D, DS, RP, warp, R > 1 ? R - 1 : 1, lane);
     }
     __syncthreads();
-    if (is_ladder_warp) { // the ladder warp sits out the chain-only barriers; it meets the chain warps again at the next iteration's first barrier
-      continue;
-    }
     // ================================================================ S3: swap outcome; proposal, enforce, prior, gate
     const int na = L.napp[rung];
     ch.beta = L.n_beta[rung];
@@ -310,13 +338,13 @@ __global__ void __launch_bounds__(MAXT) ptg_xpstep_kernel(const __grid_constant_
       for (int k = 0; k < CPL; k++) { const int c = CPL * lane + k; if (c < D) rowA[c] = newx[k]; }
     }
     if (lane == 0) P.kindflag[rung] = (mh && gate) ? 2 : 0;
-    xp_bar_chains(nchain_threads);
+    __syncthreads();
     // ================================================================ S4: quadratic form rows Y = NEWX Cinv^T on the tensor cores
     {
       const unsigned mask = __ballot_sync(0xffffffffu, lane < R && P.kindflag[lane] == 2);
       if (mask) xp_dmma(P.bufA, P.Cs, P.bufB, mask, D, DS, RP, warp, R, lane);
     }
-    xp_bar_chains(nchain_threads);
+    __syncthreads();
     // ================================================================ S5: quadratic form, Metropolis test, append
     double newlike = -CUDART_INF, newlpost = -CUDART_INF;
     if (mh && gate) {
@@ -354,7 +382,6 @@ __global__ void __launch_bounds__(MAXT) ptg_xpstep_kernel(const __grid_constant_
     }
   }
   __syncthreads();
-  if (is_ladder_warp) return;
 #pragma unroll
   for (int k = 0; k < CPL; k++) { const int c = CPL * lane + k; if (c < D) s.cur_x[(long long)c * m.n_chains + chain] = ch.x[k]; }
   if (lane == 0) {
