@@ -205,15 +205,25 @@ def sinusoid_spec(rungs, n=10000, dt=1e-3, **kw):
     return Spec("sinusoid", 9, rungs, centers=c, halfwidths=c.copy(), bound="oowoowoow", extra=sinusoid_data(n, dt), **kw)
 
 
-def fullcov_spec(d, rungs, seed=100, prop="covde", **kw):
-    """config D: C = Wishart(nu = d+5, I) sample (cython/exampleGaussian.py:181-182); prior +-100 sqrt(C_ii);
-    Gaussian proposal with covariance 2.38^2/d C, eigen-rotated (exampleGaussian.py:88,95)"""
+def fullcov_spec(d, rungs, seed=100, prop="covde", prior_scale=None, **kw):
+    """config D: C = Wishart(nu = d+5, I) sample (cython/exampleGaussian.py:181-182); prior +-prior_scale sqrt(C_ii);
+    Gaussian proposal with covariance 2.38^2/d C, eigen-rotated (exampleGaussian.py:88,95).
+
+    prior_scale: the example's priorscale is 100 (exampleGaussian.py:70).  The reference evaluates a prior as log(prod_i pdf_i)
+    (probability_function.hh:59, .cc:156-166), and prod_i 1 / (200 sqrt(C_ii)) underflows to 0 for d = 100 (~1e-330): the log prior is then
+    -inf EVERYWHERE, the likelihood gate (chain.cc:980) never opens, every proposal is accepted through the NaN Hastings ratio
+    (chain.cc:989-1001) and the run is a likelihood-free random walk -- in the reference as much as here (the oracle and the engine
+    reproduce it bit for bit).  A d = 100 workload that exercises the likelihood therefore needs a box whose density survives the product:
+    the default is 100 up to d = 64, 10 up to d = 110 (prod ~ 1e-231) and 5 above."""
     rng = np.random.default_rng(seed)
     A = rng.normal(size=(d + 5, d))
     Cm = A.T @ A
     cinv = np.linalg.inv(Cm)
     like0 = -0.5 * (d * np.log(2 * np.pi) + np.linalg.slogdet(Cm)[1])
-    sp = Spec("fullcov", d, rungs, centers=np.zeros(d), halfwidths=100 * np.sqrt(np.diag(Cm)), prop=prop,
+    if prior_scale is None:
+        prior_scale = 100 if d <= 64 else (10 if d <= 110 else 5)
+    assert np.sum(np.log(2 * prior_scale * np.sqrt(np.diag(Cm)))) < 700, "the prior density product underflows: lower prior_scale"
+    sp = Spec("fullcov", d, rungs, centers=np.zeros(d), halfwidths=prior_scale * np.sqrt(np.diag(Cm)), prop=prop,
               extra=dict(cinv=cinv.ravel(), like0=like0), **kw)
     w, V = np.linalg.eigh(2.38 ** 2 / d * Cm)
     sp.eig = (np.sqrt(w), V)
