@@ -60,7 +60,8 @@ class gpu_parallel_tempering_chains : public parallel_tempering_chains {
     if (const uniform_dist_product *u = dynamic_cast<const uniform_dist_product *>(the_prior)) {
       for (int i = 0; i < d; i++) { ty[i] = PTG_PRIOR_UNIFORM; a[i] = u->min[i]; b[i] = u->max[i]; }
     } else if (const gaussian_dist_product *g = dynamic_cast<const gaussian_dist_product *>(the_prior)) {
-      for (int i = 0; i < d; i++) { ty[i] = PTG_PRIOR_GAUSSIAN; a[i] = g->x0s[i]; b[i] = g->sigmas[i]; }
+      // wrap_probability (probability_function.cc:57-78): images of wrapped dimensions are added to the pdf
+      for (int i = 0; i < d; i++) { ty[i] = g->wrap_probability ? PTG_PRIOR_GAUSSIAN_WRAPPED : PTG_PRIOR_GAUSSIAN; a[i] = g->x0s[i]; b[i] = g->sigmas[i]; }
     } else if (const mixed_dist_product *m = dynamic_cast<const mixed_dist_product *>(the_prior)) {
       for (int i = 0; i < d; i++) {
         ty[i] = m->types[i]; // uniform 1, gaussian 2, polar 3, copolar 4, log 5 = PTG_PRIOR_* (probability_function.hh:151-155)
@@ -86,7 +87,6 @@ class gpu_parallel_tempering_chains : public parallel_tempering_chains {
     if (differential_evolution *de = dynamic_cast<differential_evolution *>(p)) {
       q.kind = PTG_PROP_DE; q.snooker = de->snooker; q.gamma_one_frac = de->gamma_one_frac; q.b_small = de->b_small;
       q.ignore_frac = de->ignore_frac; q.unlikely_alpha = de->unlikely_alpha; q.reduce_gamma = de->reduce_gamma_fac;
-      if (de->do_support_mixing) { std::cout << "gpu_parallel_tempering_chains: differential-evolution temperature mixing is not available on the device" << std::endl; exit(1); }
       return true;
     }
     if (gaussian_prop *g = dynamic_cast<gaussian_prop *>(p)) {
@@ -107,12 +107,13 @@ class gpu_parallel_tempering_chains : public parallel_tempering_chains {
   }
   void push_proposal(proposal_distribution &prop) {
     std::vector<ptg_proposal> props; std::vector<std::vector<double> > keep; keep.reserve(64);
-    double Tpow = 0; int wrap = 0;
+    double Tpow = 0, adapt_rate = 0, de_Tmix = 1; int wrap = 0, de_mixing = 0;
     if (proposal_distribution_set *set = dynamic_cast<proposal_distribution_set *>(&prop)) {
       wrap = 1; Tpow = set->Tpow;
-      if (set->adapt_rate > 0) { std::cout << "gpu_parallel_tempering_chains: adaptive proposal shares are not available on the device" << std::endl; exit(1); }
+      adapt_rate = set->adapt_rate; // the adaptive shares of the set (proposal_distribution.cc:132-166) run on the device, per rung
       for (size_t i = 0; i < set->proposals.size(); i++) {
         ptg_proposal q;
+        // a nested set (ptmcmc.cc:123-131, prop_adapt_rate without prop_adapt_more) draws a second selection uniform: no device form
         if (!describe_member(set->proposals[i], q, keep)) { std::cout << "gpu_parallel_tempering_chains: proposal member " << i << " has no device form" << std::endl; exit(1); }
         q.share = set->shares[i]; q.hot_share = Tpow > 0 ? set->hot_shares[i] : 0;
         props.push_back(q);
@@ -121,8 +122,13 @@ class gpu_parallel_tempering_chains : public parallel_tempering_chains {
       ptg_proposal q;
       if (!describe_member(&prop, q, keep)) { std::cout << "gpu_parallel_tempering_chains: proposal has no device form" << std::endl; exit(1); }
       q.share = 1; props.push_back(q);
+      // temperature mixing acts only on a BARE differential_evolution: parallel_tempering_chains::set_proposal asks the top-level proposal
+      // (chain.cc:1375), and a proposal_distribution_set answers support_mixing() = false whatever its members say
+      if (differential_evolution *de = dynamic_cast<differential_evolution *>(&prop))
+        if (de->do_support_mixing && nt > 1) { de_mixing = 1; de_Tmix = de->temperature_mixing_factor; }
     }
     check(ptg_set_proposals(h, (int32_t)props.size(), props.data(), Tpow, wrap), "set_proposals");
+    if (adapt_rate != 0 || de_mixing) check(ptg_set_proposal_options(h, adapt_rate, de_mixing, de_Tmix), "set_proposal_options");
   }
 
 public:

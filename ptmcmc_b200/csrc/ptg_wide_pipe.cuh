@@ -12,15 +12,15 @@
 //    the DE history indices -- their records are only PREFETCHED into L2 here) is done BEFORE the swap barrier; a rung that turns out to
 //    have been in a swap trial discards it (as the reference skips its MH step, chain.cc:1553-1558).
 //  * The rotation contracts only the rows of Gaussian-proposal chains (row indirection, 8-row tiles), the quadratic form only gated rows.
-//  * Four barriers per PT iteration instead of seven; the current states that swapped rungs exchange travel through a small global
+//  * Four barriers per PT iteration instead of seven, none of them behind a single busy warp; the current states that swapped rungs exchange travel through a small global
 //    scratch row per chain (L2 resident) instead of a third shared-memory row buffer, which is what lets both matrices fit.
 //
 //  * Shared-memory addresses are constant-bank offsets (XPLayout, computed on the host); the two Philox blocks of a step are generated
 //    once per warp (even / odd lanes) instead of by all 32 lanes.
 //
-//    S1  publish scalars + x (scratch); prep: draws, member, offsets -> OFF rows, prefetch DE records
+//    S1  publish scalars + x (scratch); prep: draws, member, offsets z o sigma -> OFF rows, DE indices (records prefetched)
 //    -- barrier --
-//    S2  T = OFF M^T on DMMA (Gaussian rows) on warps 0 .. R-2                                       | warp R-1: the ladder's swap phase
+//    S2  T = OFF M^T on DMMA (rows of the rotated proposals) on warps 0 .. R-2                       | warp R-1: the ladder's swap phase
 //    -- barrier --
 //    S3  swapped rungs append / take over states; MH rungs: proposal, enforce, prior, gate -> NEWX rows
 //    -- barrier --
@@ -35,13 +35,14 @@ struct XPShared {
   double *bufA, *bufB;        // [RP + 2][DS]: OFF / NEWX rows ; T / Y rows.  Row RP of bufA = zeros (padding rows of an MMA tile), row RP of bufB = dump
   double *plo, *phi;          // [32 CPL] prior box edges (all-uniform prior)
   int *kindflag;              // [R]: 1 = row of the rotation (set in S1), 2 = row of the quadratic form (set in S3)
+  int *gsig, *gaxis;          // [R]: rotated Gaussian proposals of this iteration: offset of the member's sigmas in prop_data, axis of a 1-D step or -1
 };
 
 // Byte offsets of every shared-memory array from the start of dynamic shared memory, computed on the host and passed as a kernel parameter:
 // the addresses are then constant-bank offsets instead of integer arithmetic the compiler re-derives inside the loop under register pressure.
 struct XPLayout {
   int DS, RP;
-  int Ms, Cs, bufA, bufB, plo, phi, kindflag;
+  int Ms, Cs, bufA, bufB, plo, phi, kindflag, gsig, gaxis;
   int sll, slpost, slprior, sbeta, n_lpost, n_beta, app_lpost, app_beta, sbins, scount, saccept, perm, napp, app_src, dir, ups, downs, inst;
 };
 static inline int ptg_xp_stride(int D) { int ds = (D + 7) & ~7; while ((ds & 15) != 8) ds += 8; return ds; }
@@ -49,7 +50,7 @@ static inline size_t ptg_xp_shared_bytes(int R, int D, int NP, int CPL) {
   const int DS = ptg_xp_stride(D), RP = (R + 7) & ~7;
   size_t b = ptg_xshared_bytes(R, 0, NP);                                   // the ladder scalars / swap outcome block of XShared (no row buffers)
   b += sizeof(double) * ((size_t)2 * D * DS + (size_t)2 * (RP + 2) * DS + 2 * (size_t)32 * CPL);
-  b += sizeof(int) * ((size_t)R + 8);
+  b += sizeof(int) * ((size_t)3 * R + 8);
   return (b + 15) & ~(size_t)15;
 }
 
@@ -66,7 +67,7 @@ static inline XPLayout ptg_xp_layout(int R, int D, int NP, int CPL) {
   y.Ms = b; b += 8 * D * y.DS; y.Cs = b; b += 8 * D * y.DS;
   y.bufA = b; b += 8 * (y.RP + 2) * y.DS; y.bufB = b; b += 8 * (y.RP + 2) * y.DS;
   y.plo = b; b += 8 * 32 * CPL; y.phi = b; b += 8 * 32 * CPL;
-  y.kindflag = b;
+  y.kindflag = b; b += 4 * R; y.gsig = b; b += 4 * R; y.gaxis = b;
   return y;
 }
 
@@ -89,7 +90,7 @@ __device__ __forceinline__ void xp_dmma(const double *In, const double *Bs, doub
     const double *brow = Bs + (size_t)n * DS;
     double c0 = 0, c1 = 0;
 #pragma unroll 4
-    for (int k0 = 0; k0 < K8; k0 += 8) {
+    for (int k0 = 0; k0 < K8; k0 += 8) { // (an explicit two-stage software pipeline of these loads measured slower: 2.20e8 vs 2.43e8 chain-steps/s)
       const double2 a2 = *reinterpret_cast<const double2 *>(arow + k0 + 2 * t);
       const double2 b2 = *reinterpret_cast<const double2 *>(brow + k0 + 2 * t);
       asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a2.x), "d"(b2.x));
@@ -105,7 +106,10 @@ __device__ __forceinline__ void xp_dmma(const double *In, const double *Bs, doub
   }
 }
 
-template <int CPL, int MAXT>
+// POOL = true (experiment, PTG_XP_POOL=1): the Box-Muller normals of the rotated proposals pooled over the CTA after the first barrier (one
+// pair per lane from the owner's stream address) and the rotation on all warps behind one more barrier.  Bit-identical, but MEASURED
+// SLOWER on B200 (2.25e8 vs 2.38e8 chain-steps/s on config D): the extra barrier costs more than the balanced prep phase saves.
+template <int CPL, int MAXT, bool POOL>
 __global__ void __launch_bounds__(MAXT) ptg_xpstep_kernel(const __grid_constant__ PtgModel m, PtgState s, long long step0, int n_steps, int trans_off, double *xscratch,
                                                           const __grid_constant__ XPLayout lay) {
   constexpr int MODE = PTG_RNG_PHILOX;
@@ -122,6 +126,7 @@ __global__ void __launch_bounds__(MAXT) ptg_xpstep_kernel(const __grid_constant_
   XPShared P;
   P.Ms = XP_SM(double, Ms); P.Cs = XP_SM(double, Cs); P.bufA = XP_SM(double, bufA); P.bufB = XP_SM(double, bufB);
   P.plo = XP_SM(double, plo); P.phi = XP_SM(double, phi); P.kindflag = XP_SM(int, kindflag);
+  P.gsig = XP_SM(int, gsig); P.gaxis = XP_SM(int, gaxis);
 #undef XP_SM
   const int DS = lay.DS, RP = lay.RP;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -227,34 +232,65 @@ __global__ void __launch_bounds__(MAXT) ptg_xpstep_kernel(const __grid_constant_
           if (snooker) asm volatile("prefetch.global.L2 [%0];" ::"l"(xhist<CPL>(m, s, ch, iz) + lane * 16));
         }
       } else if (kind == PTG_PROP_GAUSS) {
-        xnormals<CPL, MODE>(m, rs, off, lane);
-        const double *__restrict__ sig = m.prop_data + p.sigma_off;
+        int ia = -1;
+        if (p.one_d_frac > 0 && ptg_u32_to_unit(wA[1]) < p.one_d_frac) { ia = (int)(D * ptg_u32_to_unit(wA[2])); type = 1; }
+        need_t = p.has_transform && p.trans_off == trans_off;
+        if (need_t && POOL) {
+          // the offsets z o sigma of the rotated proposals are generated after the barrier by ALL warps together (one Box-Muller pair per
+          // lane, below) instead of 50 pairs by this warp while the differential-evolution warps wait
+          if (lane == 0) { P.gsig[rung] = p.sigma_off; P.gaxis[rung] = ia; }
+        } else {
+          xnormals<CPL, MODE>(m, rs, off, lane);
+          const double *__restrict__ sig = m.prop_data + p.sigma_off;
 #pragma unroll
-        for (int k = 0; k < CPL; k++) { const int c = CPL * lane + k; off[k] = (c < D) ? off[k] * __ldg(sig + c) + 0.0 : 0.0; }
-        if (p.one_d_frac > 0 && ptg_u32_to_unit(wA[1]) < p.one_d_frac) {
-          const int ia = (int)(D * ptg_u32_to_unit(wA[2]));
+          for (int k = 0; k < CPL; k++) { const int c = CPL * lane + k; off[k] = (c < D) ? off[k] * __ldg(sig + c) + 0.0 : 0.0; }
+          if (ia >= 0) {
 #pragma unroll
-          for (int k = 0; k < CPL; k++) if (CPL * lane + k != ia) off[k] = 0.0;
-          type = 1;
+            for (int k = 0; k < CPL; k++) if (CPL * lane + k != ia) off[k] = 0.0;
+          }
+          if (need_t) {
+#pragma unroll
+            for (int k = 0; k < CPL; k++) { const int c = CPL * lane + k; if (c < D) rowA[c] = off[k]; }
+          } else if (p.has_transform) xtransform<CPL>(m, m.prop_data + p.trans_off, off, rowB, lane);   // a second, different matrix: exact per-warp path
         }
-        if (p.has_transform) {
-          if (p.trans_off == trans_off) need_t = true;                             // the batched DMMA rotation of S2
-          else xtransform<CPL>(m, m.prop_data + p.trans_off, off, rowB, lane);       // a second, different matrix: exact per-warp path
-        }
-      }
-      if (need_t) {
-#pragma unroll
-        for (int k = 0; k < CPL; k++) { const int c = CPL * lane + k; if (c < D) rowA[c] = off[k]; }
       }
       if (lane == 0) P.kindflag[rung] = need_t ? 1 : 0;
     }
     __syncthreads();
-    // ================================================================ S2: rotation on the tensor cores | swap phase on the ladder warp
-    if (R > 1 && warp == swap_warp) xswap_warp(m, L, ladder_stream, step, lane, maxswaps, swap_thresh, ptry);
-    else {
-      // rows of the rotation: every warp derives the same list from the flags (ballot over the rungs)
-      const unsigned mask = __ballot_sync(0xffffffffu, lane < R && P.kindflag[lane] == 1);
-      if (mask) xp_dmma(P.bufA, P.Ms, P.bufB, mask, D, DS, RP, warp, R > 1 ? R - 1 : 1, lane);
+    // ================================================================ S2a: pooled Gaussian offsets | swap phase on the hottest rung's warp
+    {
+      const unsigned mask = __ballot_sync(0xffffffffu, lane < R && P.kindflag[lane] == 1);   // rows of the rotation, the same list in every warp
+      if (R > 1 && warp == swap_warp) xswap_warp(m, L, ladder_stream, step, lane, maxswaps, swap_thresh, ptry);
+      else if (!POOL) { if (mask) xp_dmma(P.bufA, P.Ms, P.bufB, mask, D, DS, RP, warp, R > 1 ? R - 1 : 1, lane); }
+      else if (mask) {
+        // pooled offsets: work item (j-th rotated chain, Box-Muller pair q) -> components 2q, 2q+1 of that chain's OFF row, drawn from the
+        // OWNER's stream address (PTG_BLK_NORMAL + q), so the values are those of the owner's own draw_normals
+        const int npair = (D + 1) >> 1, total = __popc(mask) * npair;
+        const int nthr = 32 * (R > 1 ? R - 1 : 1);
+        for (int item = warp * 32 + lane; item < total; item += nthr) {
+          const int j = item / npair, q = item - j * npair;
+          const int owner = (int)__fns(mask, 0, j + 1);
+          uint32_t w4[4];
+          ptg_philox_draw(m.seed, (uint64_t)(m.ladder_offset + ladder) * PTG_STREAM_STRIDE + (uint64_t)owner, PTG_DOMAIN_STEP, step, PTG_BLK_NORMAL + (uint32_t)q, w4);
+          double z0, z1;
+          box_muller(w4, z0, z1);
+          const double *__restrict__ sig = m.prop_data + P.gsig[owner];
+          const int ia = P.gaxis[owner], c0i = 2 * q, c1i = 2 * q + 1;
+          double v0 = z0 * __ldg(sig + c0i) + 0.0;
+          if (ia >= 0 && c0i != ia) v0 = 0.0;
+          P.bufA[(size_t)owner * DS + c0i] = v0;
+          if (c1i < D) {
+            double v1 = z1 * __ldg(sig + c1i) + 0.0;
+            if (ia >= 0 && c1i != ia) v1 = 0.0;
+            P.bufA[(size_t)owner * DS + c1i] = v1;
+          }
+        }
+      }
+      if (POOL) {
+        __syncthreads();
+        // ============================================================ S2b: rotation T = OFF M^T on the tensor cores, all warps
+        if (mask) xp_dmma(P.bufA, P.Ms, P.bufB, mask, D, DS, RP, warp, R, lane);
+      }
     }
     __syncthreads();
     // ================================================================ S3: swap outcome; proposal, enforce, prior, gate
