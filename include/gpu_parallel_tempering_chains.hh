@@ -107,13 +107,25 @@ class gpu_parallel_tempering_chains : public parallel_tempering_chains {
   }
   void push_proposal(proposal_distribution &prop) {
     std::vector<ptg_proposal> props; std::vector<std::vector<double> > keep; keep.reserve(64);
-    double Tpow = 0, adapt_rate = 0, de_Tmix = 1; int wrap = 0, de_mixing = 0;
+    double Tpow = 0, adapt_rate = 0, de_Tmix = 1, nest_share = 0, nest_hot = 0, nest_adapt = 0; int wrap = 0, de_mixing = 0, nest_first = 0, nest_count = 0;
     if (proposal_distribution_set *set = dynamic_cast<proposal_distribution_set *>(&prop)) {
       wrap = 1; Tpow = set->Tpow;
       adapt_rate = set->adapt_rate; // the adaptive shares of the set (proposal_distribution.cc:132-166) run on the device, per rung
       for (size_t i = 0; i < set->proposals.size(); i++) {
         ptg_proposal q;
-        // a nested set (ptmcmc.cc:123-131, prop_adapt_rate without prop_adapt_more) draws a second selection uniform: no device form
+        // ONE nested set (ptmcmc.cc:123-131: the Gaussian scales of prop_adapt_rate > 0) is flattened into the member list and declared with
+        // ptg_set_nested_set; its members' shares are their shares inside it, the slot's own share is the nested set's
+        if (proposal_distribution_set *sub = dynamic_cast<proposal_distribution_set *>(set->proposals[i])) {
+          if (nest_count || sub->Tpow > 0) { std::cout << "gpu_parallel_tempering_chains: only one nested proposal set without thermal weighting has a device form" << std::endl; exit(1); }
+          nest_first = (int)props.size(); nest_count = (int)sub->proposals.size(); nest_share = set->shares[i]; nest_hot = Tpow > 0 ? set->hot_shares[i] : 0;
+          nest_adapt = sub->adapt_rate;
+          for (size_t j = 0; j < sub->proposals.size(); j++) {
+            if (!describe_member(sub->proposals[j], q, keep)) { std::cout << "gpu_parallel_tempering_chains: nested proposal member " << j << " has no device form" << std::endl; exit(1); }
+            q.share = sub->shares[j]; q.hot_share = 0;
+            props.push_back(q);
+          }
+          continue;
+        }
         if (!describe_member(set->proposals[i], q, keep)) { std::cout << "gpu_parallel_tempering_chains: proposal member " << i << " has no device form" << std::endl; exit(1); }
         q.share = set->shares[i]; q.hot_share = Tpow > 0 ? set->hot_shares[i] : 0;
         props.push_back(q);
@@ -129,6 +141,7 @@ class gpu_parallel_tempering_chains : public parallel_tempering_chains {
     }
     check(ptg_set_proposals(h, (int32_t)props.size(), props.data(), Tpow, wrap), "set_proposals");
     if (adapt_rate != 0 || de_mixing) check(ptg_set_proposal_options(h, adapt_rate, de_mixing, de_Tmix), "set_proposal_options");
+    if (nest_count) check(ptg_set_nested_set(h, nest_first, nest_count, nest_share, nest_hot, nest_adapt), "set_nested_set");
   }
 
 public:

@@ -160,7 +160,16 @@ int ptg_set_proposals(ptg_handle *h, int32_t n, const ptg_proposal *props, doubl
  *   de_Tmix     temperature_mixing_factor (mix_temperatures_more, proposal_distribution.hh:403; ptmcmc's de_Tmix).
  * Both run in the tape-capable warp kernel (PTG_KERNEL_WARP) in either RNG mode. */
 int ptg_set_proposal_options(ptg_handle *h, double adapt_rate, int32_t de_mixing, double de_Tmix);
-/* the current shares of every chain's proposal set, shares[n_chains][n_props] (proposal_distribution_set::report(1)) */
+/* Members [first, first + count) of the list given to ptg_set_proposals form ONE NESTED proposal_distribution_set that takes a single slot of
+ * the top-level set (at position `first`) with top-level share `share` (`hot_share` when Tpow > 0); the members' own `share` fields are
+ * their shares INSIDE the nested set; adapt_rate is the nested set's own (ptmcmc_sampler::select_proposal builds exactly this for
+ * prop_adapt_rate > 0: the six Gaussian scales in an adaptive sub-set, the top level adaptive only with prop_adapt_more; ptmcmc.cc:70-72,
+ * 123-143).  A step that selects the nested slot draws a second selection uniform (Philox block PTG_BLK_NEST) and reports the type
+ * slot + 10 (j + 10 member_type).  Call after ptg_set_proposals / ptg_set_proposal_options, before initialising.  Same kernel and limits as
+ * the adaptive shares. */
+int ptg_set_nested_set(ptg_handle *h, int32_t first, int32_t count, double share, double hot_share, double adapt_rate);
+/* the current shares of every chain's proposal set, shares[n_chains][n_slots + count]: the top-level slots (n_slots = n_props, or
+ * n_props - count + 1 with a nested set), then the nested set's members (proposal_distribution_set::report(1)) */
 int ptg_get_proposal_shares(ptg_handle *h, double *shares);
 /* explicit inverse temperatures instead of the geometric ladder; [n_ladders*n_rungs] or NULL */
 int ptg_set_betas(ptg_handle *h, const double *betas);

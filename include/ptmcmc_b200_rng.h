@@ -37,6 +37,7 @@
 /* DE history index `which` (0 = z, 1 = s1, 2 = s2), attempt 0: block and word */
 #define PTG_IDX_BLK(which) ((which) == 1 ? PTG_BLK_A : PTG_BLK_B)
 #define PTG_IDX_WORD(which) ((which) == 1 ? 3 : ((which) == 2 ? 0 : 1))
+#define PTG_BLK_NEST 2        /* w0 : selection draw of a NESTED proposal set (ptg_set_nested_set)                                   (u32) */
 #define PTG_BLK_NORMAL 0x100  /* + j/2 : Box-Muller pair -> normals j, j+1 ; (w0,w1)=u_a (w2,w3)=u_b      (u52) */
 #define PTG_BLK_RETRY 0x200   /* + which*0x100 + a : DE index attempt a>=1 (w0) and unlikely-alpha test (w1) (u32) */
 #define PTG_BLK_PRIOR 0x600   /* + i : prior draw of dimension i; (w0,w1)=u (w2,w3)=u_b for Gaussian dims  (u52) */

@@ -47,6 +47,13 @@ typedef struct {
   uint64_t id;
 } stream_t;
 
+typedef struct { /* one proposal_distribution_set as a rung's clone holds it (proposal_distribution.hh:308-321) */
+  int n;
+  double shares[PTG_MAX_PROPOSALS], bins[PTG_MAX_PROPOSALS];
+  int last_accepted[PTG_MAX_PROPOSALS];
+  int adapt_count;
+} setstate_t;
+
 typedef struct {
   double *x;
   double lpost, llike, beta;
@@ -58,9 +65,7 @@ typedef struct {
   int32_t *htype;
   int64_t hcap;
   stream_t rng;
-  double *bin_max;
-  /* adaptive shares (proposal_distribution.hh:313-318): this rung's clone of the set owns them */
-  double *shares; int *last_accepted; int adapt_count;
+  setstate_t top, nest; /* this rung's clone of the proposal set (and of its nested set) owns shares, bins and the adaptation state */
   int64_t frozen;   /* history_freeze (chain.cc:1552, chain.hh:86): the size other chains see during the MH phase of a PT step */
 } chain_t;
 
@@ -76,6 +81,7 @@ struct pto_handle {
   int like_kind; double *lparams; int n_lparams; double *ldata; int64_t n_ldata; double like_nsum;
   int nprops; prop_t props[PTG_MAX_PROPOSALS]; double Tpow; int wrap_in_set;
   double adapt_rate; int de_mixing; double de_Tmix; double hot_norm[PTG_MAX_PROPOSALS];
+  int nest_first, nest_count; double nest_share, nest_hot, nest_adapt;
   double *betas0; /* optional explicit */
   chain_t *chains;
   stream_t *lstreams;
@@ -407,7 +413,7 @@ static void add_state(pto_handle *h, chain_t *c, const double *x, double llike, 
 }
 
 /* ---------------------------------------------------------------------------------------------- proposals */
-typedef struct { int type; double log_hastings; int valid; int member; } draw_result_t;
+typedef struct { int type; double log_hastings; int valid; int member, slot, nested; } draw_result_t;
 
 /* differential_evolution::draw_i_from_chain (proposal_distribution.cc:744-778); `size` is the frozen chain
  * size (chain.hh:86); with a ring of capacity C only the newest min(size,C) samples are eligible. */
@@ -647,19 +653,109 @@ static void member_draw(pto_handle *h, chain_t *c, const prop_t *p, uint64_t ste
   }
 }
 
-/* proposal_distribution_set::draw (proposal_distribution.cc:99-129) */
+/* ---- proposal sets.  The engine's member list is flat; optionally members [nest_first, nest_first + nest_count) form ONE nested
+ * proposal_distribution_set that occupies a single slot of the top-level set (what ptmcmc_sampler builds for prop_adapt_rate > 0,
+ * ptmcmc.cc:123-131).  slot -> member: slots before the nested one map to themselves, the nested slot to -1, later slots skip the
+ * nested members. */
+static int n_top(const pto_handle *h) { return h->nest_count ? h->nprops - h->nest_count + 1 : h->nprops; }
+static int slot_member(const pto_handle *h, int slot) {
+  if (!h->nest_count || slot < h->nest_first) return slot;
+  if (slot == h->nest_first) return -1;
+  return slot + h->nest_count - 1;
+}
+/* proposal_distribution_set::reset_bins (proposal_distribution.cc:37-59): normalises the shares IN PLACE */
+static void set_reset_bins(setstate_t *s, double Tpow, const double *hot, double beta, int have_chain) {
+  int n = s->n;
+  double Tfac = 0;
+  if (Tpow > 0 && have_chain) Tfac = 1 - pow(beta, Tpow);
+  double sum = 0;
+  for (int i = 0; i < n; i++) sum += s->shares[i];
+  double last = 0;
+  for (int i = 0; i < n; i++) {
+    s->shares[i] /= sum;
+    s->bins[i] = last + s->shares[i];
+    if (Tpow > 0) s->bins[i] += (hot[i] - s->shares[i]) * Tfac;
+    last = s->bins[i];
+  }
+  double back = s->bins[n - 1];
+  for (int i = 0; i < n; i++) s->bins[i] /= back;
+}
+/* constructor (proposal_distribution.cc:61-93: hot shares normalised, reset_bins without a chain) followed by set_chain on the rung's clone
+ * (proposal_distribution.hh:336: reset_bins with the rung's temperature) */
+static void set_init(setstate_t *s, int n, const double *shares, double *hot, double Tpow, double beta) {
+  s->n = n; s->adapt_count = 0;
+  for (int i = 0; i < n; i++) { s->shares[i] = shares[i]; s->last_accepted[i] = 1; } /* last_accepted.resize(Nsize,true) (:88) */
+  if (Tpow > 0) {
+    double sum = 0;
+    for (int i = 0; i < n; i++) sum += hot[i];
+    if (sum <= 0) for (int i = 0; i < n; i++) hot[i] = shares[i];
+    else for (int i = 0; i < n; i++) hot[i] /= sum;
+  }
+  set_reset_bins(s, Tpow, hot, beta, 0);
+  set_reset_bins(s, Tpow, hot, beta, 1);
+}
+/* proposal_distribution_set::accept / reject (proposal_distribution.cc:132-166).  adapt_count is never reset, so from the
+ * adapt_every-th (10 Nsize) decision on the bins are rebuilt after every decision. */
+static void set_adapt(setstate_t *s, double rate, int idx, int accepted, double Tpow, const double *hot, double beta) {
+  if (rate == 0) return;
+  if (s->last_accepted[idx] == accepted) s->shares[idx] *= 1 - rate * 0.25;
+  s->last_accepted[idx] = accepted;
+  s->adapt_count++;
+  if (s->adapt_count >= 10 * s->n) set_reset_bins(s, Tpow, hot, beta, 1);
+}
+static void chain_sets_init(pto_handle *h, chain_t *c) {
+  double sh[PTG_MAX_PROPOSALS], hot[PTG_MAX_PROPOSALS];
+  const int nt = n_top(h);
+  for (int sl = 0; sl < nt; sl++) {
+    int m = slot_member(h, sl);
+    sh[sl] = m < 0 ? h->nest_share : h->props[m].share;
+    hot[sl] = m < 0 ? h->nest_hot : h->props[m].hot_share;
+  }
+  set_init(&c->top, nt, sh, hot, h->Tpow, c->beta);
+  for (int sl = 0; sl < nt; sl++) h->hot_norm[sl] = hot[sl];
+  c->nest.n = 0;
+  if (h->nest_count) {
+    for (int j = 0; j < h->nest_count; j++) { sh[j] = h->props[h->nest_first + j].share; hot[j] = 0; }
+    set_init(&c->nest, h->nest_count, sh, hot, 0.0, c->beta); /* the nested set has no thermal weighting (ptmcmc.cc:130) */
+  }
+}
+
+/* proposal_distribution_set::draw (proposal_distribution.cc:99-129), for the top-level set and a nested one */
 static int set_draw(pto_handle *h, chain_t *c, uint64_t step, double *prop, draw_result_t *r) {
   if (!h->wrap_in_set) { member_draw(h, c, &h->props[0], step, prop, r); return 0; }
   int count = 0;
+  const int nt = n_top(h);
   while (1) {
     double x;
-    if (h->nprops > 1) x = draw_u32(h, &c->rng, PTG_DOMAIN_STEP, step, PTG_BLK_A, 0);
+    if (nt > 1) x = draw_u32(h, &c->rng, PTG_DOMAIN_STEP, step, PTG_BLK_A, 0);
     else x = 0;
-    for (int i = 0; i < h->nprops; i++) {
-      if (prop_ready(h, c, &h->props[i]) && x < c->bin_max[i]) {
-        member_draw(h, c, &h->props[i], step, prop, r);
-        r->type = i + 10 * r->type;
-        r->member = i;
+    for (int sl = 0; sl < nt; sl++) {
+      const int m = slot_member(h, sl);
+      if ((m < 0 || prop_ready(h, c, &h->props[m])) && x < c->top.bins[sl]) { /* a set is always ready (proposal_distribution.hh:70) */
+        r->slot = sl; r->nested = -1;
+        if (m >= 0) {
+          member_draw(h, c, &h->props[m], step, prop, r);
+          r->member = m;
+        } else { /* the nested set's own draw */
+          int ncount = 0, done = 0;
+          while (!done) {
+            double x2;
+            if (h->nest_count > 1) x2 = draw_u32(h, &c->rng, PTG_DOMAIN_STEP, step, PTG_BLK_NEST, 0);
+            else x2 = 0;
+            for (int j = 0; j < h->nest_count && !done; j++) {
+              if (prop_ready(h, c, &h->props[h->nest_first + j]) && x2 < c->nest.bins[j]) {
+                member_draw(h, c, &h->props[h->nest_first + j], step, prop, r);
+                r->type = j + 10 * r->type;
+                r->member = h->nest_first + j; r->nested = j;
+                done = 1;
+              }
+            }
+            if (done) break;
+            ncount++;
+            if (ncount > 100 || is_philox(&c->rng)) return -1;
+          }
+        }
+        r->type = sl + 10 * r->type;
         return 0;
       }
     }
@@ -668,62 +764,11 @@ static int set_draw(pto_handle *h, chain_t *c, uint64_t step, double *prop, draw
     if (is_philox(&c->rng)) return -1; /* addressed draws cannot be redrawn */
   }
 }
-
-/* proposal_distribution_set::reset_bins (proposal_distribution.cc:37-59): called once by the constructor
- * (no chain: Tfac=0) and once by set_chain on each rung's clone (proposal_distribution.hh:336) */
-static void compute_bins(pto_handle *h, double beta, double *bin_max, double *shares_out) {
-  int n = h->nprops;
-  double shares[PTG_MAX_PROPOSALS], hot[PTG_MAX_PROPOSALS];
-  for (int i = 0; i < n; i++) { shares[i] = h->props[i].share; hot[i] = h->props[i].hot_share; }
-  if (h->Tpow > 0) { /* constructor, proposal_distribution.cc:72-79 */
-    double sum = 0;
-    for (int i = 0; i < n; i++) sum += hot[i];
-    if (sum <= 0) for (int i = 0; i < n; i++) hot[i] = shares[i];
-    else for (int i = 0; i < n; i++) hot[i] /= sum;
-  }
-  for (int pass = 0; pass < 2; pass++) {
-    double Tfac = 0;
-    if (h->Tpow > 0 && pass == 1) Tfac = 1 - pow(beta, h->Tpow);
-    double sum = 0;
-    for (int i = 0; i < n; i++) sum += shares[i];
-    double last = 0;
-    for (int i = 0; i < n; i++) {
-      shares[i] /= sum;
-      bin_max[i] = last + shares[i];
-      if (h->Tpow > 0) bin_max[i] += (hot[i] - shares[i]) * Tfac;
-      last = bin_max[i];
-    }
-    double back = bin_max[n - 1];
-    for (int i = 0; i < n; i++) bin_max[i] /= back;
-  }
-  for (int i = 0; i < n; i++) { if (shares_out) shares_out[i] = shares[i]; h->hot_norm[i] = hot[i]; }
-}
-
-/* proposal_distribution_set::reset_bins on a rung's own clone (proposal_distribution.cc:37-59): normalises the shares IN PLACE */
-static void chain_reset_bins(pto_handle *h, chain_t *c) {
-  int n = h->nprops;
-  double Tfac = 0;
-  if (h->Tpow > 0) Tfac = 1 - pow(c->beta, h->Tpow);
-  double sum = 0;
-  for (int i = 0; i < n; i++) sum += c->shares[i];
-  double last = 0;
-  for (int i = 0; i < n; i++) {
-    c->shares[i] /= sum;
-    c->bin_max[i] = last + c->shares[i];
-    if (h->Tpow > 0) c->bin_max[i] += (h->hot_norm[i] - c->shares[i]) * Tfac;
-    last = c->bin_max[i];
-  }
-  double back = c->bin_max[n - 1];
-  for (int i = 0; i < n; i++) c->bin_max[i] /= back;
-}
-/* proposal_distribution_set::accept / reject (proposal_distribution.cc:132-166).  adapt_count is never reset, so from the
- * adapt_every-th decision on the bins are rebuilt after every decision. */
-static void set_adapt(pto_handle *h, chain_t *c, int member, int accepted) {
-  if (!h->wrap_in_set || h->adapt_rate == 0) return;
-  if (c->last_accepted[member] == accepted) c->shares[member] *= 1 - h->adapt_rate * 0.25;
-  c->last_accepted[member] = accepted;
-  c->adapt_count++;
-  if (c->adapt_count >= 10 * h->nprops) chain_reset_bins(h, c);
+/* accept() / reject() of the top-level set, handed down to the member that drew (proposal_distribution.cc:132-166) */
+static void sets_adapt(pto_handle *h, chain_t *c, const draw_result_t *r, int accepted) {
+  if (!h->wrap_in_set) return;
+  set_adapt(&c->top, h->adapt_rate, r->slot, accepted, h->Tpow, h->hot_norm, c->beta);
+  if (r->nested >= 0) set_adapt(&c->nest, h->nest_adapt, r->nested, accepted, 0.0, h->hot_norm, c->beta);
 }
 
 /* ---------------------------------------------------------------------------------------------- MH step */
@@ -731,7 +776,7 @@ static void set_adapt(pto_handle *h, chain_t *c, int member, int accepted) {
 static int mh_step(pto_handle *h, chain_t *c, uint64_t step, double *lhr_out, int *code_out) {
   const int d = h->d;
   double newx[PTG_MAX_DIM];
-  draw_result_t r; r.type = 0; r.log_hastings = 0; r.valid = 1; r.member = 0;
+  draw_result_t r; r.type = 0; r.log_hastings = 0; r.valid = 1; r.member = 0; r.slot = 0; r.nested = -1;
   double oldlprior = c->lpost - c->beta * c->llike;
   if (set_draw(h, c, step, newx, &r) != 0) return fail(PTG_EINVAL, "proposal set: no member ready");
   int valid = r.valid;
@@ -758,11 +803,11 @@ static int mh_step(pto_handle *h, chain_t *c, uint64_t step, double *lhr_out, in
   if (accept) {
     c->naccept++;
     c->last_type = r.type;
-    set_adapt(h, c, r.member, 1);
+    sets_adapt(h, c, &r, 1);
     add_state(h, c, newx, newlike, newlpost);
     code |= PTG_TRACE_ACCEPT;
   } else {
-    set_adapt(h, c, r.member, 0);
+    sets_adapt(h, c, &r, 0);
     add_state(h, c, c->x, c->llike, c->lpost);
   }
   code |= (r.type & PTG_TRACE_TYPE_MASK);
@@ -933,7 +978,7 @@ int pto_destroy(pto_handle *h) {
   for (int64_t i = 0; i < h->nchains; i++) {
     chain_t *c = &h->chains[i];
     free(c->x); free(c->map_x); free(c->hx); free(c->hlpost); free(c->hllike); free(c->hacc); free(c->hbeta); free(c->htype);
-    free(c->rng.urec); free(c->rng.zrec); free(c->bin_max); free(c->shares); free(c->last_accepted);
+    free(c->rng.urec); free(c->rng.zrec);
   }
   for (int l = 0; l < h->L; l++) { free(h->lstreams[l].urec); free(h->lstreams[l].zrec); }
   for (int i = 0; i < h->nprops; i++) { free(h->props[i].sigmas); free(h->props[i].transform); }
@@ -996,7 +1041,7 @@ int pto_set_proposals(pto_handle *h, int32_t n, const ptg_proposal *props, doubl
   if (n < 1 || n > PTG_MAX_PROPOSALS) return fail(PTG_EINVAL, "bad proposal count");
   if (!wrap_in_set && n != 1) return fail(PTG_EINVAL, "a bare proposal must be single");
   h->nprops = n; h->Tpow = Tpow; h->wrap_in_set = wrap_in_set;
-  h->adapt_rate = 0; h->de_mixing = 0; h->de_Tmix = 1;
+  h->adapt_rate = 0; h->de_mixing = 0; h->de_Tmix = 1; h->nest_first = h->nest_count = 0; h->nest_adapt = 0;
   for (int i = 0; i < n; i++) {
     prop_t *p = &h->props[i]; const ptg_proposal *q = &props[i];
     p->kind = q->kind; p->share = q->share; p->hot_share = q->hot_share;
@@ -1022,9 +1067,18 @@ int pto_set_proposal_options(pto_handle *h, double adapt_rate, int32_t de_mixing
   h->adapt_rate = adapt_rate; h->de_mixing = de_mixing; h->de_Tmix = de_Tmix;
   return 0;
 }
+int pto_set_nested_set(pto_handle *h, int32_t first, int32_t count, double share, double hot_share, double adapt_rate) {
+  if (!h->have_props || !h->wrap_in_set) return fail(PTG_EINVAL, "a nested set needs a proposal set");
+  if (first < 0 || count < 1 || first + count > h->nprops) return fail(PTG_EINVAL, "nested set out of range");
+  h->nest_first = first; h->nest_count = count; h->nest_share = share; h->nest_hot = hot_share; h->nest_adapt = adapt_rate;
+  return 0;
+}
 int pto_get_proposal_shares(pto_handle *h, double *shares) {
-  for (int64_t i = 0; i < h->nchains; i++)
-    for (int k = 0; k < h->nprops; k++) shares[i * h->nprops + k] = h->chains[i].shares ? h->chains[i].shares[k] : h->props[k].share;
+  const int nt = n_top(h), nb = nt + h->nest_count;
+  for (int64_t i = 0; i < h->nchains; i++) {
+    for (int k = 0; k < nt; k++) shares[i * nb + k] = h->chains[i].top.shares[k];
+    for (int k = 0; k < h->nest_count; k++) shares[i * nb + nt + k] = h->chains[i].nest.shares[k];
+  }
   return 0;
 }
 int pto_set_betas(pto_handle *h, const double *betas) {
@@ -1097,13 +1151,7 @@ static int finish_init(pto_handle *h) {
   for (int64_t i = 0; i < h->nchains; i++) {
     chain_t *c = &h->chains[i];
     c->nhist = 0;
-    free(c->bin_max); free(c->shares); free(c->last_accepted);
-    c->bin_max = (double *)calloc(PTG_MAX_PROPOSALS, sizeof(double));
-    c->shares = (double *)calloc(PTG_MAX_PROPOSALS, sizeof(double));
-    c->last_accepted = (int *)calloc(PTG_MAX_PROPOSALS, sizeof(int));
-    for (int k = 0; k < PTG_MAX_PROPOSALS; k++) c->last_accepted[k] = 1; /* last_accepted.resize(Nsize,true) (proposal_distribution.cc:88) */
-    c->adapt_count = 0;
-    compute_bins(h, c->beta, c->bin_max, c->shares); /* set_proposal after initialize (ptmcmc.cc:514-522) */
+    chain_sets_init(h, c); /* set_proposal after initialize (ptmcmc.cc:514-522) */
   }
   for (int l = 0; l < h->L; l++)
     for (int r = 0; r < h->R; r++) { /* chain.cc:1345-1358 */

@@ -28,6 +28,7 @@ int pto_set_prior(pto_handle *h, const int32_t *type, const double *a, const dou
 int pto_set_likelihood(pto_handle *h, int32_t kind, const double *params, int32_t n_params, const double *data, int64_t n_data);
 int pto_set_proposals(pto_handle *h, int32_t n, const ptg_proposal *props, double Tpow, int32_t wrap_in_set);
 int pto_set_proposal_options(pto_handle *h, double adapt_rate, int32_t de_mixing, double de_Tmix);
+int pto_set_nested_set(pto_handle *h, int32_t first, int32_t count, double share, double hot_share, double adapt_rate);
 int pto_get_proposal_shares(pto_handle *h, double *shares);
 int pto_set_betas(pto_handle *h, const double *betas);
 int pto_seed(pto_handle *h, uint64_t seed);

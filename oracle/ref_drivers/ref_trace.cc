@@ -278,12 +278,27 @@ int main(int argc, char **argv) {
     if (I("de_mixing", 0)) de->support_mixing(true); // as ptmcmc.cc:84 does; inert inside a set (chain.cc:1375 asks the SET, which says no)
     set[0] = de; shares[0] = 1 - gshare;
     double sum = (pow(2, Ng + 1) - 2), stepfac = 2, fac = pow(2.0 / stepfac, 4.0), sharefac = 1;
+    double prop_adapt_rate = D("prop_adapt_rate", 0);
+    if (prop_adapt_rate > 0) {
+      // hierarchical: the Gaussian scales in a nested adaptive set, the top level adaptive only with prop_adapt_more (ptmcmc.cc:70-72,123-143)
+      vector<proposal_distribution *> gset(Ng); vector<double> gshares(Ng);
+      for (int i = 0; i < Ng; i++) {
+        fac *= stepfac;
+        gset[i] = new gaussian_prop(scales / 100.0 / fac, g1d, false);
+        sharefac *= 2; gshares[i] = sharefac / sum;
+      }
+      set.resize(2); shares.resize(2); hot.resize(2);
+      set[1] = new proposal_distribution_set(gset, gshares, prop_adapt_rate);
+      shares[1] = gshare;
+      cprop = new proposal_distribution_set(set, shares, I("prop_adapt_more", 0) ? prop_adapt_rate : 0, 0, hot);
+    } else {
     for (int i = 1; i < 1 + Ng; i++) {
       fac *= stepfac;
       set[i] = new gaussian_prop(scales / 100.0 / fac, g1d, false);
       sharefac *= 2; shares[i] = sharefac / sum * gshare;
     }
     cprop = new proposal_distribution_set(set, shares, D("adapt_rate", 0), 0, hot);
+    }
   } else if (prop == "de") {
     differential_evolution *de = new differential_evolution(D("de_snooker", 0.1), D("de_g1_frac", 0.3), D("de_eps", 1e-4),
                                                             D("de_ignore_frac", 0.0), D("de_unlikely_alpha", 0));

@@ -125,6 +125,7 @@ class CApi:
         """props: list of dicts(kind=..., share=..., [DE fields] / [sigmas, one_d_frac, transform])"""
         arr = (Proposal * len(props))()
         self.n_props = len(props)
+        self.n_nested = 0
         for i, p in enumerate(props):
             q = arr[i]
             q.kind = p["kind"]; q.share = p.get("share", 1.0); q.hot_share = p.get("hot_share", 0.0)
@@ -142,8 +143,15 @@ class CApi:
         """adaptive shares of the set (proposal_distribution.cc:132-166) / temperature mixing of a bare DE proposal (:594-741)"""
         self._call("set_proposal_options", self.h, C.c_double(adapt_rate), C.c_int32(1 if de_mixing else 0), C.c_double(de_Tmix))
 
+    def set_nested_set(self, first, count, share, hot_share=0.0, adapt_rate=0.0):
+        """members [first, first + count) form one nested proposal_distribution_set in a single top-level slot (ptmcmc.cc:123-143)"""
+        self._call("set_nested_set", self.h, C.c_int32(first), C.c_int32(count), C.c_double(share), C.c_double(hot_share), C.c_double(adapt_rate))
+        self.n_nested = count
+
     def get_proposal_shares(self):
-        sh = np.empty((self.n_chains, max(self.n_props, 1)))
+        """[n_chains, top-level slots + nested members]"""
+        nn = getattr(self, "n_nested", 0)
+        sh = np.empty((self.n_chains, max(self.n_props + (1 if nn else 0), 1)))
         self._call("get_proposal_shares", self.h, _dp(sh))
         return sh
 

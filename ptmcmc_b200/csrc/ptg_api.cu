@@ -41,6 +41,7 @@ struct ptg_handle {
   std::vector<HostProp> props;
   double Tpow;
   double adapt_rate; int de_mixing; double de_Tmix;   // ptg_set_proposal_options
+  int nest_first, nest_count; double nest_share, nest_hot, nest_adapt;   // ptg_set_nested_set
   std::vector<double> lparams, ldata, betas;
   std::vector<int32_t> lower, upper; std::vector<double> xmin, xmax; std::vector<PtgPrior1D> prior; // every dimension (dim may exceed 16)
   int wide_trans_off;              // offset of the (first) eigen-rotation matrix in prop_data, -1 = none
@@ -421,22 +422,20 @@ extern "C" int ptg_set_proposals(ptg_handle *h, int32_t n, const ptg_proposal *p
   }
   h->Tpow = Tpow; h->m.wrap_in_set = wrap_in_set ? 1 : 0; h->m.n_props = n;
   h->adapt_rate = 0; h->de_mixing = 0; h->de_Tmix = 1;
+  h->nest_first = h->nest_count = 0; h->nest_share = h->nest_hot = h->nest_adapt = 0;
   h->have_props = true;
   h->model_dirty = true;
   return 0;
 }
 
+static int restrict_to_warp_kernel(const ptg_handle *h, const char *what);
 // proposal_distribution_set's adapt_rate (proposal_distribution.cc:61,132-166) and differential_evolution::support_mixing /
 // mix_temperatures_more (proposal_distribution.hh:403,412)
 extern "C" int ptg_set_proposal_options(ptg_handle *h, double adapt_rate, int32_t de_mixing, double de_Tmix) {
   if (!h) return fail(PTG_EINVAL, "null handle");
   if (!h->have_props) return fail(PTG_EINVAL, "set the proposals first");
   if (h->inited) return fail(PTG_EINVAL, "proposal options must be set before initialising");
-  if (adapt_rate != 0 || de_mixing) {
-    if (h->wide) return fail(PTG_EINVAL, "adaptive shares / temperature mixing run in the thread-per-chain warp kernel: dim <= 16");
-    if (h->m.n_rungs > 32 || h->m.maxswaps > 32) return fail(PTG_EINVAL, "adaptive shares / temperature mixing need n_rungs <= 32 and at most 32 swap trials per step");
-    if (h->m.like_kind == PTG_LIKE_HOST_CALLBACK) return fail(PTG_EINVAL, "adaptive shares / temperature mixing are not available with a host-callback likelihood");
-  }
+  if (adapt_rate != 0 || de_mixing) { int rc = restrict_to_warp_kernel(h, "adaptive shares / temperature mixing"); if (rc) return rc; }
   if (adapt_rate != 0 && !h->m.wrap_in_set) return fail(PTG_EINVAL, "adaptive shares need a proposal set (wrap_in_set = 1)");
   if (de_mixing) {
     if (h->m.wrap_in_set || h->props[0].p.kind != PTG_PROP_DE)
@@ -449,19 +448,42 @@ extern "C" int ptg_set_proposal_options(ptg_handle *h, double adapt_rate, int32_
   return 0;
 }
 
-static void compute_bins(const ptg_handle *h, double beta, double *bin_max, double *shares_out, double *hot_out);
+static int restrict_to_warp_kernel(const ptg_handle *h, const char *what) {
+  if (h->wide) return fail(PTG_EINVAL, "%s run in the thread-per-chain warp kernel: dim <= 16", what);
+  if (h->m.n_rungs > 32 || h->m.maxswaps > 32) return fail(PTG_EINVAL, "%s need n_rungs <= 32 and at most 32 swap trials per step", what);
+  if (h->m.like_kind == PTG_LIKE_HOST_CALLBACK) return fail(PTG_EINVAL, "%s are not available with a host-callback likelihood", what);
+  return 0;
+}
+// a nested proposal_distribution_set inside the top-level one (ptmcmc.cc:70-72,123-143)
+extern "C" int ptg_set_nested_set(ptg_handle *h, int32_t first, int32_t count, double share, double hot_share, double adapt_rate) {
+  if (!h) return fail(PTG_EINVAL, "null handle");
+  if (!h->have_props || !h->m.wrap_in_set) return fail(PTG_EINVAL, "a nested set needs a proposal set (ptg_set_proposals with wrap_in_set = 1 first)");
+  if (h->inited) return fail(PTG_EINVAL, "the nested set must be declared before initialising");
+  if (first < 0 || count < 1 || first + count > h->m.n_props) return fail(PTG_EINVAL, "nested set [%d, %d) is outside the %d members", first, first + count, h->m.n_props);
+  if (!(share >= 0)) return fail(PTG_EINVAL, "bad share");
+  int rc = restrict_to_warp_kernel(h, "nested proposal sets"); if (rc) return rc;
+  h->nest_first = first; h->nest_count = count; h->nest_share = share; h->nest_hot = hot_share; h->nest_adapt = adapt_rate;
+  h->model_dirty = true;
+  return 0;
+}
+
+static void compute_set(int n, const double *shares_in, const double *hot_in, double Tpow, double beta, double *bin_max, double *shares_out, double *hot_out);
+static void top_level_shares(const ptg_handle *h, double *sh, double *hot);
 extern "C" int ptg_get_proposal_shares(ptg_handle *h, double *shares) {
   if (!h || !shares) return fail(PTG_EINVAL, "null argument");
   if (!h->model_uploaded) return fail(PTG_EINVAL, "not initialised");
   const PtgModel &m = h->m;
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   if (h->s.ad_shares) {
-    CUDA_TRY(cudaMemcpyAsync(shares, h->s.ad_shares, (size_t)m.n_chains * m.n_props * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(shares, h->s.ad_shares, (size_t)m.n_chains * m.n_bins * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
   } else {
-    std::vector<double> bins(m.n_props), sh(m.n_props);
-    compute_bins(h, 1.0, bins.data(), sh.data(), nullptr);
-    for (int64_t c = 0; c < m.n_chains; c++) for (int k = 0; k < m.n_props; k++) shares[c * m.n_props + k] = sh[k];
+    double sh[PTG_MAX_PROPOSALS], hot[PTG_MAX_PROPOSALS], bn[PTG_MAX_PROPOSALS], out[2 * PTG_MAX_PROPOSALS];
+    top_level_shares(h, sh, hot);
+    compute_set(m.n_slots, sh, hot, h->Tpow, 1.0, bn, out, nullptr);
+    for (int j = 0; j < m.nest_count; j++) { sh[j] = h->props[m.nest_first + j].p.share; hot[j] = 0; }
+    if (m.nest_count) compute_set(m.nest_count, sh, hot, 0.0, 1.0, bn, out + m.n_slots, nullptr);
+    for (int64_t c = 0; c < m.n_chains; c++) for (int k = 0; k < m.n_bins; k++) shares[c * m.n_bins + k] = out[k];
   }
   return 0;
 }
@@ -514,12 +536,11 @@ extern "C" int ptg_inject_tape_marks(ptg_handle *h, int64_t n_steps, const int64
 }
 
 // proposal_distribution_set::reset_bins (proposal_distribution.cc:37-59): run once by the constructor (no chain yet,
-// Tfac = 0) and once more by set_chain on each rung's clone (proposal_distribution.hh:336)
-static void compute_bins(const ptg_handle *h, double beta, double *bin_max, double *shares_out, double *hot_out) {
-  const int n = (int)h->props.size();
+// Tfac = 0) and once more by set_chain on each rung's clone (proposal_distribution.hh:336); for one set of n members
+static void compute_set(int n, const double *shares_in, const double *hot_in, double Tpow, double beta, double *bin_max, double *shares_out, double *hot_out) {
   double shares[PTG_MAX_PROPOSALS], hot[PTG_MAX_PROPOSALS];
-  for (int i = 0; i < n; i++) { shares[i] = h->props[i].p.share; hot[i] = h->props[i].p.hot_share; }
-  if (h->Tpow > 0) {
+  for (int i = 0; i < n; i++) { shares[i] = shares_in[i]; hot[i] = hot_in[i]; }
+  if (Tpow > 0) {
     double sum = 0;
     for (int i = 0; i < n; i++) sum += hot[i];
     if (sum <= 0) for (int i = 0; i < n; i++) hot[i] = shares[i];
@@ -527,20 +548,42 @@ static void compute_bins(const ptg_handle *h, double beta, double *bin_max, doub
   }
   for (int pass = 0; pass < 2; pass++) {
     double Tfac = 0;
-    if (h->Tpow > 0 && pass == 1) Tfac = 1 - pow(beta, h->Tpow);
+    if (Tpow > 0 && pass == 1) Tfac = 1 - pow(beta, Tpow);
     double sum = 0;
     for (int i = 0; i < n; i++) sum += shares[i];
     double last = 0;
     for (int i = 0; i < n; i++) {
       shares[i] /= sum;
       bin_max[i] = last + shares[i];
-      if (h->Tpow > 0) bin_max[i] += (hot[i] - shares[i]) * Tfac;
+      if (Tpow > 0) bin_max[i] += (hot[i] - shares[i]) * Tfac;
       last = bin_max[i];
     }
     double back = bin_max[n - 1];
     for (int i = 0; i < n; i++) bin_max[i] /= back;
   }
   for (int i = 0; i < n; i++) { if (shares_out) shares_out[i] = shares[i]; if (hot_out) hot_out[i] = hot[i]; }
+}
+// shares / hot shares of the top-level slots: the members outside the nested set, and the nested set itself at slot nest_first
+static void top_level_shares(const ptg_handle *h, double *sh, double *hot) {
+  const int n = (int)h->props.size(), nc = h->nest_count, nf = h->nest_first;
+  const int nslots = nc ? n - nc + 1 : n;
+  for (int sl = 0; sl < nslots; sl++) {
+    const int mem = (nc == 0 || sl < nf) ? sl : (sl == nf ? -1 : sl + nc - 1);
+    sh[sl] = mem < 0 ? h->nest_share : h->props[mem].p.share;
+    hot[sl] = mem < 0 ? h->nest_hot : h->props[mem].p.hot_share;
+  }
+}
+// bins (and optionally normalised shares) of every table entry for a chain at inverse temperature beta: [n_slots] top level, then [nest_count]
+static void compute_bins(const ptg_handle *h, double beta, double *bin_max, double *shares_out, double *hot_out) {
+  const int n = (int)h->props.size(), nc = h->nest_count;
+  const int nslots = nc ? n - nc + 1 : n;
+  double sh[PTG_MAX_PROPOSALS], hot[PTG_MAX_PROPOSALS];
+  top_level_shares(h, sh, hot);
+  compute_set(nslots, sh, hot, h->Tpow, beta, bin_max, shares_out, hot_out);
+  if (nc) {
+    for (int j = 0; j < nc; j++) { sh[j] = h->props[h->nest_first + j].p.share; hot[j] = 0; }
+    compute_set(nc, sh, hot, 0.0, beta, bin_max + nslots, shares_out ? shares_out + nslots : nullptr, nullptr); // no thermal weighting inside (ptmcmc.cc:130)
+  }
 }
 
 static int upload_model(ptg_handle *h) {
@@ -575,27 +618,31 @@ static int upload_model(ptg_handle *h) {
   }
   if (pdata.empty()) pdata.push_back(0.0);
   m.adapt_rate = h->adapt_rate; m.de_mixing = h->de_mixing; m.de_Tmix = h->de_Tmix; m.Tpow = h->Tpow;
-  if (m.adapt_rate != 0) {
+  m.nest_first = h->nest_first; m.nest_count = h->nest_count; m.nest_adapt = h->nest_adapt;
+  m.n_slots = h->nest_count ? m.n_props - h->nest_count + 1 : m.n_props; m.n_bins = m.n_slots + h->nest_count;
+  if (h->nest_count && (h->wide || m.like_kind == PTG_LIKE_HOST_CALLBACK)) return fail(PTG_EINVAL, "nested proposal sets need dim <= 16 and a device likelihood");
+  if (m.adapt_rate != 0 || (m.nest_count && m.nest_adapt != 0)) {
     // adaptive shares: every chain's clone of the set starts from the normalised shares and the bins of its own rung's temperature
     // (constructor + set_chain, proposal_distribution.cc:61-93, .hh:336), all members "last accepted" (:88), adapt_count 0
-    const size_t nc = (size_t)m.n_chains, np = (size_t)m.n_props;
+    const size_t nc = (size_t)m.n_chains, np = (size_t)m.n_bins;
     std::vector<double> sh(nc * np), bn(nc * np);
     for (size_t c = 0; c < nc; c++) compute_bins(h, h->betas[c], &bn[c * np], &sh[c * np], m.hot_norm);
     int rc2 = 0;
     if (!h->s.ad_shares) {
       rc2 |= dev_alloc(h, &h->s.ad_shares, nc * np, false); rc2 |= dev_alloc(h, &h->s.ad_bins, nc * np, false);
-      rc2 |= dev_alloc(h, &h->s.ad_last, nc, false); rc2 |= dev_alloc(h, &h->s.ad_count, nc);
+      rc2 |= dev_alloc(h, &h->s.ad_last, nc, false); rc2 |= dev_alloc(h, &h->s.ad_count, nc); rc2 |= dev_alloc(h, &h->s.ad_count2, nc);
     }
     if (rc2) return PTG_ENOMEM;
     CUDA_TRY(cudaMemcpyAsync(h->s.ad_shares, sh.data(), sh.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->s.ad_bins, bn.data(), bn.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaMemsetAsync(h->s.ad_last, 0xff, nc * sizeof(int32_t), h->stream));
     CUDA_TRY(cudaMemsetAsync(h->s.ad_count, 0, nc * sizeof(int32_t), h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->s.ad_count2, 0, nc * sizeof(int32_t), h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
   }
   // bins per rung, from ladder 0's initial inverse temperatures
-  std::vector<double> bins((size_t)m.n_rungs * m.n_props);
-  for (int r = 0; r < m.n_rungs; r++) compute_bins(h, h->betas[r], &bins[(size_t)r * m.n_props], nullptr, m.hot_norm);
+  std::vector<double> bins((size_t)m.n_rungs * m.n_bins);
+  for (int r = 0; r < m.n_rungs; r++) compute_bins(h, h->betas[r], &bins[(size_t)r * m.n_bins], nullptr, m.hot_norm);
   if (h->Tpow > 0)
     for (int l = 1; l < m.n_ladders; l++)
       for (int r = 0; r < m.n_rungs; r++)
@@ -797,7 +844,7 @@ static int pick_kernel(const ptg_handle *h, int *W) {
   if (h->kernel_choice == PTG_KERNEL_SHARED) k = PTG_KERNEL_SHARED;
   if (h->kernel_choice == PTG_KERNEL_WARP && *W) k = PTG_KERNEL_WARP;
   // adaptive shares and temperature mixing exist in the tape-capable warp kernel (either RNG mode); ptg_set_proposal_options made sure it applies
-  if ((h->m.adapt_rate != 0 || h->m.de_mixing) && *W) k = PTG_KERNEL_WARP;
+  if ((h->m.adapt_rate != 0 || h->m.de_mixing || h->m.nest_count) && *W) k = PTG_KERNEL_WARP;
   return k;
 }
 
@@ -1552,8 +1599,9 @@ static std::vector<CkArr> ck_arrays(ptg_handle *h) {
       {s.u_pos, (n + m.n_ladders) * 8}, {s.z_pos, (n + m.n_ladders) * 8}};
   if (m.record_full) { v.push_back({s.hist_acc, n * cap * 8}); v.push_back({s.hist_beta, n * cap * 8}); v.push_back({s.hist_type, n * cap * 4}); }
   if (s.ad_shares) { // the adapted shares of every chain's proposal set (proposal_distribution_set::checkpoint, proposal_distribution.cc:168-200)
-    const size_t np = (size_t)m.n_props;
+    const size_t np = (size_t)m.n_bins;
     v.push_back({s.ad_shares, n * np * 8}); v.push_back({s.ad_bins, n * np * 8}); v.push_back({s.ad_last, n * 4}); v.push_back({s.ad_count, n * 4});
+    v.push_back({s.ad_count2, n * 4});
   }
   return v;
 }

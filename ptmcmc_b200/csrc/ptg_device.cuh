@@ -210,18 +210,16 @@ __device__ __forceinline__ bool prior_draw(const PtgModel &m, Stream<MODE> &rs, 
 // rejects in a row of `member` scale its share by 1 - adapt_rate / 4; adapt_count is never reset in the reference, so from the
 // adapt_every-th (10 n) decision on reset_bins (:37-59) runs after every decision: shares normalised in place, bins rebuilt with the
 // chain's CURRENT temperature when Tpow > 0.
-__device__ __forceinline__ void set_adapt(const PtgModel &m, const PtgState &s, long long chain, int member, bool accepted, double beta) {
-  const int n = m.n_props;
-  double *sh = s.ad_shares + chain * n, *bn = s.ad_bins + chain * n;
-  int last = s.ad_last[chain];
-  if ((((last >> member) & 1) != 0) == accepted) sh[member] *= 1 - m.adapt_rate * 0.25;
-  last = accepted ? (last | (1 << member)) : (last & ~(1 << member));
-  s.ad_last[chain] = last;
-  const int cnt = s.ad_count[chain] + 1;
-  s.ad_count[chain] = cnt;
-  if (cnt >= 10 * n) {
+// sh / bn: this chain's shares and bins of ONE set (n entries), bit0 of `last`: the set's first member
+__device__ __forceinline__ void set_adapt_one(double *sh, double *bn, int n, int &last, int bit0, int32_t &count, double rate, int idx, bool accepted, double Tpow,
+                                              const double *hot, double beta) {
+  const int bit = bit0 + idx;
+  if ((((last >> bit) & 1) != 0) == accepted) sh[idx] *= 1 - rate * 0.25;
+  last = accepted ? (last | (1 << bit)) : (last & ~(1 << bit));
+  count = count + 1;
+  if (count >= 10 * n) {
     double Tfac = 0;
-    if (m.Tpow > 0) Tfac = 1 - pow(beta, m.Tpow);
+    if (Tpow > 0) Tfac = 1 - pow(beta, Tpow);
     double sum = 0;
     for (int i = 0; i < n; i++) sum += sh[i];
     double lastb = 0;
@@ -229,13 +227,25 @@ __device__ __forceinline__ void set_adapt(const PtgModel &m, const PtgState &s, 
       const double v = sh[i] / sum;
       sh[i] = v;
       double b = lastb + v;
-      if (m.Tpow > 0) b += (m.hot_norm[i] - v) * Tfac;
+      if (Tpow > 0) b += (hot[i] - v) * Tfac;
       bn[i] = b;
       lastb = b;
     }
     const double back = bn[n - 1];
     for (int i = 0; i < n; i++) bn[i] /= back;
   }
+}
+// accept() / reject() of the top-level set, handed down to a nested set when one of its members drew (nested >= 0)
+__device__ __forceinline__ void set_adapt(const PtgModel &m, const PtgState &s, long long chain, int slot, int nested, bool accepted, double beta) {
+  double *sh = s.ad_shares + chain * m.n_bins, *bn = s.ad_bins + chain * m.n_bins;
+  int last = s.ad_last[chain];
+  if (m.adapt_rate != 0) { int32_t c = s.ad_count[chain]; set_adapt_one(sh, bn, m.n_slots, last, 0, c, m.adapt_rate, slot, accepted, m.Tpow, m.hot_norm, beta); s.ad_count[chain] = c; }
+  if (nested >= 0 && m.nest_adapt != 0) {
+    int32_t c = s.ad_count2[chain];
+    set_adapt_one(sh + m.n_slots, bn + m.n_slots, m.nest_count, last, 16, c, m.nest_adapt, nested, accepted, 0.0, m.hot_norm, beta);
+    s.ad_count2[chain] = c;
+  }
+  s.ad_last[chain] = last;
 }
 
 // ------------------------------------------------------------------------------------------------- likelihoods

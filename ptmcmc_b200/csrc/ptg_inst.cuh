@@ -23,7 +23,7 @@ template <int D, int MODE>
 static cudaError_t launch_wstep_t(const PtgModel &m, const PtgState &s, long long step0, int n_steps, int W, cudaStream_t st) {
   const long long warps = (m.n_ladders + (32 / W) - 1) / (32 / W);
   const int blocks = (int)((warps + 3) / 4);
-  const size_t smem = (size_t)m.n_rungs * m.n_props * sizeof(double);
+  const size_t smem = (size_t)m.n_rungs * m.n_bins * sizeof(double);
   ptg_wstep_kernel<D, MODE><<<blocks, 128, smem, st>>>(m, s, step0, n_steps, W);
   return cudaGetLastError();
 }

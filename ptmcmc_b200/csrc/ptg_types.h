@@ -40,7 +40,11 @@ struct PtgModel {
   double like_t0, like_dt;    // data chi^2 likelihoods: abscissae are the uniform grid t0 + i dt (like_uniform_t), e.g. config C2's time samples
   int32_t like_uniform_t, de_mixing; // de_mixing: temperature mixing of a bare DE proposal's history draws (proposal_distribution.cc:594-741)
   double adapt_rate, de_Tmix, Tpow;  // adaptive shares of the set (proposal_distribution.cc:132-166); reset_bins' thermal exponent
-  double hot_norm[PTG_MAX_PROPOSALS]; // normalised hot shares (constructor, proposal_distribution.cc:72-79)
+  double hot_norm[PTG_MAX_PROPOSALS]; // normalised hot shares of the top-level slots (constructor, proposal_distribution.cc:72-79)
+  // one nested proposal set (ptg_set_nested_set): members [nest_first, nest_first + nest_count) share top-level slot nest_first;
+  // n_slots = top-level slots, n_bins = n_slots + nest_count = entries per rung / per chain of the bins and shares tables
+  int32_t nest_first, nest_count, n_slots, n_bins;
+  double nest_adapt;
   double uniform_lprior;      // log(prod 1/(b-a)) when every factor is uniform (evaluated once on the device)
   uint64_t seed;
   int64_t ladder_offset;
@@ -56,7 +60,7 @@ struct PtgModel {
   const double *lparams;      // device
   const double *ldata;        // device
   const double *prop_data;    // device: sigmas / transforms
-  const double *bins;         // device [n_rungs][n_props] cumulative shares (reset_bins)
+  const double *bins;         // device [n_rungs][n_bins] cumulative shares (reset_bins): top-level slots, then the nested set's members
 };
 
 // Device-resident chain state (SoA over chains) + history + ladder statistics.
@@ -89,7 +93,8 @@ struct PtgState {
   uint32_t *pend_w;                     // [n_chains][2] acceptance-draw words
   // adaptive shares: every chain's clone of the proposal set owns shares, bins, last_accepted (bit per member) and adapt_count
   double *ad_shares, *ad_bins;          // [n_chains][n_props]
-  int32_t *ad_last, *ad_count;          // [n_chains]
+  int32_t *ad_last, *ad_count;          // [n_chains]: last_accepted bits (top-level slots in bits 0-15, nested members in bits 16-31), top adapt_count
+  int32_t *ad_count2;                   // [n_chains]: the nested set's adapt_count
   int32_t *err;       // device error flag (PTG_ETAPE, PTG_ESTUCK)
 };
 // Rung-sharded ladders, exchange fused into the production step kernel over NVLink peer memory (ptg_fast.cuh).

@@ -371,23 +371,41 @@ __device__ __forceinline__ MhOut wmh_step(const PtgModel &m, const PtgState &s, 
   uint32_t wA[4] = {0u, 0u, 0u, 0u}, wB[4] = {0u, 0u, 0u, 0u};
   if constexpr (MODE == PTG_RNG_PHILOX) { rs.fetch(PTG_BLK_A, wA); rs.fetch(PTG_BLK_B, wB); }
 
-  // ---- member selection: first ready member with u < bin_max (proposal_distribution.cc:105-112)
-  int member = 0;
-  const bool adaptive = m.adapt_rate != 0 && m.wrap_in_set != 0;   // this chain's own, adapting bins
-  if (adaptive && do_mh) bins = s.ad_bins + ch.chain * m.n_props;
+  // ---- member selection: first ready member with u < bin_max (proposal_distribution.cc:105-112); top-level SLOTS map to members, one
+  // slot may hold a nested set (ptg_set_nested_set) that repeats the selection over its own members with a second uniform
+  int member = 0, slot = 0, nested = -1;
+  const bool adaptive = (m.adapt_rate != 0 || m.nest_adapt != 0) && m.wrap_in_set != 0;   // this chain's own, adapting bins
+  if (adaptive && do_mh) bins = s.ad_bins + ch.chain * m.n_bins;
   const bool mixing = m.de_mixing != 0 && w.R > 1;
   if (m.wrap_in_set && do_mh) {
     member = -1;
     for (int count = 0; count <= 100 && member < 0; count++) {
       double x = 0.0;
-      if (m.n_props > 1) { if constexpr (MODE == PTG_RNG_PHILOX) x = ptg_u32_to_unit(wA[0]); else x = rs.next_u(); }
-      for (int i = 0; i < m.n_props; i++) {
-        const bool ready = (m.props[i].kind != PTG_PROP_DE) || hsize >= D * 10; // differential_evolution::is_ready
-        if (member < 0 && ready && x < bins[i]) member = i;
+      if (m.n_slots > 1) { if constexpr (MODE == PTG_RNG_PHILOX) x = ptg_u32_to_unit(wA[0]); else x = rs.next_u(); }
+      slot = -1;
+      for (int sl = 0; sl < m.n_slots; sl++) {
+        const int mem = (m.nest_count == 0 || sl < m.nest_first) ? sl : (sl == m.nest_first ? -1 : sl + m.nest_count - 1);
+        const bool ready = mem < 0 || (m.props[mem].kind != PTG_PROP_DE) || hsize >= D * 10; // differential_evolution::is_ready; a set is always ready
+        if (slot < 0 && ready && x < bins[sl]) { slot = sl; member = mem; }
+      }
+      if (slot >= 0 && member < 0) { // the nested set's own draw
+        const double *nb = bins + m.n_slots;
+        for (int ncount = 0; ncount <= 100 && member < 0; ncount++) {
+          double x2 = 0.0;
+          if (m.nest_count > 1) {
+            if constexpr (MODE == PTG_RNG_PHILOX) { uint32_t q[4]; rs.fetch(PTG_BLK_NEST, q); x2 = ptg_u32_to_unit(q[0]); } else x2 = rs.next_u();
+          }
+          for (int j = 0; j < m.nest_count; j++) {
+            const bool ready = (m.props[m.nest_first + j].kind != PTG_PROP_DE) || hsize >= D * 10;
+            if (member < 0 && ready && x2 < nb[j]) { member = m.nest_first + j; nested = j; }
+          }
+          if constexpr (MODE == PTG_RNG_PHILOX) break;
+        }
+        break; // (a nested set whose members are all unready ends the run in the reference, proposal_distribution.cc:121-127)
       }
       if constexpr (MODE == PTG_RNG_PHILOX) break;
     }
-    if (member < 0) { rs.err = 2; member = 0; }
+    if (member < 0) { rs.err = 2; member = 0; slot = 0; nested = -1; }
   }
   const PtgProp &p = m.props[member];
   const int kind = do_mh ? p.kind : 0;
@@ -515,7 +533,10 @@ __device__ __forceinline__ MhOut wmh_step(const PtgModel &m, const PtgState &s, 
     prop_lh = prior_eval_log<D>(m, ch.x, true) - prior_eval_log<D>(m, newx, valid);
     type = 0;
   }
-  if (m.wrap_in_set) type = member + 10 * type;
+  if (m.wrap_in_set) {
+    if (nested >= 0) type = nested + 10 * type;   // the nested set's type() first (proposal_distribution.cc:113)
+    type = slot + 10 * type;
+  }
 
   // ---- enforce, prior, gated likelihood (chain.cc:976-987)
   if (valid) valid = space_enforce<D>(m, newx);
@@ -540,7 +561,7 @@ __device__ __forceinline__ MhOut wmh_step(const PtgModel &m, const PtgState &s, 
   }
   if (do_mh) {
     ch.ntries++;
-    if (adaptive) set_adapt(m, s, ch.chain, member, accept, ch.beta);
+    if (adaptive) set_adapt(m, s, ch.chain, slot, nested, accept, ch.beta);
     if (accept) {
       ch.naccept++;
       ch.last_type = type;
@@ -557,17 +578,17 @@ __device__ __forceinline__ MhOut wmh_step(const PtgModel &m, const PtgState &s, 
 }
 
 // ------------------------------------------------------------------------------------------------- kernel
-// blockDim.x = 128 (4 warps); dynamic shared memory = n_rungs * n_props doubles (the proposal bins, read-only)
+// blockDim.x = 128 (4 warps); dynamic shared memory = n_rungs * n_bins doubles (the proposal bins, read-only)
 #ifndef PTG_WSTEP_MINB
 #define PTG_WSTEP_MINB 1
 #endif
 template <int D, int MODE>
 __global__ void __launch_bounds__(128, PTG_WSTEP_MINB) ptg_wstep_kernel(const __grid_constant__ PtgModel m, PtgState s, long long step0, int n_steps, int W) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double *sbins = reinterpret_cast<double *>(smem_raw); // [R][n_props]
+  double *sbins = reinterpret_cast<double *>(smem_raw); // [R][n_bins]
   __shared__ WMix smix[4];
   const int R = m.n_rungs;
-  for (int i = threadIdx.x; i < R * m.n_props; i += blockDim.x) sbins[i] = m.bins[i];
+  for (int i = threadIdx.x; i < R * m.n_bins; i += blockDim.x) sbins[i] = m.bins[i];
   __syncthreads();
   WMix &mx = smix[threadIdx.x >> 5];
 
@@ -607,7 +628,7 @@ __global__ void __launch_bounds__(128, PTG_WSTEP_MINB) ptg_wstep_kernel(const __
     stream_blank<MODE>(m, ls);
   const double swap_thresh = (R - 1) * m.swap_rate / m.maxswaps; // chain.cc:1413
   double ptry = 2 * m.swap_rate; if (ptry > 1) ptry = 1;
-  const double *bins = sbins + (w.rung < R ? w.rung : 0) * m.n_props;
+  const double *bins = sbins + (w.rung < R ? w.rung : 0) * m.n_bins;
 
   for (int it = 0; it < n_steps; it++) {
     const uint64_t step = (uint64_t)(step0 + it);

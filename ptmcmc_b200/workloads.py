@@ -128,7 +128,17 @@ class Spec:
         sc = self.scales()
         de = dict(kind=K.PROP_DE, share=1.0, snooker=e.get("de_snooker", 0.1), gamma_one_frac=0.3, b_small=1e-4,
                   ignore_frac=e.get("de_ignore_frac", 0.0), unlikely_alpha=e.get("de_unlikely_alpha", 0.0), reduce_gamma=4.0)
-        if self.prop == "default":
+        if self.prop == "default" and e.get("prop_adapt_rate", 0) > 0:
+            # ptmcmc_sampler::select_proposal with prop_adapt_rate > 0 (ptmcmc.cc:70-72,123-143): the six Gaussian scales form a nested,
+            # adaptive set; the top level [DE, nested set] adapts only with prop_adapt_more
+            mix = default_mix(sc, unlikely_alpha=e.get("de_unlikely_alpha", 0.0))
+            for i, p in enumerate(mix[1:]):
+                p["share"] = 2.0 ** (i + 1) / (2.0 ** len(mix) - 2)   # gshares[i] = sharefac / sum (:128)
+            api.set_proposals(mix)
+            api.set_nested_set(1, len(mix) - 1, share=0.2, adapt_rate=e["prop_adapt_rate"])
+            if e.get("prop_adapt_more", 0):
+                api.set_proposal_options(adapt_rate=e["prop_adapt_rate"])
+        elif self.prop == "default":
             api.set_proposals(default_mix(sc, unlikely_alpha=e.get("de_unlikely_alpha", 0.0)))
         elif self.prop == "de":
             api.set_proposals([de], wrap_in_set=False)

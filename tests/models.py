@@ -137,6 +137,10 @@ def parity_cases():
         ("adaptive_shares_default", Spec("gauss", 2, 6, centers=[2, -3], halfwidths=[2, 3], seed=0.67, Tmax=100, extra=dict(adapt_rate=0.05)), 1200, 2),
         ("adaptive_shares_Tpow_evolve", Spec("sines", 2, 6, prop="prior", seed=0.73, evolve_rate=0.01,
                                              extra=dict(Tpow=1.5, prior_draw_frac=0.2, hot_de=0.4, hot_prior=0.6, adapt_rate=0.2)), 1000, 1),
+        # what ptmcmc_sampler builds for --prop_adapt_rate (ptmcmc.cc:70-72,123-143; the reference's own exampleLISA test runs with it): the
+        # Gaussian scales in a NESTED adaptive set, and with --prop_adapt_more the top level adaptive as well
+        ("nested_adaptive_gaussians", Spec("gauss", 3, 6, centers=[2, -3, 1], halfwidths=[2, 3, 1], seed=0.101, Tmax=100, extra=dict(prop_adapt_rate=0.05)), 1000, 2),
+        ("nested_adaptive_more_evolve", Spec("sines", 2, 8, seed=0.103, evolve_rate=0.01, extra=dict(prop_adapt_rate=0.01, prop_adapt_more=1)), 1200, 1),
         # the wrapped Gaussian prior (probability_function.cc:57-78): images of the wrapped dimensions are added to the pdf
         ("gaussian_wrap_prior", Spec("gauss", 3, 5, centers=[0.5, -1.0, 2.0], halfwidths=[0.8, 1.5, 0.6], prior="gaussian_wrap", bound="wow",
                                      seed=0.79, Tmax=50, extra=dict(sigma=2.5)), 800, 2),

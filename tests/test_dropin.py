@@ -94,3 +94,22 @@ def test_engine_checkpoint_is_read_by_the_reference_restart(tmp_path):
     assert len(after) > len(before) and after[-1, 0] >= 11990
     tail = after[after[:, 0] > 7000][:, 3:]
     assert np.abs(tail.mean(0) - np.array([2.0, -3.0, 5.0])).max() < 0.12 and np.abs(tail.std(0) - 0.5).max() < 0.08
+
+
+@pytest.mark.gpu
+@needs_exe
+def test_sampler_adaptive_proposal_options_run_on_the_engine(tmp_path):
+    """--prop_adapt_rate --prop_adapt_more, the options the reference's own exampleLISA test runs with (test/exampleLISA/Makefile:7): the
+    sampler builds a nested adaptive set of Gaussian scales under an adaptive top level (ptmcmc.cc:70-72,123-143); the drop-in class flattens
+    it for the engine (ptg_set_nested_set / ptg_set_proposal_options) and the reference's run loop reports the adapted shares"""
+    extra = ["--prop_adapt_rate=0.01", "--prop_adapt_more"]
+    cpu = run(tmp_path, "acpu", extra=extra)
+    assert cpu.returncode == 0, cpu.stdout[-800:]
+    gpu = run(tmp_path, "agpu", gpu=True, extra=extra)
+    assert gpu.returncode == 0, gpu.stdout[-1500:] + gpu.stderr[-500:]
+    assert "chains stepped by the ptg engine" in gpu.stdout
+    c, g = read_chain(os.path.join(str(tmp_path), "acpu_t0.dat")), read_chain(os.path.join(str(tmp_path), "agpu_t0.dat"))
+    pc, pg = c[c[:, 0] > 2000][:, 3:], g[g[:, 0] > 2000][:, 3:]
+    for p in (pc, pg):
+        assert np.abs(p.mean(0) - np.array([2.0, -3.0, 5.0])).max() < 0.08
+        assert np.abs(p.std(0) - 0.5).max() < 0.06

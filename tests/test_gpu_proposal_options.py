@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 CASES = {c[0]: c for c in parity_cases()}
 
 
-@pytest.mark.parametrize("name", ["adaptive_shares_default", "adaptive_shares_Tpow_evolve"])
+@pytest.mark.parametrize("name", ["adaptive_shares_default", "adaptive_shares_Tpow_evolve", "nested_adaptive_gaussians", "nested_adaptive_more_evolve"])
 def test_adapted_shares_equal_the_reference_algorithm(name, oracle_cls, engine_cls):
     """after a tape replay every chain's shares are the ones the reference's accept / reject bookkeeping produced (bit-exact without
     Tpow; with Tpow the rebuilt bins go through pow(), the shares themselves do not)"""
@@ -26,7 +26,11 @@ def test_adapted_shares_equal_the_reference_algorithm(name, oracle_cls, engine_c
     assert so.shape == sg.shape
     assert so.tobytes() == sg.tobytes()
     assert np.ptp(so, axis=0).max() > 1e-3          # the rungs really adapted differently
-    assert np.allclose(so.sum(axis=1), 1.0, atol=1e-12)
+    nn = int(getattr(g, "n_nested", 0))                # every set's shares are normalised: the top level, and the nested set behind it
+    nt = so.shape[1] - nn
+    assert np.allclose(so[:, :nt].sum(axis=1), 1.0, atol=1e-12)
+    if nn:
+        assert np.allclose(so[:, nt:].sum(axis=1), 1.0, atol=1e-12)
 
 
 def test_adaptive_run_survives_checkpoint_restore(engine_cls, tmp_path):
@@ -74,6 +78,23 @@ def test_mixing_draws_from_other_rungs(engine_cls):
     assert not np.array_equal(res[0][0], res[1][0])
     # hot-rung acceptance is unaffected in order of magnitude; every chain keeps moving
     assert (res[0][1] > 0.01).all() and (res[1][1] > 0.01).all()
+
+
+def test_nested_set_errors_and_static_shares(engine_cls):
+    sp = Spec("gauss", 2, 4, centers=[2, -3], halfwidths=[2, 3])
+    e = engine_cls(sp.config(n_ladders=2)); sp.setup(e)
+    with pytest.raises(K.CApiError, match="outside"):
+        e.set_nested_set(3, 6, share=0.2)
+    e.set_nested_set(1, 6, share=0.2)                # a static nested set: same selection probabilities, two selection draws
+    e.init_from_prior(); e.step(50); e.synchronize()
+    sh = e.get_proposal_shares()
+    assert sh.shape == (8, 8) and np.allclose(sh[:, :2], [0.8, 0.2]) and np.allclose(sh[:, 2:].sum(axis=1), 1.0)
+    e.close()
+    sp = Spec("gauss", 2, 4, centers=[2, -3], halfwidths=[2, 3], prop="de")
+    e = engine_cls(sp.config(n_ladders=1)); sp.setup(e)
+    with pytest.raises(K.CApiError, match="needs a proposal set"):
+        e.set_nested_set(0, 1, share=1.0)
+    e.close()
 
 
 def test_proposal_option_errors(engine_cls):
