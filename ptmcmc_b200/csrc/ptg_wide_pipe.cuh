@@ -109,6 +109,9 @@ __device__ __forceinline__ void xp_dmma(const double *In, const double *Bs, doub
 // POOL = true (experiment, PTG_XP_POOL=1): the Box-Muller normals of the rotated proposals pooled over the CTA after the first barrier (one
 // pair per lane from the owner's stream address) and the rotation on all warps behind one more barrier.  Bit-identical, but MEASURED
 // SLOWER on B200 (2.25e8 vs 2.38e8 chain-steps/s on config D): the extra barrier costs more than the balanced prep phase saves.
+// Also measured and removed: one warp per 8-column strip holding the accumulators of all row tiles (up to four independent MMA chains per
+// warp, each matrix fragment loaded once for all of them): bit-identical, 1.59e8 -- 13 busy warps and 280 B of spills lose far more than
+// the covered accumulate latency gains.
 template <int CPL, int MAXT, bool POOL>
 __global__ void __launch_bounds__(MAXT) ptg_xpstep_kernel(const __grid_constant__ PtgModel m, PtgState s, long long step0, int n_steps, int trans_off, double *xscratch,
                                                           const __grid_constant__ XPLayout lay) {
@@ -261,7 +264,9 @@ __global__ void __launch_bounds__(MAXT) ptg_xpstep_kernel(const __grid_constant_
     {
       const unsigned mask = __ballot_sync(0xffffffffu, lane < R && P.kindflag[lane] == 1);   // rows of the rotation, the same list in every warp
       if (R > 1 && warp == swap_warp) xswap_warp(m, L, ladder_stream, step, lane, maxswaps, swap_thresh, ptry);
-      else if (!POOL) { if (mask) xp_dmma(P.bufA, P.Ms, P.bufB, mask, D, DS, RP, warp, R > 1 ? R - 1 : 1, lane); }
+      else if (!POOL) {
+        if (mask) xp_dmma(P.bufA, P.Ms, P.bufB, mask, D, DS, RP, warp, R > 1 ? R - 1 : 1, lane);
+      }
       else if (mask) {
         // pooled offsets: work item (j-th rotated chain, Box-Muller pair q) -> components 2q, 2q+1 of that chain's OFF row, drawn from the
         // OWNER's stream address (PTG_BLK_NORMAL + q), so the values are those of the owner's own draw_normals

@@ -203,3 +203,33 @@ def test_ring_window_at_the_bench_configuration(engine_cls):
     rw, ru = recipe(wrapped), recipe(unwrapped)
     print("ESS per iteration (reference recipe): ring 8192 %.5f, unwrapped %.5f" % (rw, ru))
     assert abs(rw / ru - 1) < 0.10
+
+
+def test_config_d_posterior_at_the_bench_configuration(engine_cls):
+    """BASELINE config D as bench.py runs it (d = 100, 24 rungs, save_every 8, ring 1280, prior box +-10 sqrt(C_ii), pipelined DMMA kernel):
+    after the bench's burn-in the cold chains sample N(0, C) -- E[x^T Cinv x] = d, per-parameter variance C_ii, and the likelihood IS
+    evaluated (with the example's +-100 box the reference's log(prod pdf) prior underflows at d = 100 and nothing ever is: that run has
+    acceptance 1 for every step that is not a swap; ptmcmc_b200/workloads.py fullcov_spec)."""
+    import bench
+    w = bench.WORKLOADS["d_fullcov"]
+    spec = bench.make_spec(w)
+    d, R, L = w["dim"], w["rungs"], 192
+    cinv = spec.extra["cinv"].reshape(d, d)
+    C = np.linalg.inv(cinv)
+    e = engine_cls(spec.config(n_ladders=L, rng_mode=K.RNG_PHILOX, hist_capacity=w["hist"], save_every=w["save_every"], record_level=K.RECORD_BASIC))
+    spec.setup(e); e.init_from_prior(); e.step(w["burn_in"] + 4000); e.synchronize()
+    cnt = e.get_counters()
+    acc = (cnt["naccept"] / cnt["ntries"]).reshape(L, R)
+    assert 0.05 < acc[:, 0].mean() < 0.6          # a Metropolis sampler at work, not the accept-everything random walk
+    nout = 400                                     # 400 stored samples = 3200 iterations
+    x = np.empty((L, nout, d)); lp = np.empty((L, nout)); ll = np.empty((L, nout))
+    e.step_host(0, nout, x, lp, ll)
+    s = x[:, ::8, :].reshape(-1, d)
+    chi2 = np.einsum("ni,ij,nj->n", s, cinv, s)
+    print("config D cold chains: E[chi2] %.2f (target %d), acceptance %.3f, mean loglike %.2f (like0 - d/2 = %.2f)" %
+          (chi2.mean(), d, acc[:, 0].mean(), ll.mean(), spec.extra["like0"] - d / 2))
+    assert abs(chi2.mean() / d - 1) < 0.04
+    sd = np.sqrt(np.diag(C))
+    assert np.abs(s.mean(axis=0) / sd).max() < 0.12
+    assert np.abs(s.var(axis=0) / np.diag(C) - 1).max() < 0.15
+    assert np.allclose(ll, spec.extra["like0"] - 0.5 * np.einsum("lni,ij,lnj->ln", x, cinv, x), rtol=1e-10, atol=1e-8)
