@@ -245,15 +245,16 @@ __device__ __noinline__ FVec<D> ftransform(const double *__restrict__ M, FVec<D>
 // read with warp-uniform (broadcast) loads, 1/S_i is precomputed (ptg_api.cu).  The tape-capable kernels and the general instantiation
 // keep the reference's unfused arithmetic (like_eval_kind); these agree with it to ~1e-15 relative (1e-12 gate in the tests).
 //   polynomial (poly_example.cc:85-106): Horner's rule, D + 2 fp64 instructions per point
+// sum over the points [lo, hi) of (poly(x_i) - y_i)^2 / S_i
 template <int D>
-__device__ __forceinline__ double flike_poly_fused(const PtgModel &m, const double x[D]) {
+__device__ __forceinline__ double flike_poly_partial(const PtgModel &m, const double x[D], long long lo, long long hi) {
   const long long N = m.n_ldata / 3;
   const double *__restrict__ xs = m.ldata, *__restrict__ ys = m.ldata + N, *__restrict__ iS = m.ldata + 3 * N;
   // eight points per trip: all 24 loads are issued before the eight independent Horner chains start (a chain that runs alone on its
-  // scheduler -- config B puts one warp on each -- has nothing else to cover load and fp64 latency with)
+  // scheduler -- config B puts one or two warps on each -- has nothing else to cover load and fp64 latency with)
   double p4[4] = {0, 0, 0, 0};
-  long long i = 0;
-  for (; i + 8 <= N; i += 8) {
+  long long i = lo;
+  for (; i + 8 <= hi; i += 8) {
     double xi[8], yi[8], wi[8];
 #pragma unroll
     for (int u = 0; u < 8; u++) { xi[u] = __ldg(xs + i + u); yi[u] = __ldg(ys + i + u); wi[u] = __ldg(iS + i + u); }
@@ -268,7 +269,7 @@ __device__ __forceinline__ double flike_poly_fused(const PtgModel &m, const doub
 #pragma unroll
     for (int u = 0; u < 8; u++) { const double dd = y[u] - yi[u]; p4[u & 3] = fma(dd * dd, wi[u], p4[u & 3]); }
   }
-  for (; i < N; i++) {
+  for (; i < hi; i++) {
     const double xi = __ldg(xs + i);
     double y = x[D - 1];
 #pragma unroll
@@ -276,11 +277,41 @@ __device__ __forceinline__ double flike_poly_fused(const PtgModel &m, const doub
     const double dd = y - __ldg(ys + i);
     p4[0] = fma(dd * dd, __ldg(iS + i), p4[0]);
   }
-  double sum = ((p4[0] + p4[1]) + (p4[2] + p4[3])) + m.like_nsum;
+  return (p4[0] + p4[1]) + (p4[2] + p4[3]);
+}
+__device__ __forceinline__ double flike_chi2_finish(const PtgModel &m, double part) {
+  double sum = part + m.like_nsum;
   sum /= -2;
   double result = sum - __ldg(m.lparams);
   if (!isfinite(result)) result = -CUDART_INF;
   return result;
+}
+template <int D>
+__device__ __forceinline__ double flike_poly_fused(const PtgModel &m, const double x[D]) {
+  return flike_chi2_finish(m, flike_poly_partial<D>(m, x, 0, m.n_ldata / 3));
+}
+// The same sum with the data points of ONE chain split over the S = 32 / W0 lanes that a ladder of n_rungs <= W0 <= 16 leaves idle when it
+// is given a whole warp (the host launches the polynomial instantiation with W = 32): lane r + h W0 (h = 0 .. S-1; h >= 1 are ghost
+// lanes) evaluates slice h of the chain in lane r, the slices are added up in slice order.  BASELINE config B (1024 ladders x 16 rungs)
+// puts less than one warp on a scheduler with two ladders per warp; one ladder per warp doubles the warps and halves the longest
+// dependent stretch of every step.  The split depends on the ladder's size only, never on the batch size (a shard and the full batch
+// sum in the same order).  Called by all 32 lanes, converged.
+template <int D>
+__device__ __forceinline__ double flike_poly_split(const PtgModel &m, const double x[D], bool want, int W0) {
+  const int lane = threadIdx.x & 31;
+  const int S = 32 / W0, src = lane & (W0 - 1), slice = lane / W0;
+  double hx[D];
+#pragma unroll
+  for (int i = 0; i < D; i++) hx[i] = __shfl_sync(0xffffffffu, x[i], src);
+  const bool hwant = __shfl_sync(0xffffffffu, want ? 1 : 0, src) != 0;
+  const long long N = m.n_ldata / 3;
+  const long long chunk = (((N + S - 1) / S) + 7) & ~7LL;
+  const long long lo = slice * chunk < N ? slice * chunk : N, hi = (lo + chunk) < N ? (lo + chunk) : N;
+  double part = 0;
+  if (hwant) part = flike_poly_partial<D>(m, hx, lo, hi);
+  double tot = 0;
+  for (int h = 0; h < S; h++) tot += __shfl_sync(0xffffffffu, part, src + h * W0);
+  return flike_chi2_finish(m, tot);
 }
 //   sum of sinusoids y(t) = sum_k A_k sin(2 pi f_k t + phi_k): on a uniform time grid sin / cos of every component
 //   advance by one rotation per sample (4 fused multiply-adds) and are re-anchored with sincos of the reference's own phase expression
@@ -508,6 +539,8 @@ __global__ void __launch_bounds__(MAXT, 1) ptg_fstep_kernel(const __grid_constan
 #define hbase (s.hist + chain * ((long long)m.hist_cap * PTG_HX(D)))
 #define step ((uint64_t)(step0 + it))
   const double *bins = sbins + (rung < R ? rung : 0) * NP;
+  int poly_w0 = 32; // polynomial instantiation: lanes per ladder slot when the ladder has the warp to itself (W = 32): smallest power of two >= n_rungs
+  if (LK == PTG_LIKE_POLY_CHI2 && W == 32) { poly_w0 = 1; while (poly_w0 < R) poly_w0 <<= 1; }
 
   FChain<D> ch;
 #define st_di (cnt[FC_DI])
@@ -1027,7 +1060,12 @@ __global__ void __launch_bounds__(MAXT, 1) ptg_fstep_kernel(const __grid_constan
     // chain.cc:980.  A proposal outside the prior's support has newlprior = -inf and newlprior - oldlprior > dprior_min is false for every
     // finite oldlprior, so with an all-uniform prior (every current state inside the box) the second clause never opens the gate
     const bool gate = valid && ((newlprior > -1e200) || FS(newlprior - (cur_lpost - ch.beta * ch.llike) > m.dprior_min, false));
-    if (gate && do_mh) {
+    if constexpr (LK == PTG_LIKE_POLY_CHI2) {
+      // every lane takes part: the ghost lanes of a ladder that has a warp to itself evaluate slices of its chains' data sums
+      __syncwarp();
+      const double v = flike_poly_split<D>(m, newx, gate && do_mh, poly_w0);
+      if (gate && do_mh) { newlike = v; newlpost = newlike * ch.beta + newlprior; } else code |= PTG_TRACE_NOLIKE;
+    } else if (gate && do_mh) {
       if constexpr (LK == PTG_LIKE_SINES) newlike = flike_sines_staged<D>(spar, sines_pow2, m.lparams, newx);
       else newlike = flike<D, LK>(m, newx);
       newlpost = newlike * ch.beta + newlprior;

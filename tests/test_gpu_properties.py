@@ -457,3 +457,27 @@ def test_pipelined_fullcov_kernel_is_bit_identical(d, R, L, kw, engine_cls):
         e.close()
     for a, b in zip(*runs):
         assert a == b
+
+
+@pytest.mark.parametrize("R,d,n", [(16, 5, 1000), (8, 5, 1000), (5, 4, 203), (3, 2, 37), (24, 5, 500), (32, 3, 64), (1, 5, 100)])
+def test_split_polynomial_likelihood_matches_the_reference_arithmetic(R, d, n, engine_cls, oracle_cls):
+    """the production polynomial functor splits a chain's data sum over the lanes a short ladder leaves idle in its warp (2 slices at 9-16
+    rungs, 4 at 5-8, 8 at 3-4, ...; ragged slices, ghost rungs inside a slot group, ladders that fill the warp): every STORED log-likelihood
+    equals the reference's unfused arithmetic at the stored position to 1e-12, decisions agree with the unfused kernel's over a short run"""
+    spec = Spec("poly", d, R, centers=np.zeros(d), halfwidths=np.full(d, 10.0), prop="de", Tmax=1e6, de_ni=12, extra=poly_data(n=n, d=d))
+    L = 37
+    mk = lambda: engine_cls(spec.config(n_ladders=L, rng_mode=K.RNG_PHILOX, hist_capacity=spec.de_ni * d + 300, record_level=K.RECORD_BASIC, trace_steps=40))
+    e = mk(); spec.setup(e); e.init_from_prior(); e.step(120); e.synchronize()
+    o = oracle_cls(spec.config(n_ladders=1)); spec.setup(o)
+    cnt = e.get_counters()
+    for l, r in ((0, 0), (L // 2, R // 2), (L - 1, R - 1)):
+        nrec = int(cnt["nsize"][l * R + r])
+        h = e.get_history(l, r, nrec - 100, 100, full=False)
+        want = o.eval_loglike(h["x"])
+        fin = np.isfinite(want)
+        assert (np.isfinite(h["llike"]) == fin).all()
+        assert (np.abs(h["llike"][fin] - want[fin]) <= 1e-12 * np.abs(want[fin])).all()
+    # the unfused functor (pinned PTG_KERNEL_FAST, two ladders per warp where they fit) takes the same decisions over the first steps
+    f = mk(); f.select_kernel(K.KERNEL_FAST); spec.setup(f); f.init_from_prior(); f.step(120); f.synchronize()
+    ce, cf = e.get_trace(0, 40)[1], f.get_trace(0, 40)[1]
+    assert (ce == cf).mean() > 0.999
