@@ -290,34 +290,12 @@ template <int D>
 __device__ __forceinline__ double flike_poly_fused(const PtgModel &m, const double x[D]) {
   return flike_chi2_finish(m, flike_poly_partial<D>(m, x, 0, m.n_ldata / 3));
 }
-// The same sum with the data points of ONE chain split over the S = 32 / W0 lanes that a ladder of n_rungs <= W0 <= 16 leaves idle when it
-// is given a whole warp (the host launches the polynomial instantiation with W = 32): lane r + h W0 (h = 0 .. S-1; h >= 1 are ghost
-// lanes) evaluates slice h of the chain in lane r, the slices are added up in slice order.  BASELINE config B (1024 ladders x 16 rungs)
-// puts less than one warp on a scheduler with two ladders per warp; one ladder per warp doubles the warps and halves the longest
-// dependent stretch of every step.  The split depends on the ladder's size only, never on the batch size (a shard and the full batch
-// sum in the same order).  Called by all 32 lanes, converged.
-template <int D>
-__device__ __forceinline__ double flike_poly_split(const PtgModel &m, const double x[D], bool want, int W0) {
-  const int lane = threadIdx.x & 31;
-  const int S = 32 / W0, src = lane & (W0 - 1), slice = lane / W0;
-  double hx[D];
-#pragma unroll
-  for (int i = 0; i < D; i++) hx[i] = __shfl_sync(0xffffffffu, x[i], src);
-  const bool hwant = __shfl_sync(0xffffffffu, want ? 1 : 0, src) != 0;
-  const long long N = m.n_ldata / 3;
-  const long long chunk = (((N + S - 1) / S) + 7) & ~7LL;
-  const long long lo = slice * chunk < N ? slice * chunk : N, hi = (lo + chunk) < N ? (lo + chunk) : N;
-  double part = 0;
-  if (hwant) part = flike_poly_partial<D>(m, hx, lo, hi);
-  double tot = 0;
-  for (int h = 0; h < S; h++) tot += __shfl_sync(0xffffffffu, part, src + h * W0);
-  return flike_chi2_finish(m, tot);
-}
 //   sum of sinusoids y(t) = sum_k A_k sin(2 pi f_k t + phi_k): on a uniform time grid sin / cos of every component
 //   advance by one rotation per sample (4 fused multiply-adds) and are re-anchored with sincos of the reference's own phase expression
 //   every 128 samples (drift < 1e-13); an irregular grid evaluates sin at every sample
+// sum over the samples [lo, hi) (lo a multiple of 128 on a uniform grid: the re-anchoring blocks) of (y(t_i) - y_i)^2 / S_i
 template <int D>
-__device__ __forceinline__ double flike_sinusoid_fused(const PtgModel &m, const double x[D]) {
+__device__ __forceinline__ double flike_sinusoid_partial(const PtgModel &m, const double x[D], long long lo, long long hi) {
   constexpr int NS = D / 3;
   const long long N = m.n_ldata / 3;
   const double *__restrict__ xs = m.ldata, *__restrict__ ys = m.ldata + N, *__restrict__ iS = m.ldata + 3 * N;
@@ -326,12 +304,12 @@ __device__ __forceinline__ double flike_sinusoid_fused(const PtgModel &m, const 
     double sd[NS > 0 ? NS : 1], cd[NS > 0 ? NS : 1];
 #pragma unroll
     for (int k = 0; k < NS; k++) sincos(2 * PTG_PI * x[3 * k + 1] * m.like_dt, &sd[k], &cd[k]);
-    for (long long base = 0; base < N; base += 128) {
+    for (long long base = lo; base < hi; base += 128) {
       double sn[NS > 0 ? NS : 1], cs[NS > 0 ? NS : 1];
       const double tb = __ldg(xs + base);
 #pragma unroll
       for (int k = 0; k < NS; k++) sincos(2 * PTG_PI * x[3 * k + 1] * tb + x[3 * k + 2], &sn[k], &cs[k]);
-      const int nq = (int)((N - base) < 128 ? (N - base) : 128);
+      const int nq = (int)((hi - base) < 128 ? (hi - base) : 128);
 #pragma unroll 2
       for (int q = 0; q < nq; q++) {
         double y = 0;
@@ -348,7 +326,7 @@ __device__ __forceinline__ double flike_sinusoid_fused(const PtgModel &m, const 
       }
     }
   } else {
-    for (long long i = 0; i < N; i++) {
+    for (long long i = lo; i < hi; i++) {
       const double ti = __ldg(xs + i);
       double y = 0;
 #pragma unroll
@@ -357,11 +335,51 @@ __device__ __forceinline__ double flike_sinusoid_fused(const PtgModel &m, const 
       part = fma(dd * dd, __ldg(iS + i), part);
     }
   }
-  double sum = part + m.like_nsum;
-  sum /= -2;
-  double result = sum - __ldg(m.lparams);
-  if (!isfinite(result)) result = -CUDART_INF;
-  return result;
+  return part;
+}
+template <int D>
+__device__ __forceinline__ double flike_sinusoid_fused(const PtgModel &m, const double x[D]) {
+  return flike_chi2_finish(m, flike_sinusoid_partial<D>(m, x, 0, m.n_ldata / 3));
+}
+
+// The data sums of a WARP'S LADDER, compacted: of the 32 lanes only the chains whose proposal passed the prior gate evaluate a likelihood
+// (ncu: 15-17 of 32 lanes active in the data loops of configs B and C2), so the n wanting chains of the warp's ladder are given S = 32 / n
+// lanes each -- lane g S + h evaluates slice h of the g-th wanting chain's data (its proposal arrives by shuffle) and the slices are added
+// up in slice order.  The data-likelihood instantiations always run ONE ladder per warp (the host launches them with W = 32), so n and
+// with it the summation order depend on the ladder's own state only: a shard and the full batch still produce the same chains.
+// Slices are whole groups of 8 points (polynomial) / whole re-anchoring blocks of 128 samples (sinusoids on a uniform grid).
+// Called by all 32 lanes, converged; returns the log-likelihood to the wanting lanes.
+// (Measured and rejected: cutting every sum into K = max(8, 32 / n) slices dealt to the lanes 32 at a time, which also fills the warp when
+// 17 ... 31 chains want a likelihood -- config B 7.5e8 -> 1.9e8, C2 5.8e7 -> 4.2e7: short slices lose the eight-point software pipeline
+// and every pass pays the proposal shuffles and the recurrence set-up again.)
+template <int D, int LK>
+__device__ __forceinline__ double flike_data_compact(const PtgModel &m, const double x[D], bool want) {
+  const int lane = threadIdx.x & 31;
+  const unsigned mask = __ballot_sync(0xffffffffu, want);
+  const int n = __popc(mask);
+  if (n == 0) return 0.0;
+  const int S = 32 / n;
+  const int g = lane / S, h = lane - g * S;
+  const bool valid = g < n;
+  const int owner = valid ? (int)__fns(mask, 0, g + 1) : 0;
+  double hx[D];
+#pragma unroll
+  for (int i = 0; i < D; i++) hx[i] = __shfl_sync(0xffffffffu, x[i], owner);
+  const long long N = m.n_ldata / 3;
+  const long long unit = (LK == PTG_LIKE_SINUSOID_CHI2 && m.like_uniform_t) ? 128 : 8;
+  const long long nunit = (N + unit - 1) / unit, per = (nunit + S - 1) / S;
+  long long lo = (long long)h * per * unit, hi = lo + per * unit;
+  if (lo > N) lo = N;
+  if (hi > N) hi = N;
+  double part = 0;
+  if (valid) {
+    if constexpr (LK == PTG_LIKE_POLY_CHI2) part = flike_poly_partial<D>(m, hx, lo, hi);
+    else part = flike_sinusoid_partial<D>(m, hx, lo, hi);
+  }
+  const int r = __popc(mask & ((1u << lane) - 1u));
+  double tot = 0;
+  for (int k = 0; k < S; k++) tot += __shfl_sync(0xffffffffu, part, (r * S + k) & 31);
+  return flike_chi2_finish(m, tot);
 }
 
 // likelihood of the specialised instantiations: the one functor, no switch
@@ -539,8 +557,6 @@ __global__ void __launch_bounds__(MAXT, 1) ptg_fstep_kernel(const __grid_constan
 #define hbase (s.hist + chain * ((long long)m.hist_cap * PTG_HX(D)))
 #define step ((uint64_t)(step0 + it))
   const double *bins = sbins + (rung < R ? rung : 0) * NP;
-  int poly_w0 = 32; // polynomial instantiation: lanes per ladder slot when the ladder has the warp to itself (W = 32): smallest power of two >= n_rungs
-  if (LK == PTG_LIKE_POLY_CHI2 && W == 32) { poly_w0 = 1; while (poly_w0 < R) poly_w0 <<= 1; }
 
   FChain<D> ch;
 #define st_di (cnt[FC_DI])
@@ -1060,10 +1076,12 @@ __global__ void __launch_bounds__(MAXT, 1) ptg_fstep_kernel(const __grid_constan
     // chain.cc:980.  A proposal outside the prior's support has newlprior = -inf and newlprior - oldlprior > dprior_min is false for every
     // finite oldlprior, so with an all-uniform prior (every current state inside the box) the second clause never opens the gate
     const bool gate = valid && ((newlprior > -1e200) || FS(newlprior - (cur_lpost - ch.beta * ch.llike) > m.dprior_min, false));
-    if constexpr (LK == PTG_LIKE_POLY_CHI2) {
-      // every lane takes part: the ghost lanes of a ladder that has a warp to itself evaluate slices of its chains' data sums
+    if constexpr (LK == PTG_LIKE_POLY_CHI2 || LK == PTG_LIKE_SINUSOID_CHI2) {
+      // every lane takes part: the data sums of the chains that passed the gate are spread over all 32 lanes (one ladder per warp)
       __syncwarp();
-      const double v = flike_poly_split<D>(m, newx, gate && do_mh, poly_w0);
+      double v;
+      if (W == 32) v = flike_data_compact<D, LK>(m, newx, gate && do_mh);
+      else v = (gate && do_mh) ? flike<D, LK>(m, newx) : 0.0;                 // ladders share the warp (fused exchange launches): one lane per chain
       if (gate && do_mh) { newlike = v; newlpost = newlike * ch.beta + newlprior; } else code |= PTG_TRACE_NOLIKE;
     } else if (gate && do_mh) {
       if constexpr (LK == PTG_LIKE_SINES) newlike = flike_sines_staged<D>(spar, sines_pow2, m.lparams, newx);

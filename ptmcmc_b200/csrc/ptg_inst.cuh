@@ -54,9 +54,9 @@ static cudaError_t launch_fstep_k(const PtgModel &m, const PtgState &s, long lon
 }
 template <int D>
 static cudaError_t launch_fstep_t(const PtgModel &m, const PtgState &s, long long step0, int n_steps, int W, const PtgXchg &xc, int lk, cudaStream_t st) {
-  // polynomial data likelihood: one ladder per warp whatever its size; the lanes a short ladder leaves idle evaluate slices of its chains'
-  // data sums (ptg_fast.cuh: flike_poly_split).  A property of the workload, not of the batch size.
-  if (lk == PTG_LIKE_POLY_CHI2 && !xc.on) W = 32;
+  // data chi^2 likelihoods: one ladder per warp whatever its size; the data sums of the chains that passed the prior gate are spread over all
+  // 32 lanes (ptg_fast.cuh: flike_data_compact).  A property of the workload, not of the batch size.
+  if ((lk == PTG_LIKE_POLY_CHI2 || lk == PTG_LIKE_SINUSOID_CHI2) && !xc.on) W = 32;
   const long long warps = (m.n_ladders + (32 / W) - 1) / (32 / W);
   // CTA size: the largest of 28 / 14 / 4 warps that still puts a CTA on (nearly) every SM.  The kernel is compiled for 72
   // registers (launch bound 896 x 1), so 896 resident threads per SM in every geometry; one 28-warp CTA per SM measured

@@ -459,12 +459,17 @@ def test_pipelined_fullcov_kernel_is_bit_identical(d, R, L, kw, engine_cls):
         assert a == b
 
 
-@pytest.mark.parametrize("R,d,n", [(16, 5, 1000), (8, 5, 1000), (5, 4, 203), (3, 2, 37), (24, 5, 500), (32, 3, 64), (1, 5, 100)])
-def test_split_polynomial_likelihood_matches_the_reference_arithmetic(R, d, n, engine_cls, oracle_cls):
-    """the production polynomial functor splits a chain's data sum over the lanes a short ladder leaves idle in its warp (2 slices at 9-16
-    rungs, 4 at 5-8, 8 at 3-4, ...; ragged slices, ghost rungs inside a slot group, ladders that fill the warp): every STORED log-likelihood
-    equals the reference's unfused arithmetic at the stored position to 1e-12, decisions agree with the unfused kernel's over a short run"""
-    spec = Spec("poly", d, R, centers=np.zeros(d), halfwidths=np.full(d, 10.0), prop="de", Tmax=1e6, de_ni=12, extra=poly_data(n=n, d=d))
+@pytest.mark.parametrize("model,R,d,n", [("poly", 16, 5, 1000), ("poly", 8, 5, 1000), ("poly", 5, 4, 203), ("poly", 3, 2, 37), ("poly", 24, 5, 500),
+                                         ("poly", 32, 3, 64), ("poly", 1, 5, 100), ("sinusoid", 32, 9, 1000), ("sinusoid", 6, 9, 517), ("sinusoid", 16, 9, 130)])
+def test_compacted_data_likelihood_matches_the_reference_arithmetic(model, R, d, n, engine_cls, oracle_cls):
+    """the production data-chi^2 functors run one ladder per warp and spread the data sums of the chains that passed the prior gate over
+    all 32 lanes (32 / n lanes per chain, slices added in slice order; ragged slices, one to 32 wanting chains, ladders of 1 ... 32 rungs):
+    every STORED log-likelihood equals the reference's unfused arithmetic at the stored position to 1e-12, and the decisions agree with the
+    unfused one-lane-per-chain kernel's over the first steps"""
+    if model == "poly":
+        spec = Spec("poly", d, R, centers=np.zeros(d), halfwidths=np.full(d, 10.0), prop="de", Tmax=1e6, de_ni=12, extra=poly_data(n=n, d=d))
+    else:
+        spec = sinusoid_spec(R, n=n, dt=0.01, de_ni=12)
     L = 37
     mk = lambda: engine_cls(spec.config(n_ladders=L, rng_mode=K.RNG_PHILOX, hist_capacity=spec.de_ni * d + 300, record_level=K.RECORD_BASIC, trace_steps=40))
     e = mk(); spec.setup(e); e.init_from_prior(); e.step(120); e.synchronize()
@@ -477,7 +482,7 @@ def test_split_polynomial_likelihood_matches_the_reference_arithmetic(R, d, n, e
         fin = np.isfinite(want)
         assert (np.isfinite(h["llike"]) == fin).all()
         assert (np.abs(h["llike"][fin] - want[fin]) <= 1e-12 * np.abs(want[fin])).all()
-    # the unfused functor (pinned PTG_KERNEL_FAST, two ladders per warp where they fit) takes the same decisions over the first steps
+    # the unfused functor (pinned PTG_KERNEL_FAST, several ladders per warp where they fit) takes the same decisions over the first steps
     f = mk(); f.select_kernel(K.KERNEL_FAST); spec.setup(f); f.init_from_prior(); f.step(120); f.synchronize()
     ce, cf = e.get_trace(0, 40)[1], f.get_trace(0, 40)[1]
     assert (ce == cf).mean() > 0.999
