@@ -30,19 +30,27 @@
 #pragma once
 #include "ptg_wide_mma.cuh"
 
+// Warp-uniform scalars of one chain, parked in shared memory between the stages that use them: every lane of a chain's warp holds the same
+// values, and keeping all of them in registers across the whole iteration is what pushed the 80-register kernel into 160 B of spills.
+struct XPPark {
+  double lprior, map_lpost;
+  long long nhist, ntries, naccept;
+  int last_type, since_save;
+};
 struct XPShared {
   double *Ms, *Cs;            // [D][DS] each, resident matrices (row n of the matrix = output component n)
   double *bufA, *bufB;        // [RP + 2][DS]: OFF / NEWX rows ; T / Y rows.  Row RP of bufA = zeros (padding rows of an MMA tile), row RP of bufB = dump
   double *plo, *phi;          // [32 CPL] prior box edges (all-uniform prior)
   int *kindflag;              // [R]: 1 = row of the rotation (set in S1), 2 = row of the quadratic form (set in S3)
   int *gsig, *gaxis;          // [R]: rotated Gaussian proposals of this iteration: offset of the member's sigmas in prop_data, axis of a 1-D step or -1
+  XPPark *park;               // [R]
 };
 
 // Byte offsets of every shared-memory array from the start of dynamic shared memory, computed on the host and passed as a kernel parameter:
 // the addresses are then constant-bank offsets instead of integer arithmetic the compiler re-derives inside the loop under register pressure.
 struct XPLayout {
   int DS, RP;
-  int Ms, Cs, bufA, bufB, plo, phi, kindflag, gsig, gaxis;
+  int Ms, Cs, bufA, bufB, plo, phi, kindflag, gsig, gaxis, park;
   int sll, slpost, slprior, sbeta, n_lpost, n_beta, app_lpost, app_beta, sbins, scount, saccept, perm, napp, app_src, dir, ups, downs, inst;
 };
 static inline int ptg_xp_stride(int D) { int ds = (D + 7) & ~7; while ((ds & 15) != 8) ds += 8; return ds; }
@@ -51,6 +59,8 @@ static inline size_t ptg_xp_shared_bytes(int R, int D, int NP, int CPL) {
   size_t b = ptg_xshared_bytes(R, 0, NP);                                   // the ladder scalars / swap outcome block of XShared (no row buffers)
   b += sizeof(double) * ((size_t)2 * D * DS + (size_t)2 * (RP + 2) * DS + 2 * (size_t)32 * CPL);
   b += sizeof(int) * ((size_t)3 * R + 8);
+  b = (b + 15) & ~(size_t)15;
+  b += sizeof(XPPark) * (size_t)R;
   return (b + 15) & ~(size_t)15;
 }
 
@@ -67,7 +77,8 @@ static inline XPLayout ptg_xp_layout(int R, int D, int NP, int CPL) {
   y.Ms = b; b += 8 * D * y.DS; y.Cs = b; b += 8 * D * y.DS;
   y.bufA = b; b += 8 * (y.RP + 2) * y.DS; y.bufB = b; b += 8 * (y.RP + 2) * y.DS;
   y.plo = b; b += 8 * 32 * CPL; y.phi = b; b += 8 * 32 * CPL;
-  y.kindflag = b; b += 4 * R; y.gsig = b; b += 4 * R; y.gaxis = b;
+  y.kindflag = b; b += 4 * R; y.gsig = b; b += 4 * R; y.gaxis = b; b += 4 * R;
+  b = (b + 15) & ~15; y.park = b;
   return y;
 }
 
@@ -129,7 +140,7 @@ __global__ void __launch_bounds__(MAXT) ptg_xpstep_kernel(const __grid_constant_
   XPShared P;
   P.Ms = XP_SM(double, Ms); P.Cs = XP_SM(double, Cs); P.bufA = XP_SM(double, bufA); P.bufB = XP_SM(double, bufB);
   P.plo = XP_SM(double, plo); P.phi = XP_SM(double, phi); P.kindflag = XP_SM(int, kindflag);
-  P.gsig = XP_SM(int, gsig); P.gaxis = XP_SM(int, gaxis);
+  P.gsig = XP_SM(int, gsig); P.gaxis = XP_SM(int, gaxis); P.park = XP_SM(XPPark, park);
 #undef XP_SM
   const int DS = lay.DS, RP = lay.RP;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -171,6 +182,13 @@ __global__ void __launch_bounds__(MAXT) ptg_xpstep_kernel(const __grid_constant_
       L.scount[rung] = 0; L.saccept[rung] = 0;
     }
   }
+  XPPark *const PK = P.park + rung;
+  // park: lane 0 writes the warp-uniform scalars the next stages do not need; unpark: every lane reads them back (broadcast)
+#define XP_PARK() do { if (lane == 0) { PK->lprior = ch.lprior; PK->map_lpost = ch.map_lpost; PK->nhist = ch.nhist; PK->ntries = ch.ntries; PK->naccept = ch.naccept; \
+                                        PK->last_type = ch.last_type; PK->since_save = ch.since_save; } __syncwarp(); } while (0)
+#define XP_UNPARK() do { ch.lprior = PK->lprior; ch.map_lpost = PK->map_lpost; ch.nhist = PK->nhist; ch.ntries = PK->ntries; ch.naccept = PK->naccept; \
+                         ch.last_type = PK->last_type; ch.since_save = PK->since_save; } while (0)
+  XP_PARK();
   const int maxswaps = m.maxswaps;
   const double swap_thresh = (R - 1) * m.swap_rate / maxswaps;
   double ptry = 2 * m.swap_rate; if (ptry > 1) ptry = 1;
@@ -193,7 +211,7 @@ __global__ void __launch_bounds__(MAXT) ptg_xpstep_kernel(const __grid_constant_
 #pragma unroll
       for (int k = 0; k < CPL; k++) myscratch[CPL * lane + k] = ch.x[k];      // states of swapped rungs travel through this row
       if (lane == 0) {
-        L.sll[rung] = ch.llike; L.slpost[rung] = ch.lpost; L.slprior[rung] = ch.lprior; L.sbeta[rung] = ch.beta;
+        L.sll[rung] = ch.llike; L.slpost[rung] = ch.lpost; L.slprior[rung] = PK->lprior; L.sbeta[rung] = ch.beta;
         L.n_lpost[rung] = ch.lpost; L.n_beta[rung] = ch.beta; L.perm[rung] = rung; L.napp[rung] = 0;
       }
       rs.step = step;
@@ -217,6 +235,7 @@ __global__ void __launch_bounds__(MAXT) ptg_xpstep_kernel(const __grid_constant_
       const PtgProp &p = m.props[member];
       kind = p.kind;
       if (kind == PTG_PROP_DE) {
+        ch.map_lpost = PK->map_lpost;              // the unlikely_alpha test of the history draw reads it (proposal_distribution.cc:766)
         const double usnk = ptg_u32_to_unit(wA[1]), ug = ptg_u32_to_unit(wA[2]);
         snooker = p.snooker > usnk;
         int a1 = 0, a2 = 0;
@@ -308,6 +327,7 @@ __global__ void __launch_bounds__(MAXT) ptg_xpstep_kernel(const __grid_constant_
     for (int k = 0; k < CPL; k++) newx[k] = ch.x[k];
     if (!mh) {
       // xswapped_rung with the published states in the global scratch rows
+      XP_UNPARK();
       for (int k = 0; k < 2 && k < na; k++) {
         const int src = L.app_src[2 * rung + k];
         double xs[CPL];
@@ -319,6 +339,7 @@ __global__ void __launch_bounds__(MAXT) ptg_xpstep_kernel(const __grid_constant_
 #pragma unroll
       for (int q = 0; q < CPL; q++) ch.x[q] = ladscratch[(size_t)src * (32 * CPL) + CPL * lane + q];
       ch.llike = L.sll[src]; ch.lprior = L.slprior[src]; ch.lpost = L.n_lpost[rung];
+      XP_PARK();
     } else if (m.evolve_rate > 0) ch.lpost = L.n_lpost[rung];
     const double oldlprior = ch.lpost - ch.beta * ch.llike;
     bool valid = m.zero_valid != 0, gate = false;
@@ -342,6 +363,7 @@ __global__ void __launch_bounds__(MAXT) ptg_xpstep_kernel(const __grid_constant_
             for (int k = 0; k < CPL; k++) { minusz[k] = zz[k] * (-1); smz[k] = ch.x[k] + minusz[k]; t[k] = smz[k] * smz[k]; }
             smznorm2 = xsum_tree<CPL>(t);
             if (++isafe > 1000 || smznorm2 != 0) break;
+            ch.map_lpost = PK->map_lpost;
             iz = xde_index<CPL, MODE>(m, s, ch, p, rs, wB[1], 0, hsize, az);
           }
           double a[CPL], b[CPL];
@@ -399,6 +421,7 @@ __global__ void __launch_bounds__(MAXT) ptg_xpstep_kernel(const __grid_constant_
     if (mh) {
       code = 0;
       bool accept = true;
+      XP_UNPARK();
       if (gate) newlpost = newlike * ch.beta + newlprior; else code |= PTG_TRACE_NOLIKE;
       lhr = prop_lh;
       if (isnan(lhr)) accept = false;
@@ -416,6 +439,7 @@ __global__ void __launch_bounds__(MAXT) ptg_xpstep_kernel(const __grid_constant_
       }
       xappend<CPL>(m, s, ch, ch.x, ch.llike, ch.lpost, ch.beta, lane);
       code |= (type & PTG_TRACE_TYPE_MASK);
+      XP_PARK();
     }
     if (lane == 0 && (long long)step < m.trace_steps) {
       s.trace_lhr[step * m.n_chains + chain] = lhr;
@@ -423,6 +447,9 @@ __global__ void __launch_bounds__(MAXT) ptg_xpstep_kernel(const __grid_constant_
     }
   }
   __syncthreads();
+  XP_UNPARK();
+#undef XP_PARK
+#undef XP_UNPARK
 #pragma unroll
   for (int k = 0; k < CPL; k++) { const int c = CPL * lane + k; if (c < D) s.cur_x[(long long)c * m.n_chains + chain] = ch.x[k]; }
   if (lane == 0) {
