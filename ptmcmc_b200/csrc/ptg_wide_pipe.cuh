@@ -199,13 +199,10 @@ __global__ void __launch_bounds__(MAXT) ptg_xpstep_kernel(const __grid_constant_
   for (int it = 0; it < n_steps; it++) {
     const uint64_t step = (uint64_t)(step0 + it);
     // ================================================================ S1: publish + everything that does not depend on the swap outcome
-    double off[CPL];
     int type = 0, member = 0, kind = 0, i1 = 0, i2 = 0, iz = 0, az = 0;
     bool snooker = false, need_t = false;
     double gamma = 0;
     uint32_t wB[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-    for (int k = 0; k < CPL; k++) off[k] = 0;
     int hsize = 0;
     {
 #pragma unroll
@@ -262,6 +259,7 @@ __global__ void __launch_bounds__(MAXT) ptg_xpstep_kernel(const __grid_constant_
           // lane, below) instead of 50 pairs by this warp while the differential-evolution warps wait
           if (lane == 0) { P.gsig[rung] = p.sigma_off; P.gaxis[rung] = ia; }
         } else {
+          double off[CPL];
           xnormals<CPL, MODE>(m, rs, off, lane);
           const double *__restrict__ sig = m.prop_data + p.sigma_off;
 #pragma unroll
@@ -273,7 +271,13 @@ __global__ void __launch_bounds__(MAXT) ptg_xpstep_kernel(const __grid_constant_
           if (need_t) {
 #pragma unroll
             for (int k = 0; k < CPL; k++) { const int c = CPL * lane + k; if (c < D) rowA[c] = off[k]; }
-          } else if (p.has_transform) xtransform<CPL>(m, m.prop_data + p.trans_off, off, rowB, lane);   // a second, different matrix: exact per-warp path
+          } else {
+            if (p.has_transform) xtransform<CPL>(m, m.prop_data + p.trans_off, off, rowB, lane);   // a second, different matrix: exact per-warp path
+            // an offset that needs no batched rotation waits in the chain's own T row (the rotation writes only rows of rotated proposals)
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < CPL; k++) { const int c = CPL * lane + k; if (c < D) rowB[c] = off[k]; }
+          }
         }
       }
       if (lane == 0) P.kindflag[rung] = need_t ? 1 : 0;
@@ -321,6 +325,7 @@ __global__ void __launch_bounds__(MAXT) ptg_xpstep_kernel(const __grid_constant_
     const int na = L.napp[rung];
     ch.beta = L.n_beta[rung];
     const bool mh = (na == 0);
+    ch.llike = L.sll[rung]; ch.lpost = L.n_lpost[rung];   // an MH rung's own published values (pried if the ladder evolves); swapped rungs overwrite them below
     double newx[CPL];
     double prop_lh = 0;
 #pragma unroll
@@ -340,7 +345,7 @@ __global__ void __launch_bounds__(MAXT) ptg_xpstep_kernel(const __grid_constant_
       for (int q = 0; q < CPL; q++) ch.x[q] = ladscratch[(size_t)src * (32 * CPL) + CPL * lane + q];
       ch.llike = L.sll[src]; ch.lprior = L.slprior[src]; ch.lpost = L.n_lpost[rung];
       XP_PARK();
-    } else if (m.evolve_rate > 0) ch.lpost = L.n_lpost[rung];
+    }
     const double oldlprior = ch.lpost - ch.beta * ch.llike;
     bool valid = m.zero_valid != 0, gate = false;
     double newlprior = -CUDART_INF;
@@ -378,12 +383,11 @@ __global__ void __launch_bounds__(MAXT) ptg_xpstep_kernel(const __grid_constant_
           type = 1;
         }
       } else if (kind == PTG_PROP_GAUSS) {
-        if (need_t) {
+        double offs[CPL];
 #pragma unroll
-          for (int k = 0; k < CPL; k++) { const int c = CPL * lane + k; off[k] = (c < D) ? rowB[c] : 0.0; }
-        }
+        for (int k = 0; k < CPL; k++) { const int c = CPL * lane + k; offs[k] = (c < D) ? rowB[c] : 0.0; }
 #pragma unroll
-        for (int k = 0; k < CPL; k++) newx[k] = ch.x[k] + off[k];
+        for (int k = 0; k < CPL; k++) newx[k] = ch.x[k] + offs[k];
       }
       if (m.wrap_in_set) type = member + 10 * type;
       if (valid) valid = xenforce<CPL>(m, newx, lane);
