@@ -352,16 +352,15 @@ __device__ __forceinline__ double flike_sinusoid_fused(const PtgModel &m, const 
 // (Measured and rejected: cutting every sum into K = max(8, 32 / n) slices dealt to the lanes 32 at a time, which also fills the warp when
 // 17 ... 31 chains want a likelihood -- config B 7.5e8 -> 1.9e8, C2 5.8e7 -> 4.2e7: short slices lose the eight-point software pipeline
 // and every pass pays the proposal shuffles and the recurrence set-up again.)
+// One pass of the compacted data sums: the wanting chains of rank [c0, c0 + nc) get S = 32 / nc lanes each.  Returns the chain's data sum
+// to the wanting lanes of those ranks (garbage elsewhere).  Called by all 32 lanes, converged.
 template <int D, int LK>
-__device__ __forceinline__ double flike_data_compact(const PtgModel &m, const double x[D], bool want) {
+__device__ __forceinline__ double flike_data_pass(const PtgModel &m, const double x[D], unsigned mask, int r, int c0, int nc) {
   const int lane = threadIdx.x & 31;
-  const unsigned mask = __ballot_sync(0xffffffffu, want);
-  const int n = __popc(mask);
-  if (n == 0) return 0.0;
-  const int S = 32 / n;
+  const int S = 32 / nc;
   const int g = lane / S, h = lane - g * S;
-  const bool valid = g < n;
-  const int owner = valid ? (int)__fns(mask, 0, g + 1) : 0;
+  const bool valid = g < nc;
+  const int owner = valid ? (int)__fns(mask, 0, c0 + g + 1) : 0;
   double hx[D];
 #pragma unroll
   for (int i = 0; i < D; i++) hx[i] = __shfl_sync(0xffffffffu, x[i], owner);
@@ -376,9 +375,31 @@ __device__ __forceinline__ double flike_data_compact(const PtgModel &m, const do
     if constexpr (LK == PTG_LIKE_POLY_CHI2) part = flike_poly_partial<D>(m, hx, lo, hi);
     else part = flike_sinusoid_partial<D>(m, hx, lo, hi);
   }
-  const int r = __popc(mask & ((1u << lane) - 1u));
   double tot = 0;
-  for (int k = 0; k < S; k++) tot += __shfl_sync(0xffffffffu, part, (r * S + k) & 31);
+  for (int k = 0; k < S; k++) tot += __shfl_sync(0xffffffffu, part, ((r - c0) * S + k) & 31);
+  return tot;
+}
+// 17 ... 26 wanting chains would leave every chain ONE lane and 6 ... 15 lanes idle (config C2: 32 rungs, 17-20 proposals pass the gate
+// most of the time).  They go in TWO passes instead: the first 16 chains with two lanes each, the other 1 ... 10 with 32 / (n - 16) >= 3
+// lanes each -- N / 2 + N / (32 / (n - 16)) samples per lane instead of N.  Above 26 the second pass would not be shorter than half the
+// data and the single pass stays.  The split depends on n alone, like the slice width.
+template <int D, int LK>
+__device__ __forceinline__ double flike_data_compact(const PtgModel &m, const double x[D], bool want) {
+  const int lane = threadIdx.x & 31;
+  const unsigned mask = __ballot_sync(0xffffffffu, want);
+  const int n = __popc(mask);
+  if (n == 0) return 0.0;
+  const int r = __popc(mask & ((1u << lane) - 1u));
+  const bool two = n > 16 && n <= 26;
+  double tot = 0;
+  int c0 = 0;
+#pragma unroll 1
+  for (int pass = 0; pass < (two ? 2 : 1); pass++) {   // one body for both passes (three inlined copies spilled)
+    const int nc = two ? (pass == 0 ? 16 : n - 16) : n;
+    const double t = flike_data_pass<D, LK>(m, x, mask, r, c0, nc);
+    if (r >= c0 && r < c0 + nc) tot = t;
+    c0 += nc;
+  }
   return flike_chi2_finish(m, tot);
 }
 
