@@ -310,13 +310,23 @@ __device__ __forceinline__ double flike_sinusoid_partial(const PtgModel &m, cons
 #pragma unroll
       for (int k = 0; k < NS; k++) sincos(2 * PTG_PI * x[3 * k + 1] * tb + x[3 * k + 2], &sn[k], &cs[k]);
       const int nq = (int)((hi - base) < 128 ? (hi - base) : 128);
+      // y_i and 1 / S_i are loaded TWO samples ahead of their use (ncu: the subtraction behind the y_i load held 24 % of all stall
+      // samples -- L1-hit latency that 3.5 warps per scheduler cannot cover); the index is clamped to the slice, so no branch
+      const double *__restrict__ yblk = ys + base, *__restrict__ wblk = iS + base;
+      const int lim = nq - 1;                      // the block's last sample
+      double ya = __ldg(yblk), wa = __ldg(wblk);
+      double yb = __ldg(yblk + (1 < lim ? 1 : lim)), wb = __ldg(wblk + (1 < lim ? 1 : lim));
 #pragma unroll 2
       for (int q = 0; q < nq; q++) {
+        const double yq = ya, wq = wa;
+        ya = yb; wa = wb;
+        const int qn = q + 2 < lim ? q + 2 : lim;
+        yb = __ldg(yblk + qn); wb = __ldg(wblk + qn);
         double y = 0;
 #pragma unroll
         for (int k = 0; k < NS; k++) y = fma(x[3 * k], sn[k], y);
-        const double dd = y - __ldg(ys + base + q);
-        part = fma(dd * dd, __ldg(iS + base + q), part);
+        const double dd = y - yq;
+        part = fma(dd * dd, wq, part);
 #pragma unroll
         for (int k = 0; k < NS; k++) {
           const double ns = fma(sn[k], cd[k], cs[k] * sd[k]);
