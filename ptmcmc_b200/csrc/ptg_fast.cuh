@@ -389,10 +389,11 @@ __device__ __forceinline__ double flike_data_pass(const PtgModel &m, const doubl
   for (int k = 0; k < S; k++) tot += __shfl_sync(0xffffffffu, part, ((r - c0) * S + k) & 31);
   return tot;
 }
-// 17 ... 26 wanting chains would leave every chain ONE lane and 6 ... 15 lanes idle (config C2: 32 rungs, 17-20 proposals pass the gate
-// most of the time).  They go in TWO passes instead: the first 16 chains with two lanes each, the other 1 ... 10 with 32 / (n - 16) >= 3
-// lanes each -- N / 2 + N / (32 / (n - 16)) samples per lane instead of N.  Above 26 the second pass would not be shorter than half the
-// data and the single pass stays.  The split depends on n alone, like the slice width.
+// One pass gives each of the n wanting chains 32 / n lanes (integer division): 11 ... 15 chains get two lanes and leave up to 10 idle, 17 ... 31
+// get ONE lane each (config C2: 32 rungs, 17-20 proposals pass the gate most of the time).  TWO passes can do better: the first a chains
+// (a a power of two) on 32 / a lanes each, the other n - a on 32 / (n - a) lanes each -- e.g. 18 chains: N / 2 + N / 16 samples per lane
+// instead of N; 11 chains: N / 4 + N / 10 instead of N / 2.  The split with the fewest slice units per lane is taken when it saves at least a
+// tenth (a pass repeats the proposal shuffles and the recurrence set-up); it depends on n and the data size alone, like the slice width.
 template <int D, int LK>
 __device__ __forceinline__ double flike_data_compact(const PtgModel &m, const double x[D], bool want) {
   const int lane = threadIdx.x & 31;
@@ -400,12 +401,28 @@ __device__ __forceinline__ double flike_data_compact(const PtgModel &m, const do
   const int n = __popc(mask);
   if (n == 0) return 0.0;
   const int r = __popc(mask & ((1u << lane) - 1u));
-  const bool two = n > 16 && n <= 26;
+  const long long N = m.n_ldata / 3;
+  const int unit = (LK == PTG_LIKE_SINUSOID_CHI2 && m.like_uniform_t) ? 128 : 8;
+  const int nunit = (int)((N + unit - 1) / unit);
+  auto per = [&](int nc) { const int S = 32 / nc; return (nunit + S - 1) / S; };   // slice units per lane of a pass over nc chains
+  int first = n, best = per(n);
+  const int single = best;
+  // sinusoids only: the polynomial's short dependent stretch per point makes a second pass cost more than the idle lanes (config B,
+  // 1024 warps on 592 schedulers: 7.1e8 -> 4.2e8 chain-steps/s with the split, measured)
+  if constexpr (LK == PTG_LIKE_SINUSOID_CHI2) {
+#pragma unroll
+    for (int a = 16; a >= 1; a >>= 1) {
+      if (a < n) {
+        const int c = per(a) + per(n - a);
+        if (c < best && 10 * c <= 9 * single) { best = c; first = a; }
+      }
+    }
+  }
   double tot = 0;
   int c0 = 0;
 #pragma unroll 1
-  for (int pass = 0; pass < (two ? 2 : 1); pass++) {   // one body for both passes (three inlined copies spilled)
-    const int nc = two ? (pass == 0 ? 16 : n - 16) : n;
+  for (int pass = 0; pass < (first < n ? 2 : 1); pass++) {   // one body for both passes (separate inlined copies spilled)
+    const int nc = (pass == 0) ? first : n - first;
     const double t = flike_data_pass<D, LK>(m, x, mask, r, c0, nc);
     if (r >= c0 && r < c0 + nc) tot = t;
     c0 += nc;
