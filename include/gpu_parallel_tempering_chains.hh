@@ -144,6 +144,12 @@ class gpu_parallel_tempering_chains : public parallel_tempering_chains {
     if (nest_count) check(ptg_set_nested_set(h, nest_first, nest_count, nest_share, nest_hot, nest_adapt), "set_nested_set");
   }
 
+  /// reboot of stuck hot replicas (do_reboot, chain.hh:308; chain.cc:1689-1759) swaps whole MH_chain objects -- histories, generators and
+  /// counters -- between rungs; the engine's per-rung rings have no device form of that, so a run that asks for it stops here
+  void refuse_reboot() const {
+    if (max_reboot_rate > 0) { std::cout << "gpu_parallel_tempering_chains: reboot of hot replicas (pt_reboot_rate > 0) has no device form" << std::endl; exit(1); }
+  }
+
 public:
   /// same arguments as parallel_tempering_chains (chain.cc:1163-1211) + the engine's ring capacity per rung and the mirror cadence
   gpu_parallel_tempering_chains(int Ntemps, double Tmax, double swap_rate = 0.01, int add_every_N = 1, bool do_evid = false, bool verbose_evid = true,
@@ -186,6 +192,7 @@ public:
   }
   /// one PT iteration on the device (replaces chain.cc:1393-1761)
   void step() override {
+    refuse_reboot();
     check(ptg_step(h, 1), "step");
     nsteps++;
     // the run loop dumps after step k * Nevery + 1 (ptmcmc.cc:599-601: `cc->step(); if (0 == istep % Nevery) dump`): mirror on that cadence
@@ -196,6 +203,7 @@ public:
   std::string status() override { sync(); return parallel_tempering_chains::status(); }
   /// n iterations in one launch (what a run loop aware of the engine calls between dumps)
   void step_many(long long n) {
+    refuse_reboot();
     check(ptg_step(h, n), "step");
     nsteps += n;
     sync();
